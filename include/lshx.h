@@ -1,0 +1,205 @@
+/*
+ * lshx.h -- C ABI of liblshx.so: the B200 (sm_100a) hot path of lshrs.
+ *
+ * The reference (mxngjxa/lshrs, pure Python) has no FFI; its "operator
+ * interface" for this path is the Python surface
+ *     LSHHasher.__init__ / hash_vector / hash_batch / _project_and_pack
+ *         (reference lshrs/hash/lsh.py:51-94, 96-134, 136-169, 171-211)
+ *     l2_norm / cosine_similarity / top_k_cosine
+ *         (reference lshrs/utils/norm.py:4-61, lshrs/utils/similarity.py:26-90, 93-183)
+ * and the call sites LSHRS.ingest / index / query
+ *         (reference lshrs/core/main.py:386-411, 442-518, 524-658).
+ * Each entry point below names the reference lines it replaces.  A maintainer
+ * binds it with ctypes (INTEGRATION.md shows the stub); lshrs_b200/_native.py
+ * is that binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative lshx_status otherwise;
+ *     lshx_last_error() returns a thread-local message for the last failure.
+ *   - all matrices are row-major, contiguous, float32; signatures are uint8 in
+ *     exactly the reference's byte order (np.packbits(bitorder="little") per
+ *     band, bands concatenated: uint8[n][num_bands][ceil(rows_per_band/8)]).
+ *   - the caller owns every buffer it passes; the library owns only what hangs
+ *     off the opaque handles and frees it in *_destroy.  Nothing is retained
+ *     across calls.
+ *   - a handle is bound to one CUDA device.  Calls on one handle are
+ *     serialised by an internal mutex (the reference hasher is called from
+ *     many Python threads, tests/test_concurrency.py:31-42); use one handle
+ *     per GPU for multi-GPU sharding.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own
+ *     stream).  Calls taking HOST buffers are synchronous; calls whose buffers
+ *     are all DEVICE pointers only enqueue work on `stream`.
+ *   - there is NO CPU fallback: without a usable sm_100 device *_create fails.
+ */
+#ifndef LSHX_H_
+#define LSHX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSHX_ABI_VERSION 1
+
+typedef enum lshx_status {
+  LSHX_OK = 0,
+  LSHX_ERR_INVALID_ARG = -1, /* bad size / null pointer / unsupported shape        */
+  LSHX_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed                  */
+  LSHX_ERR_NO_DEVICE = -3,   /* no CUDA device, or not compute capability 10.x       */
+  LSHX_ERR_OOM = -4,         /* device or pinned-host allocation failed              */
+  LSHX_ERR_ZERO_VECTOR = -5  /* rerank: a zero-norm query or candidate (l2_norm)     */
+} lshx_status;
+
+/* Which projection kernel lshx_hash_batch launches. */
+typedef enum lshx_hash_kernel {
+  LSHX_KERNEL_AUTO = 0,    /* tcgen05 when the shape allows it, else FFMA            */
+  LSHX_KERNEL_FFMA = 1,    /* FP32 FFMA register-tiled kernel                        */
+  LSHX_KERNEL_TCGEN05 = 2  /* tcgen05 3xTF32 split, TMA-staged, TMEM accumulators    */
+} lshx_hash_kernel;
+
+typedef struct lshx_hasher lshx_hasher;   /* opaque */
+typedef struct lshx_reranker lshx_reranker; /* opaque */
+
+/* ---- library ---------------------------------------------------------- */
+
+int lshx_abi_version(void);
+/* Thread-local text of the last error raised on this thread ("" if none). */
+const char* lshx_last_error(void);
+/* Number of visible CUDA devices with compute capability 10.x (0 if none). */
+int lshx_device_count(void);
+/* Kernels launched by this library in this process since load (all handles). */
+uint64_t lshx_launch_count(void);
+
+/* ---- hasher: replaces LSHHasher (reference lshrs/hash/lsh.py) ---------- */
+
+/*
+ * Replaces the device-side half of LSHHasher.__init__ (lsh.py:51-94).  The
+ * projection matrices are still drawn on the host with numpy's PCG64 stream
+ * (lsh.py:93-94) and passed here as ONE row-major float32 matrix
+ * R[num_bands*rows_per_band][dim] (band b = rows [b*r, (b+1)*r)).
+ * Fails with LSHX_ERR_INVALID_ARG for non-positive sizes (lsh.py:78-83).
+ */
+int lshx_hasher_create(int device, int dim, int num_bands, int rows_per_band,
+                       const float* projections_host, lshx_hasher** out);
+
+/*
+ * Re-upload the projections.  Replaces the attribute rebinding
+ * `hasher.projections = [...]` done by LSHRS.load_from_disk / __setstate__
+ * (reference lshrs/core/main.py:981, 1044).
+ */
+int lshx_hasher_set_projections(lshx_hasher* h, const float* projections_host);
+
+/* Select the projection kernel (default LSHX_KERNEL_AUTO). */
+int lshx_hasher_set_kernel(lshx_hasher* h, int kernel /* lshx_hash_kernel */);
+/* The kernel the last lshx_hash_batch on this handle actually launched. */
+int lshx_hasher_last_kernel(const lshx_hasher* h);
+
+/* Bytes of signature per vector: num_bands * ceil(rows_per_band / 8). */
+int lshx_hasher_signature_bytes(const lshx_hasher* h);
+
+/*
+ * Replaces LSHHasher.hash_batch / hash_vector / _project_and_pack
+ * (lsh.py:136-169, 96-134, 171-211): for each of the n rows of X,
+ *     bit(b, j) = (R[b*r + j] . x) > 0          strict; 0 and NaN give 0
+ * packed little-endian per band into out[n][num_bands][ceil(r/8)].
+ *
+ *   X            n x dim float32, host (x_is_device = 0) or device pointer
+ *   out          n x signature_bytes uint8, host or device pointer
+ *   zero_flag    optional (may be NULL) n bytes, same memory space as `out`:
+ *                1 where every |x_i| <= 1e-8 -- the np.allclose(arr, 0,
+ *                atol=1e-8) test of LSHRS._prepare_vector (main.py:1083)
+ *                fused into the same pass; NaN elements give 0 like numpy.
+ *   stream       cudaStream_t or NULL.
+ * n == 0 is a no-op.  Host buffers are staged through handle-owned device
+ * buffers in chunks (H2D, kernel, D2H overlapped on two streams); pinned host
+ * memory makes those copies asynchronous.
+ */
+int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_is_device,
+                    uint8_t* out, int out_is_device, uint8_t* zero_flag, void* stream);
+
+/*
+ * Lower-case hex of the band bytes, the variable part of
+ * RedisStorage.bucket_key (reference lshrs/storage/redis.py:225:
+ * f"{prefix}:{band_id}:bucket:{hash_val.hex()}").  Host helper:
+ * sig[n][sig_bytes] -> hex[n][2*sig_bytes] ASCII (no terminator).
+ */
+int lshx_signatures_to_hex(const uint8_t* sig, int64_t n, int sig_bytes, char* hex_out);
+
+int lshx_hasher_destroy(lshx_hasher* h);
+
+/* ---- reranker: replaces top_k_cosine (reference lshrs/utils/similarity.py) */
+
+/* Per-device workspace for rerank calls on vectors of length `dim`. */
+int lshx_rerank_create(int device, int dim, lshx_reranker** out);
+
+/*
+ * Replaces cosine_similarity + top_k_cosine (similarity.py:80-90, 157-183) and
+ * the rank-fraction cut of LSHRS.query (reference lshrs/core/main.py:646-658)
+ * for a batch of nq queries.
+ *
+ *   Q             nq x dim float32 queries
+ *   vectors       float32 rows of length dim that candidates are taken from
+ *   cand_offsets  nq+1 int64; query i owns candidate slots
+ *                 [cand_offsets[i], cand_offsets[i+1])
+ *   cand_ids      optional int64 per slot: row of `vectors` holding that
+ *                 candidate (gather mode, corpus resident in HBM).  NULL means
+ *                 slot s IS row s of `vectors` (packed candidates, what
+ *                 top_k_cosine(query, candidates) receives).
+ *   n_vectors     rows in `vectors` (ids are range-checked against it; an
+ *                 out-of-range id scores NaN, ranks last and is counted in
+ *                 out_zero)
+ *   max_candidates  largest per-query candidate count; only read when
+ *                 on_device == 1 (the offsets are not host-readable then),
+ *                 otherwise computed from cand_offsets
+ *   k             > 0: keep the k best per query (k >= n_i keeps all n_i)
+ *                 <= 0: use p
+ *   p             in (0, 1] when k <= 0: keep max(1, ceil(n_i * p)), evaluated
+ *                 in double like Python's math.ceil(len * top_p)
+ *                 (main.py:650); when k > 0 and p > 0 both apply:
+ *                 min(k, max(1, ceil(n_i * p))) (main.py:653-656)
+ *   out_stride    slots reserved per query in out_pos / out_score
+ *                 (>= the largest per-query result count)
+ *   out_pos       nq x out_stride int32: POSITION within the query's candidate
+ *                 list (what top_k_cosine returns), best first; ties by
+ *                 ascending position
+ *   out_score     nq x out_stride float32 cosine similarities, descending
+ *   out_count     nq int32: results written for query i
+ *   out_zero      nq int32: number of zero-norm vectors met for query i
+ *                 (its own query vector counts); l2_norm raises ValueError
+ *                 ("Cannot normalize zero vector", norm.py:57) in that case,
+ *                 the host wrapper does the same when out_zero[i] != 0.
+ *   on_device     0: every pointer is a HOST pointer (synchronous call, staged)
+ *                 1: every pointer is a DEVICE pointer (enqueue on `stream`)
+ *                 2: Q / offsets / ids / outputs are HOST, `vectors` is DEVICE
+ *                    (queries against a corpus resident in HBM)
+ * Scores: fp32 dot(c, q) / (||c|| ||q||), within 1e-5 of the reference's
+ * normalise-then-dot order (BASELINE.json north_star tolerance).
+ * Limits: a query may have any number of candidates when its result count is
+ * <= 8192; above that the candidate count must be <= 16384 (one in-SM sort).
+ */
+int lshx_rerank_topk(lshx_reranker* r, const float* Q, int64_t nq,
+                     const float* vectors, int64_t n_vectors,
+                     const int64_t* cand_offsets, const int64_t* cand_ids,
+                     int64_t max_candidates, int k, double p, int out_stride,
+                     int32_t* out_pos, float* out_score, int32_t* out_count,
+                     int32_t* out_zero, int on_device, void* stream);
+
+/*
+ * Replaces cosine_similarity alone (similarity.py:80-90): scores[s] for every
+ * candidate slot, no selection.  Same argument meaning as lshx_rerank_topk;
+ * out_scores has total_candidates == cand_offsets[nq] entries.
+ */
+int lshx_rerank_scores(lshx_reranker* r, const float* Q, int64_t nq,
+                       const float* vectors, int64_t n_vectors,
+                       const int64_t* cand_offsets, const int64_t* cand_ids,
+                       int64_t total_candidates, float* out_scores, int32_t* out_zero,
+                       int on_device, void* stream);
+
+int lshx_rerank_destroy(lshx_reranker* r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSHX_H_ */

@@ -1,0 +1,183 @@
+"""ctypes binding of ``liblshx.so`` -- the C-ABI declared in ``include/lshx.h``.
+
+This is the only place the package touches native code.  There is no CPU
+fallback: if the shared library is missing (and cannot be built) or no sm_100
+device is usable, the first call raises :class:`LshxError` /
+:class:`LshxUnavailable` loudly.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint64, c_void_p
+from pathlib import Path
+
+__all__ = [
+    "LshxError",
+    "LshxUnavailable",
+    "lib",
+    "lib_path",
+    "check",
+    "default_device",
+    "launch_count",
+    "device_count",
+    "KERNEL_AUTO",
+    "KERNEL_FFMA",
+    "KERNEL_TCGEN05",
+    "EXPORTED_SYMBOLS",
+]
+
+KERNEL_AUTO, KERNEL_FFMA, KERNEL_TCGEN05 = 0, 1, 2
+ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM, ERR_ZERO_VECTOR = -1, -2, -3, -4, -5
+
+# every symbol include/lshx.h declares (tests/test_cabi.py checks them against the header)
+EXPORTED_SYMBOLS = (
+    "lshx_abi_version",
+    "lshx_last_error",
+    "lshx_device_count",
+    "lshx_launch_count",
+    "lshx_hasher_create",
+    "lshx_hasher_set_projections",
+    "lshx_hasher_set_kernel",
+    "lshx_hasher_last_kernel",
+    "lshx_hasher_signature_bytes",
+    "lshx_hash_batch",
+    "lshx_signatures_to_hex",
+    "lshx_hasher_destroy",
+    "lshx_rerank_create",
+    "lshx_rerank_topk",
+    "lshx_rerank_scores",
+    "lshx_rerank_destroy",
+)
+
+
+class LshxError(RuntimeError):
+    """A liblshx call failed (CUDA error, out of memory, unsupported shape)."""
+
+    def __init__(self, code: int, message: str) -> None:
+        super().__init__(f"liblshx error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class LshxUnavailable(LshxError):
+    """The CUDA extension cannot run here (no library, or no sm_100 device)."""
+
+
+_lock = threading.Lock()
+_lib: ctypes.CDLL | None = None
+
+
+def lib_path() -> Path:
+    override = os.environ.get("LSHX_LIBRARY")
+    if override:
+        return Path(override)
+    return Path(__file__).resolve().parent / "_lib" / "liblshx.so"
+
+
+def _declare(cdll: ctypes.CDLL) -> None:
+    vp = c_void_p
+    cdll.lshx_abi_version.restype = c_int
+    cdll.lshx_abi_version.argtypes = []
+    cdll.lshx_last_error.restype = c_char_p
+    cdll.lshx_last_error.argtypes = []
+    cdll.lshx_device_count.restype = c_int
+    cdll.lshx_device_count.argtypes = []
+    cdll.lshx_launch_count.restype = c_uint64
+    cdll.lshx_launch_count.argtypes = []
+
+    cdll.lshx_hasher_create.restype = c_int
+    cdll.lshx_hasher_create.argtypes = [c_int, c_int, c_int, c_int, vp, POINTER(vp)]
+    cdll.lshx_hasher_set_projections.restype = c_int
+    cdll.lshx_hasher_set_projections.argtypes = [vp, vp]
+    cdll.lshx_hasher_set_kernel.restype = c_int
+    cdll.lshx_hasher_set_kernel.argtypes = [vp, c_int]
+    cdll.lshx_hasher_last_kernel.restype = c_int
+    cdll.lshx_hasher_last_kernel.argtypes = [vp]
+    cdll.lshx_hasher_signature_bytes.restype = c_int
+    cdll.lshx_hasher_signature_bytes.argtypes = [vp]
+    cdll.lshx_hash_batch.restype = c_int
+    cdll.lshx_hash_batch.argtypes = [vp, vp, c_int64, c_int, vp, c_int, vp, vp]
+    cdll.lshx_signatures_to_hex.restype = c_int
+    cdll.lshx_signatures_to_hex.argtypes = [vp, c_int64, c_int, vp]
+    cdll.lshx_hasher_destroy.restype = c_int
+    cdll.lshx_hasher_destroy.argtypes = [vp]
+
+    cdll.lshx_rerank_create.restype = c_int
+    cdll.lshx_rerank_create.argtypes = [c_int, c_int, POINTER(vp)]
+    cdll.lshx_rerank_topk.restype = c_int
+    cdll.lshx_rerank_topk.argtypes = [vp, vp, c_int64, vp, c_int64, vp, vp, c_int64, c_int, c_double,
+                                      c_int, vp, vp, vp, vp, c_int, vp]
+    cdll.lshx_rerank_scores.restype = c_int
+    cdll.lshx_rerank_scores.argtypes = [vp, vp, c_int64, vp, c_int64, vp, vp, c_int64, vp, vp, c_int, vp]
+    cdll.lshx_rerank_destroy.restype = c_int
+    cdll.lshx_rerank_destroy.argtypes = [vp]
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return liblshx.so; builds it with nvcc if it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = lib_path()
+        if not path.exists() and not os.environ.get("LSHX_LIBRARY"):
+            try:
+                from lshrs_b200 import _build
+
+                _build.build()
+            except Exception as exc:  # noqa: BLE001 - re-raised as the loud failure below
+                raise LshxUnavailable(
+                    ERR_NO_DEVICE,
+                    f"{path} is missing and could not be built ({exc}); lshrs_b200 has no CPU fallback",
+                ) from exc
+        try:
+            cdll = ctypes.CDLL(str(path))
+        except OSError as exc:
+            raise LshxUnavailable(ERR_NO_DEVICE, f"cannot load {path}: {exc}; lshrs_b200 has no CPU fallback") from exc
+        _declare(cdll)
+        if cdll.lshx_abi_version() != 1:
+            raise LshxUnavailable(ERR_INVALID_ARG, f"{path} has ABI version {cdll.lshx_abi_version()}, expected 1")
+        _lib = cdll
+        return cdll
+
+
+def check(code: int) -> None:
+    """Raise for a negative liblshx status."""
+    if code >= 0:
+        return
+    msg = lib().lshx_last_error().decode("utf-8", "replace")
+    if code == ERR_NO_DEVICE:
+        raise LshxUnavailable(code, msg)
+    if code == ERR_OOM:
+        raise MemoryError(f"liblshx: {msg}")
+    raise LshxError(code, msg)
+
+
+def default_device() -> int:
+    """Device a new hasher / reranker binds to: $LSHRS_B200_DEVICE, else $LOCAL_RANK, else 0."""
+    for var in ("LSHRS_B200_DEVICE", "LOCAL_RANK"):
+        val = os.environ.get(var)
+        if val is not None and val.strip() != "":
+            return int(val)
+    return 0
+
+
+def launch_count() -> int:
+    """Kernels launched by liblshx in this process so far."""
+    return int(lib().lshx_launch_count())
+
+
+def device_count() -> int:
+    """Usable sm_100 devices (0 on a CPU-only machine)."""
+    return int(lib().lshx_device_count())
+
+
+# re-exported for type hints in the wrappers
+c_float_p = POINTER(c_float)
+c_uint8_p = POINTER(c_uint8)
+c_int32_p = POINTER(c_int32)

@@ -1,0 +1,377 @@
+"""``LSHRS`` -- the reference orchestrator's hot-path call sites on top of the GPU kernels.
+
+Mirrors the parts of reference lshrs/core/main.py that call the hasher and the
+reranker: ``ingest`` (main.py:386-411), ``index`` (442-518), ``flush``
+(413-440), ``query`` (524-658), ``get_top_k`` (660-693), ``get_above_p``
+(695-738), ``delete`` / ``clear`` / ``stats`` and the buffer helpers
+(1050-1143) -- same signatures, validation order, error types and messages,
+same ``(band_id, bytes, index)`` operations with the same flush boundaries.
+Bucket storage is NOT re-implemented: pass the reference's ``RedisStorage`` (or
+anything with its five methods) as ``storage=``; persistence, pickling and the
+Postgres/Parquet loaders are host control flow that stays in the reference
+(INTEGRATION.md shows the two-import patch that puts the reference's own
+``LSHRS`` on these kernels).
+
+What is new is batching: ``index()`` hashes the whole batch in ONE kernel call
+with the zero-vector test fused in, and ``query_batch`` hashes all queries at
+once and reranks all of them in one launch.
+"""
+
+from __future__ import annotations
+
+import logging
+import math
+from collections.abc import Callable, Sequence
+from threading import Lock
+from typing import Any, Optional, Union
+
+import numpy as np
+
+from lshrs_b200._config.config import HashSignatures
+from lshrs_b200.hash.lsh import LSHHasher
+from lshrs_b200.storage.memory import BucketOperation, BucketStorage
+from lshrs_b200.utils.similarity import _get_reranker
+
+logger = logging.getLogger(__name__)
+
+VectorFetchFn = Callable[[Sequence[int]], np.ndarray]
+CandidateScores = list[tuple[int, float]]
+
+# (num_bands, rows_per_band) the reference's get_optimal_config(num_perm, 0.5) selects
+# (reference lshrs/utils/br.py:325-395, recorded by tools/make_golden.py in
+# tests/golden/manifest.json).  Other thresholds need the reference's br module.
+_AUTO_CONFIG_T05 = {64: (16, 4), 128: (8, 16), 256: (16, 16), 512: (16, 32), 1024: (128, 8)}
+
+_ZERO_VECTOR_MSG = "Cannot index zero vector - norm undefined. Check embeddings for corruption."
+
+
+def _auto_config(num_perm: int, threshold: float) -> tuple[int, int]:
+    try:  # the reference's own chooser when it is installed next to us
+        from lshrs.utils.br import get_optimal_config  # type: ignore
+
+        b, r = get_optimal_config(num_perm, threshold)
+        return int(b), int(r)
+    except ImportError:
+        pass
+    if abs(threshold - 0.5) < 1e-12 and num_perm in _AUTO_CONFIG_T05:
+        return _AUTO_CONFIG_T05[num_perm]
+    raise ValueError(
+        f"num_bands and rows_per_band must be given for num_perm={num_perm}, "
+        f"similarity_threshold={threshold} (band/row auto-configuration lives in the reference's lshrs.utils.br)"
+    )
+
+
+class LSHRS:
+    """LSH index front-end whose hashing and reranking run on a B200."""
+
+    def __init__(
+        self,
+        *,
+        dim: int,
+        num_perm: int = 128,
+        num_bands: Optional[int] = None,
+        rows_per_band: Optional[int] = None,
+        similarity_threshold: float = 0.5,
+        buffer_size: int = 10_000,
+        vector_fetch_fn: Optional[VectorFetchFn] = None,
+        storage: Optional[BucketStorage] = None,
+        redis_host: str = "localhost",
+        redis_port: int = 6379,
+        redis_db: int = 0,
+        redis_password: Optional[str] = None,
+        redis_prefix: str = "lsh",
+        redis_max_connections: int = 50,
+        decode_responses: bool = False,
+        seed: int = 42,
+        device: Optional[int] = None,
+    ) -> None:
+        if dim <= 0:
+            raise ValueError("Vector dimensionality must be greater than zero")
+        if num_perm <= 0:
+            raise ValueError("num_perm must be greater than zero")
+        if buffer_size <= 0:
+            raise ValueError("buffer_size must be greater than zero")
+        if num_bands is None or rows_per_band is None:
+            num_bands, rows_per_band = _auto_config(num_perm, similarity_threshold)
+        if num_bands * rows_per_band != num_perm:
+            raise ValueError(
+                f"num_bands * rows_per_band must equal num_perm (received {num_bands} * {rows_per_band} != {num_perm})"
+            )
+        self._dim = dim
+        self._buffer_size = buffer_size
+        self._vector_fetch_fn = vector_fetch_fn
+        self._hasher = LSHHasher(num_bands=num_bands, rows_per_band=rows_per_band, dim=dim, seed=seed, device=device)
+        if storage is None:
+            storage = self._make_redis_storage(
+                host=redis_host, port=redis_port, db=redis_db, password=redis_password,
+                decode_responses=decode_responses, prefix=redis_prefix, max_connections=redis_max_connections,
+            )
+        self._storage = storage
+        self._buffer: list[BucketOperation] = []
+        self._buffer_lock = Lock()
+        self._config: dict[str, Any] = {
+            "dim": dim, "num_perm": num_perm, "num_bands": num_bands, "rows_per_band": rows_per_band,
+            "similarity_threshold": similarity_threshold, "buffer_size": buffer_size, "seed": seed,
+        }
+        self._redis_config: dict[str, Any] = {
+            "host": redis_host, "port": redis_port, "db": redis_db, "password": redis_password,
+            "prefix": redis_prefix, "decode_responses": decode_responses, "max_connections": redis_max_connections,
+        }
+
+    @staticmethod
+    def _make_redis_storage(**kwargs: Any) -> BucketStorage:
+        try:
+            from lshrs.storage.redis import RedisStorage  # type: ignore  # the reference's, unchanged
+        except ImportError as exc:
+            raise RuntimeError(
+                "no storage given: pass storage=<RedisStorage or compatible> (Redis bucket storage stays in the "
+                "reference package lshrs.storage.redis, which is not importable here)"
+            ) from exc
+        return RedisStorage(**kwargs)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        self.flush()
+        self._storage.close()
+
+    def __enter__(self) -> "LSHRS":
+        return self
+
+    def __exit__(self, exc_type, exc_value, traceback) -> None:
+        self.close()
+
+    def __repr__(self) -> str:  # pragma: no cover
+        c = self._config
+        return (f"LSHRS(dim={self._dim}, num_perm={c['num_perm']}, num_bands={c['num_bands']}, "
+                f"rows_per_band={c['rows_per_band']}, redis_prefix='{self._redis_config['prefix']}')")
+
+    # ------------------------------------------------------------------ ingestion
+    def ingest(self, index: int, vector: np.ndarray) -> None:
+        """Hash one vector and buffer its ``num_bands`` bucket operations."""
+        if index < 0:
+            raise ValueError("index must be non-negative")
+        vec = self._prepare_vector(vector)
+        signatures = self._hasher.hash_vector(vec)
+        self._enqueue_operations(index, signatures)
+        self._flush_buffer_if_needed()
+
+    def flush(self) -> None:
+        """Send buffered operations to storage; on failure put them back at the front and re-raise."""
+        with self._buffer_lock:
+            if not self._buffer:
+                return
+            pending = list(self._buffer)
+            self._buffer.clear()
+        try:
+            self._storage.batch_add(pending)
+        except Exception as exc:
+            logger.error(f"Failed to flush buffer to Redis: {exc}")
+            with self._buffer_lock:
+                self._buffer[0:0] = pending
+            raise
+
+    def index(self, indices: Sequence[int], vectors: Optional[np.ndarray] = None) -> None:
+        """Ingest a batch: ONE kernel call hashes every row and flags zero vectors.
+
+        Observable behaviour equals the reference's per-row ``ingest`` loop: the
+        same operations in the same order, a flush whenever the buffer reaches
+        ``buffer_size`` after a whole vector, rows before the first invalid one
+        are ingested before the error is raised, and a final flush.
+        """
+        if not len(indices):
+            return
+        if vectors is None:
+            vectors = self._require_vector_fetch_fn()(indices)
+        arr = np.asarray(vectors, dtype=np.float32)
+        if arr.ndim != 2 or arr.shape[1] != self._dim:
+            raise ValueError(f"Vectors must have shape (n, {self._dim}); received {arr.shape}")
+        if arr.shape[0] != len(indices):
+            raise ValueError(
+                "Number of vectors does not match number of indices "
+                f"(received {arr.shape[0]} vectors for {len(indices)} indices)"
+            )
+        packed, zero_flag = self._hasher.hash_batch_packed(arr, return_zero_flag=True)
+        nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
+        blob = packed.tobytes()
+        stride = nb * bpb
+        for row, idx in enumerate(indices):
+            idx = int(idx)
+            if idx < 0:
+                raise ValueError("index must be non-negative")
+            if zero_flag[row]:
+                raise ValueError(_ZERO_VECTOR_MSG)
+            base = row * stride
+            ops = [(b, blob[base + b * bpb : base + (b + 1) * bpb], idx) for b in range(nb)]
+            with self._buffer_lock:
+                self._buffer.extend(ops)
+            self._flush_buffer_if_needed()
+        self.flush()
+
+    # ------------------------------------------------------------------ querying
+    def query(self, vector: np.ndarray, *, top_k: Optional[int] = 10,
+              top_p: Optional[float] = None) -> Union[list[int], CandidateScores]:
+        """Candidates by band collisions; with ``top_p`` reranked by cosine on the GPU."""
+        q = self._prepare_vector(vector)
+        counts = self._candidate_counts(q)
+        if not counts:
+            return []
+        ordered = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))
+        if top_p is None:
+            if top_k is None:
+                top_k = len(ordered)
+            if top_k <= 0:
+                raise ValueError("top_k must be greater than zero when provided")
+            return [idx for idx, _ in ordered[:top_k]]
+        if not 0 < top_p <= 1:
+            raise ValueError("top_p must be within the range (0, 1]")
+        candidate_indices = [idx for idx, _ in ordered]
+        fetched = self._require_vector_fetch_fn()(candidate_indices)
+        arr = np.ascontiguousarray(np.asarray(fetched, dtype=np.float32))
+        if arr.ndim != 2 or arr.shape[1] != self._dim:
+            raise ValueError(f"Fetched vectors must have shape (n, {self._dim}); received {arr.shape}")
+        if arr.shape[0] != len(candidate_indices):
+            raise ValueError(
+                "vector_fetch_fn returned mismatched batch size "
+                f"(expected {len(candidate_indices)}, received {arr.shape[0]})"
+            )
+        if top_k is not None and top_k <= 0:
+            raise ValueError("top_k must be greater than zero when provided")
+        n = len(candidate_indices)
+        # The reference sorts ALL n candidates (top_k_cosine(k=n)) and slices
+        # max(1, ceil(n * top_p)) [then min(., top_k)]; the kernel applies the same
+        # cut and only the kept rows come back over PCIe.
+        rer = _get_reranker(self._dim, self._hasher.device)
+        pos, score, count, zero = rer.topk(q, arr, np.array([0, n], dtype=np.int64),
+                                           k=int(top_k) if top_k is not None else 0, p=float(top_p))
+        if zero.any():
+            raise ValueError("Cannot normalize zero vector")
+        return [(candidate_indices[int(pos[0, i])], float(score[0, i])) for i in range(int(count[0]))]
+
+    def get_top_k(self, vector: np.ndarray, topk: int = 10) -> list[int]:
+        return list(self.query(vector, top_k=topk, top_p=None))  # type: ignore[arg-type]
+
+    def get_above_p(self, vector: np.ndarray, p: float = 0.95) -> CandidateScores:
+        return list(self.query(vector, top_k=None, top_p=p))  # type: ignore[arg-type]
+
+    def query_batch(self, vectors: np.ndarray, *, top_k: Optional[int] = 10, top_p: Optional[float] = None,
+                    corpus=None) -> list:
+        """``query`` for many vectors: one hash launch, one rerank launch.
+
+        Returns one result list per row, identical to calling :meth:`query` row
+        by row.  With ``top_p``, candidate vectors come from ``corpus`` when given
+        (a CUDA torch tensor ``(N, dim)`` resident in HBM, candidate id = row --
+        the device-side stand-in for ``vector_fetch_fn``), else from ``vector_fetch_fn``.
+        """
+        arr = np.asarray(vectors, dtype=np.float32)
+        if arr.ndim != 2 or arr.shape[1] != self._dim:
+            raise ValueError(f"Vectors must have shape (n, {self._dim}); received {arr.shape}")
+        nq = arr.shape[0]
+        if nq == 0:
+            return []
+        if top_p is None and top_k is not None and top_k <= 0:
+            raise ValueError("top_k must be greater than zero when provided")
+        if top_p is not None and not 0 < top_p <= 1:
+            raise ValueError("top_p must be within the range (0, 1]")
+        packed, zero_flag = self._hasher.hash_batch_packed(arr, return_zero_flag=True)
+        if zero_flag.any():
+            raise ValueError(_ZERO_VECTOR_MSG)
+        nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
+        blob = packed.tobytes()
+        stride = nb * bpb
+        ordered_all: list[list[int]] = []
+        for row in range(nq):
+            counts: dict[int, int] = {}
+            base = row * stride
+            for b in range(nb):
+                for cand in self._storage.get_bucket(b, blob[base + b * bpb : base + (b + 1) * bpb]):
+                    counts[cand] = counts.get(cand, 0) + 1
+            ordered = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))
+            ordered_all.append([idx for idx, _ in ordered])
+        if top_p is None:
+            return [ids if top_k is None else ids[:top_k] for ids in ordered_all]
+        if top_k is not None and top_k <= 0:
+            raise ValueError("top_k must be greater than zero when provided")
+        lens = np.array([len(x) for x in ordered_all], dtype=np.int64)
+        offsets = np.zeros(nq + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        if offsets[-1] == 0:
+            return [[] for _ in range(nq)]
+        flat_ids = np.fromiter((i for ids in ordered_all for i in ids), dtype=np.int64, count=int(offsets[-1]))
+        rer = _get_reranker(self._dim, self._hasher.device)
+        if corpus is not None:
+            pos, score, count, zero = rer.topk(arr, corpus, offsets, flat_ids, k=int(top_k or 0), p=float(top_p),
+                                               vectors_on_device=True)
+        else:
+            fetched = np.ascontiguousarray(np.asarray(self._require_vector_fetch_fn()(flat_ids.tolist()), dtype=np.float32))
+            if fetched.ndim != 2 or fetched.shape[1] != self._dim:
+                raise ValueError(f"Fetched vectors must have shape (n, {self._dim}); received {fetched.shape}")
+            if fetched.shape[0] != flat_ids.shape[0]:
+                raise ValueError(
+                    "vector_fetch_fn returned mismatched batch size "
+                    f"(expected {flat_ids.shape[0]}, received {fetched.shape[0]})"
+                )
+            pos, score, count, zero = rer.topk(arr, fetched, offsets, None, k=int(top_k or 0), p=float(top_p))
+        nonempty = lens > 0
+        if zero[nonempty].any():
+            raise ValueError("Cannot normalize zero vector")
+        out: list = []
+        for row in range(nq):
+            ids = ordered_all[row]
+            out.append([(ids[int(pos[row, i])], float(score[row, i])) for i in range(int(count[row]))] if ids else [])
+        return out
+
+    # ------------------------------------------------------------------ maintenance
+    def delete(self, indices: Union[int, Sequence[int]]) -> None:
+        to_remove = [indices] if isinstance(indices, int) else [int(i) for i in indices]
+        self._storage.remove_indices(to_remove)
+
+    def clear(self) -> None:
+        self.flush()
+        self._storage.clear()
+
+    def stats(self) -> dict[str, Any]:
+        c = self._config
+        return {
+            "dimension": self._dim, "num_perm": c["num_perm"], "num_bands": c["num_bands"],
+            "rows_per_band": c["rows_per_band"], "buffer_size": self._buffer_size,
+            "similarity_threshold": c["similarity_threshold"], "redis_prefix": self._redis_config["prefix"],
+        }
+
+    # ------------------------------------------------------------------ helpers
+    def _prepare_vector(self, vector: np.ndarray) -> np.ndarray:
+        arr = np.asarray(vector, dtype=np.float32).reshape(-1)
+        if arr.shape[0] != self._dim:
+            raise ValueError(f"Vector must have dimension {self._dim}; received {arr.shape[0]}")
+        # np.allclose(arr, 0, atol=1e-8) without its temporaries: NaN makes it False, like numpy
+        if bool((np.abs(arr) <= 1e-8).all()):
+            raise ValueError(_ZERO_VECTOR_MSG)
+        return arr
+
+    def _candidate_counts(self, query_vector: np.ndarray) -> dict[int, int]:
+        signatures = self._hasher.hash_vector(query_vector)
+        counts: dict[int, int] = {}
+        for band_id, hash_val in enumerate(signatures):
+            for candidate in self._storage.get_bucket(band_id, hash_val):
+                counts[candidate] = counts.get(candidate, 0) + 1
+        return counts
+
+    def _enqueue_operations(self, index: int, signatures: Union[HashSignatures, Sequence[bytes]]) -> None:
+        ops = [(band_id, hash_val, int(index)) for band_id, hash_val in enumerate(signatures)]
+        with self._buffer_lock:
+            self._buffer.extend(ops)
+
+    def _flush_buffer_if_needed(self) -> None:
+        with self._buffer_lock:
+            due = len(self._buffer) >= self._buffer_size
+        if due:
+            self.flush()
+
+    def _require_vector_fetch_fn(self) -> VectorFetchFn:
+        if self._vector_fetch_fn is None:
+            raise RuntimeError("vector_fetch_fn must be supplied for operations requiring reranking")
+        return self._vector_fetch_fn
+
+
+lshrs = LSHRS
+
+__all__ = ["LSHRS", "lshrs", "VectorFetchFn", "CandidateScores"]

@@ -1,0 +1,501 @@
+// extern "C" entry points of liblshx.so (declared in include/lshx.h) and the host-side
+// staging pipelines around the kernels.
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "lshx_common.cuh"
+
+namespace lshx {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int check_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    set_error("no CUDA device available (%s); liblshx has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return LSHX_ERR_NO_DEVICE;
+  }
+  if (device < 0 || device >= count) {
+    set_error("device %d out of range (have %d)", device, count);
+    return LSHX_ERR_INVALID_ARG;
+  }
+  cudaDeviceProp prop;
+  LSHX_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; liblshx is built for sm_100a only", device, prop.major,
+              prop.minor);
+    return LSHX_ERR_NO_DEVICE;
+  }
+  return LSHX_OK;
+}
+
+// RAII device switch
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Grow-only device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return LSHX_OK;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    LSHX_CUDA(cudaMalloc(&p, bytes));
+    cap = bytes;
+    return LSHX_OK;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace lshx
+
+using namespace lshx;
+
+// ---------------------------------------------------------------------------------------
+// hasher
+// ---------------------------------------------------------------------------------------
+
+struct lshx_hasher {
+  int device = 0;
+  HashShape s{};
+  float* d_Rp = nullptr;  // [ncols_pad][dim] fp32, zero rows for padding
+  TcPlan* tc = nullptr;
+  int kernel_pref = LSHX_KERNEL_AUTO;
+  int last_kernel = 0;
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in = nullptr;
+  DevBuf x_stage[2], out_stage[2], flag_stage[2];
+  std::mutex mu;
+};
+
+static int upload_projections(lshx_hasher* h, const float* R) {
+  const HashShape& s = h->s;
+  // build the padded column layout on the host: band b -> columns [b*8*bpb, b*8*bpb + r)
+  std::vector<float> Rp((size_t)s.ncols_pad * s.dim, 0.f);
+  for (int b = 0; b < s.num_bands; ++b)
+    for (int j = 0; j < s.rows_per_band; ++j)
+      std::memcpy(&Rp[((size_t)b * 8 * s.bpb + j) * s.dim],
+                  &R[((size_t)b * s.rows_per_band + j) * s.dim], sizeof(float) * s.dim);
+  LSHX_CUDA(cudaMemcpy(h->d_Rp, Rp.data(), Rp.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (h->tc) {
+    tc_plan_destroy(h->tc);
+    h->tc = nullptr;
+  }
+  if (tc_shape_supported(s)) {
+    int rc = tc_plan_create(s, h->d_Rp, &h->tc);
+    if (rc != LSHX_OK) return rc;
+  }
+  return LSHX_OK;
+}
+
+extern "C" int lshx_abi_version(void) { return LSHX_ABI_VERSION; }
+extern "C" const char* lshx_last_error(void) { return g_err; }
+extern "C" uint64_t lshx_launch_count(void) { return g_launches.load(); }
+
+extern "C" int lshx_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < count; ++d) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+  }
+  return ok;
+}
+
+extern "C" int lshx_hasher_create(int device, int dim, int num_bands, int rows_per_band,
+                                  const float* projections_host, lshx_hasher** out) {
+  LSHX_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  LSHX_REQUIRE(num_bands > 0, "num_bands must be > 0");
+  LSHX_REQUIRE(rows_per_band > 0, "rows_per_band must be > 0");
+  LSHX_REQUIRE(dim > 0, "dim must be > 0");
+  LSHX_REQUIRE(projections_host != nullptr, "projections_host is null");
+  const int64_t bpb = (rows_per_band + 7) / 8;
+  LSHX_REQUIRE(bpb * num_bands <= (1 << 20), "signature of %lld bytes per vector is unsupported",
+               (long long)(bpb * num_bands));
+  int rc = check_device(device);
+  if (rc != LSHX_OK) return rc;
+  DeviceGuard g(device);
+
+  lshx_hasher* h = new lshx_hasher();
+  h->device = device;
+  HashShape& s = h->s;
+  s.dim = dim;
+  s.num_bands = num_bands;
+  s.rows_per_band = rows_per_band;
+  s.bpb = (int)bpb;
+  s.sig_bytes = (int)(bpb * num_bands);
+  s.ncols = s.sig_bytes * 8;
+  s.ncols_pad = (s.ncols + 127) / 128 * 128;
+  s.dim_pad = (dim + 31) / 32 * 32;
+  auto fail = [&](int code) {
+    lshx_hasher_destroy(h);
+    return code;
+  };
+  if (cudaMalloc(&h->d_Rp, (size_t)s.ncols_pad * dim * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes for the projections failed",
+              (size_t)s.ncols_pad * dim * sizeof(float));
+    (void)cudaGetLastError();
+    return fail(LSHX_ERR_OOM);
+  }
+  for (int i = 0; i < 2; ++i)
+    if (cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("cudaStreamCreate failed");
+      return fail(LSHX_ERR_CUDA);
+    }
+  if (cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("cudaEventCreate failed");
+    return fail(LSHX_ERR_CUDA);
+  }
+  rc = upload_projections(h, projections_host);
+  if (rc != LSHX_OK) return fail(rc);
+  *out = h;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_hasher_set_projections(lshx_hasher* h, const float* projections_host) {
+  LSHX_REQUIRE(h != nullptr && projections_host != nullptr, "null argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  LSHX_CUDA(cudaDeviceSynchronize());
+  return upload_projections(h, projections_host);
+}
+
+extern "C" int lshx_hasher_set_kernel(lshx_hasher* h, int kernel) {
+  LSHX_REQUIRE(h != nullptr, "null handle");
+  LSHX_REQUIRE(kernel >= LSHX_KERNEL_AUTO && kernel <= LSHX_KERNEL_TCGEN05, "unknown kernel %d",
+               kernel);
+  LSHX_REQUIRE(kernel != LSHX_KERNEL_TCGEN05 || h->tc != nullptr,
+               "the tcgen05 kernel does not support this shape (dim %d, %d x %d)", h->s.dim,
+               h->s.num_bands, h->s.rows_per_band);
+  std::lock_guard<std::mutex> lk(h->mu);
+  h->kernel_pref = kernel;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_hasher_last_kernel(const lshx_hasher* h) { return h ? h->last_kernel : 0; }
+extern "C" int lshx_hasher_signature_bytes(const lshx_hasher* h) { return h ? h->s.sig_bytes : 0; }
+
+static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_out,
+                       uint8_t* d_flag, cudaStream_t st) {
+  const bool use_tc =
+      h->tc != nullptr && (h->kernel_pref == LSHX_KERNEL_TCGEN05 ||
+                           (h->kernel_pref == LSHX_KERNEL_AUTO &&
+                            (reinterpret_cast<uintptr_t>(d_X) & 15) == 0));
+  if (use_tc) {
+    h->last_kernel = LSHX_KERNEL_TCGEN05;
+    return launch_hash_tc(h->s, h->tc, d_X, n, d_out, d_flag, st);
+  }
+  h->last_kernel = LSHX_KERNEL_FFMA;
+  return launch_hash_ffma(h->s, d_X, n, h->d_Rp, d_out, d_flag, st);
+}
+
+extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_is_device,
+                               uint8_t* out, int out_is_device, uint8_t* zero_flag,
+                               void* stream) {
+  LSHX_REQUIRE(h != nullptr, "null handle");
+  LSHX_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0) return LSHX_OK;
+  LSHX_REQUIRE(X != nullptr && out != nullptr, "null buffer");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  const HashShape& s = h->s;
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+
+  // ---- everything on the device: one asynchronous launch ----------------------------
+  if (x_is_device && out_is_device) {
+    cudaStream_t st = user ? user : h->streams[0];
+    return launch_hash(h, X, n, out, zero_flag, st);
+  }
+
+  // ---- at least one side on the host: chunked, two streams, synchronous -----------
+  const size_t row_bytes = (size_t)s.dim * sizeof(float);
+  int64_t chunk = (int64_t)((256u << 20) / row_bytes);
+  chunk = chunk / 128 * 128;
+  if (chunk < 128) chunk = 128;
+  if (chunk > n) chunk = n;
+  for (int i = 0; i < 2; ++i) {
+    int rc;
+    if (!x_is_device && (rc = h->x_stage[i].reserve((size_t)chunk * row_bytes)) != LSHX_OK) return rc;
+    if (!out_is_device) {
+      if ((rc = h->out_stage[i].reserve((size_t)chunk * s.sig_bytes)) != LSHX_OK) return rc;
+      if (zero_flag && (rc = h->flag_stage[i].reserve((size_t)chunk)) != LSHX_OK) return rc;
+    }
+  }
+  if (x_is_device) {
+    // inputs were produced on the caller's stream: order our streams after it
+    LSHX_CUDA(cudaEventRecord(h->ev_in, user));
+    for (int i = 0; i < 2; ++i) LSHX_CUDA(cudaStreamWaitEvent(h->streams[i], h->ev_in, 0));
+  } else if (user) {
+    LSHX_CUDA(cudaStreamSynchronize(user));
+  }
+  int slot = 0;
+  for (int64_t r0 = 0; r0 < n; r0 += chunk, slot ^= 1) {
+    const int64_t rows = (n - r0 < chunk) ? (n - r0) : chunk;
+    cudaStream_t st = h->streams[slot];
+    const float* d_x;
+    if (x_is_device) {
+      d_x = X + r0 * s.dim;
+    } else {
+      LSHX_CUDA(cudaMemcpyAsync(h->x_stage[slot].p, X + r0 * s.dim, (size_t)rows * row_bytes,
+                                cudaMemcpyHostToDevice, st));
+      d_x = static_cast<const float*>(h->x_stage[slot].p);
+    }
+    uint8_t* d_o = out_is_device ? out + r0 * s.sig_bytes : static_cast<uint8_t*>(h->out_stage[slot].p);
+    uint8_t* d_f = zero_flag ? (out_is_device ? zero_flag + r0
+                                              : static_cast<uint8_t*>(h->flag_stage[slot].p))
+                             : nullptr;
+    int rc = launch_hash(h, d_x, rows, d_o, d_f, st);
+    if (rc != LSHX_OK) return rc;
+    if (!out_is_device) {
+      LSHX_CUDA(cudaMemcpyAsync(out + r0 * s.sig_bytes, d_o, (size_t)rows * s.sig_bytes,
+                                cudaMemcpyDeviceToHost, st));
+      if (zero_flag)
+        LSHX_CUDA(cudaMemcpyAsync(zero_flag + r0, d_f, (size_t)rows, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  LSHX_CUDA(cudaStreamSynchronize(h->streams[0]));
+  LSHX_CUDA(cudaStreamSynchronize(h->streams[1]));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_signatures_to_hex(const uint8_t* sig, int64_t n, int sig_bytes, char* hex_out) {
+  LSHX_REQUIRE(sig != nullptr && hex_out != nullptr && n >= 0 && sig_bytes > 0, "bad argument");
+  static const char digits[] = "0123456789abcdef";
+  const int64_t total = n * sig_bytes;
+  for (int64_t i = 0; i < total; ++i) {
+    hex_out[2 * i] = digits[sig[i] >> 4];
+    hex_out[2 * i + 1] = digits[sig[i] & 15];
+  }
+  return LSHX_OK;
+}
+
+extern "C" int lshx_hasher_destroy(lshx_hasher* h) {
+  if (!h) return LSHX_OK;
+  {
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    if (h->tc) tc_plan_destroy(h->tc);
+    if (h->d_Rp) cudaFree(h->d_Rp);
+    for (int i = 0; i < 2; ++i) {
+      h->x_stage[i].release();
+      h->out_stage[i].release();
+      h->flag_stage[i].release();
+      if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    }
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    (void)cudaGetLastError();
+  }
+  delete h;
+  return LSHX_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// reranker
+// ---------------------------------------------------------------------------------------
+
+struct lshx_reranker {
+  int device = 0;
+  int dim = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf q, vecs, offs, ids, pos, score, count, zero, all;
+  std::mutex mu;
+};
+
+extern "C" int lshx_rerank_create(int device, int dim, lshx_reranker** out) {
+  LSHX_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  LSHX_REQUIRE(dim > 0, "dim must be > 0");
+  int rc = check_device(device);
+  if (rc != LSHX_OK) return rc;
+  DeviceGuard g(device);
+  lshx_reranker* r = new lshx_reranker();
+  r->device = device;
+  r->dim = dim;
+  if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    delete r;
+    return LSHX_ERR_CUDA;
+  }
+  *out = r;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_rerank_destroy(lshx_reranker* r) {
+  if (!r) return LSHX_OK;
+  {
+    DeviceGuard g(r->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&r->q, &r->vecs, &r->offs, &r->ids, &r->pos, &r->score, &r->count, &r->zero, &r->all})
+      b->release();
+    if (r->stream) cudaStreamDestroy(r->stream);
+    (void)cudaGetLastError();
+  }
+  delete r;
+  return LSHX_OK;
+}
+
+// Shared body of lshx_rerank_topk / lshx_rerank_scores.
+static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const float* vectors,
+                         int64_t n_vectors, const int64_t* cand_offsets, const int64_t* cand_ids,
+                         int64_t max_candidates, int64_t total_candidates, bool select, int k,
+                         double p, int out_stride, int32_t* out_pos, float* out_score,
+                         int32_t* out_count, float* out_all, int32_t* out_zero, int on_device,
+                         void* stream) {
+  LSHX_REQUIRE(r != nullptr, "null handle");
+  LSHX_REQUIRE(nq >= 0, "nq must be >= 0");
+  LSHX_REQUIRE(on_device >= 0 && on_device <= 2, "on_device must be 0, 1 or 2");
+  if (nq == 0) return LSHX_OK;
+  LSHX_REQUIRE(Q != nullptr && cand_offsets != nullptr, "null buffer");
+  if (select) {
+    LSHX_REQUIRE(k > 0 || p > 0.0, "k must be > 0");
+    LSHX_REQUIRE(!(p > 1.0), "top_p must be within the range (0, 1]");
+    LSHX_REQUIRE(out_pos && out_score && out_count && out_stride > 0, "null output buffer");
+  } else {
+    LSHX_REQUIRE(out_all != nullptr, "null output buffer");
+  }
+  std::lock_guard<std::mutex> lk(r->mu);
+  DeviceGuard g(r->device);
+  const int dim = r->dim;
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+
+  RerankArgs a{};
+  a.nq = nq;
+  a.n_vectors = n_vectors;
+  a.dim = dim;
+  a.k = k;
+  a.p = p;
+  a.out_stride = out_stride;
+  a.select = select;
+
+  if (on_device == 1) {
+    LSHX_REQUIRE(vectors != nullptr || max_candidates == 0, "null vectors");
+    a.Q = Q; a.V = vectors; a.offs = cand_offsets; a.ids = cand_ids;
+    a.out_pos = out_pos; a.out_score = out_score; a.out_count = out_count; a.out_zero = out_zero;
+    a.all_scores = out_all;
+    a.max_cand = max_candidates;
+    return launch_rerank(a, user ? user : r->stream);
+  }
+
+  // host-side offsets: validate and size
+  int64_t total = cand_offsets[nq] - cand_offsets[0];
+  int64_t maxc = 0;
+  for (int64_t i = 0; i < nq; ++i) {
+    const int64_t c = cand_offsets[i + 1] - cand_offsets[i];
+    LSHX_REQUIRE(c >= 0, "cand_offsets must be non-decreasing");
+    if (c > maxc) maxc = c;
+  }
+  LSHX_REQUIRE(cand_offsets[0] >= 0, "cand_offsets[0] must be >= 0");
+  const int64_t end = cand_offsets[nq];
+  LSHX_REQUIRE(total == 0 || (vectors != nullptr && n_vectors > 0), "no vectors to rank against");
+  if (!cand_ids) LSHX_REQUIRE(end <= n_vectors, "cand_offsets run past the %lld packed vectors", (long long)n_vectors);
+  if (!select) LSHX_REQUIRE(total_candidates >= end, "out_scores too small");
+  a.max_cand = maxc;
+
+  cudaStream_t st = r->stream;
+  if (user) LSHX_CUDA(cudaStreamSynchronize(user));
+  int rc;
+  if ((rc = r->q.reserve((size_t)nq * dim * sizeof(float))) != LSHX_OK) return rc;
+  if ((rc = r->offs.reserve((size_t)(nq + 1) * sizeof(int64_t))) != LSHX_OK) return rc;
+  LSHX_CUDA(cudaMemcpyAsync(r->q.p, Q, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  LSHX_CUDA(cudaMemcpyAsync(r->offs.p, cand_offsets, (size_t)(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  a.Q = static_cast<const float*>(r->q.p);
+  a.offs = static_cast<const int64_t*>(r->offs.p);
+  if (cand_ids && end > 0) {
+    if ((rc = r->ids.reserve((size_t)end * sizeof(int64_t))) != LSHX_OK) return rc;
+    LSHX_CUDA(cudaMemcpyAsync(r->ids.p, cand_ids, (size_t)end * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    a.ids = static_cast<const int64_t*>(r->ids.p);
+  }
+  if (on_device == 2) {
+    a.V = vectors;
+  } else if (total > 0) {
+    // host vectors: packed candidates copy only the rows that are referenced
+    const int64_t rows = cand_ids ? n_vectors : end;
+    if ((rc = r->vecs.reserve((size_t)rows * dim * sizeof(float))) != LSHX_OK) return rc;
+    LSHX_CUDA(cudaMemcpyAsync(r->vecs.p, vectors, (size_t)rows * dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    a.V = static_cast<const float*>(r->vecs.p);
+    a.n_vectors = rows;
+  }
+  if (select) {
+    if ((rc = r->pos.reserve((size_t)nq * out_stride * sizeof(int32_t))) != LSHX_OK) return rc;
+    if ((rc = r->score.reserve((size_t)nq * out_stride * sizeof(float))) != LSHX_OK) return rc;
+    if ((rc = r->count.reserve((size_t)nq * sizeof(int32_t))) != LSHX_OK) return rc;
+    a.out_pos = static_cast<int32_t*>(r->pos.p);
+    a.out_score = static_cast<float*>(r->score.p);
+    a.out_count = static_cast<int32_t*>(r->count.p);
+  } else {
+    if ((rc = r->all.reserve((size_t)(end > 0 ? end : 1) * sizeof(float))) != LSHX_OK) return rc;
+    a.all_scores = static_cast<float*>(r->all.p);
+  }
+  if ((rc = r->zero.reserve((size_t)nq * sizeof(int32_t))) != LSHX_OK) return rc;
+  a.out_zero = static_cast<int32_t*>(r->zero.p);
+
+  rc = launch_rerank(a, st);
+  if (rc != LSHX_OK) return rc;
+
+  if (select) {
+    LSHX_CUDA(cudaMemcpyAsync(out_pos, a.out_pos, (size_t)nq * out_stride * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    LSHX_CUDA(cudaMemcpyAsync(out_score, a.out_score, (size_t)nq * out_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
+    LSHX_CUDA(cudaMemcpyAsync(out_count, a.out_count, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  } else if (end > 0) {
+    LSHX_CUDA(cudaMemcpyAsync(out_all, a.all_scores, (size_t)end * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (out_zero)
+    LSHX_CUDA(cudaMemcpyAsync(out_zero, a.out_zero, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  LSHX_CUDA(cudaStreamSynchronize(st));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_rerank_topk(lshx_reranker* r, const float* Q, int64_t nq, const float* vectors,
+                                int64_t n_vectors, const int64_t* cand_offsets,
+                                const int64_t* cand_ids, int64_t max_candidates, int k, double p,
+                                int out_stride, int32_t* out_pos, float* out_score,
+                                int32_t* out_count, int32_t* out_zero, int on_device, void* stream) {
+  return rerank_common(r, Q, nq, vectors, n_vectors, cand_offsets, cand_ids, max_candidates, 0,
+                       true, k, p, out_stride, out_pos, out_score, out_count, nullptr, out_zero,
+                       on_device, stream);
+}
+
+extern "C" int lshx_rerank_scores(lshx_reranker* r, const float* Q, int64_t nq, const float* vectors,
+                                  int64_t n_vectors, const int64_t* cand_offsets,
+                                  const int64_t* cand_ids, int64_t total_candidates,
+                                  float* out_scores, int32_t* out_zero, int on_device, void* stream) {
+  return rerank_common(r, Q, nq, vectors, n_vectors, cand_offsets, cand_ids, 0, total_candidates,
+                       false, 0, 0.0, 0, nullptr, nullptr, nullptr, out_scores, out_zero, on_device,
+                       stream);
+}

@@ -1,0 +1,91 @@
+// Shared declarations of liblshx.so (internal; the public ABI is include/lshx.h).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <mutex>
+
+#include "lshx.h"
+
+namespace lshx {
+
+// Thread-local error text returned by lshx_last_error().
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define LSHX_CUDA(expr)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (expr);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ::lshx::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                        \
+      return (e_ == cudaErrorMemoryAllocation) ? LSHX_ERR_OOM : LSHX_ERR_CUDA;            \
+    }                                                                                     \
+  } while (0)
+
+#define LSHX_REQUIRE(cond, ...)       \
+  do {                                \
+    if (!(cond)) {                    \
+      ::lshx::set_error(__VA_ARGS__); \
+      return LSHX_ERR_INVALID_ARG;    \
+    }                                 \
+  } while (0)
+
+// Device-side description of one hasher (what the kernels need).
+//
+// Column layout: the kernels compute one sign bit per COLUMN of a padded
+// projection matrix Rp[ncols_pad][dim].  Band b owns columns
+// [b*8*bpb, b*8*bpb + rows_per_band); the remaining columns of each band (when
+// rows_per_band is not a multiple of 8) and the tail padding are ZERO rows, so
+// their projection is exactly 0, `> 0` is false, and the packed byte stream of
+// the columns is bit-for-bit np.packbits(bitorder="little") per band
+// (reference lshrs/hash/lsh.py:204-211).
+struct HashShape {
+  int dim;
+  int num_bands;
+  int rows_per_band;
+  int bpb;        // bytes per band = ceil(rows_per_band / 8)
+  int sig_bytes;  // num_bands * bpb
+  int ncols;      // sig_bytes * 8
+  int ncols_pad;  // ncols rounded up to a multiple of 128
+  int dim_pad;    // dim rounded up to a multiple of 32 (K padding of the split copies)
+};
+
+// ---- hash kernels (hash_ffma.cu / hash_tc.cu) --------------------------------
+// Rp: [ncols_pad][dim] fp32 with zero padding rows.
+int launch_hash_ffma(const HashShape& s, const float* d_X, int64_t n, const float* d_Rp,
+                     uint8_t* d_out, uint8_t* d_zero_flag, cudaStream_t stream);
+
+struct TcPlan;  // opaque tcgen05 state (TMA descriptor of the split projections, ...)
+bool tc_shape_supported(const HashShape& s);
+int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out);
+void tc_plan_destroy(TcPlan* p);
+int launch_hash_tc(const HashShape& s, TcPlan* plan, const float* d_X, int64_t n, uint8_t* d_out,
+                   uint8_t* d_zero_flag, cudaStream_t stream);
+
+// ---- rerank kernel (rerank.cu) ------------------------------------------------
+struct RerankArgs {
+  const float* Q;
+  int64_t nq;
+  const float* V;
+  int64_t n_vectors;
+  const int64_t* offs;
+  const int64_t* ids;  // may be null
+  int dim;
+  int k;
+  double p;
+  int out_stride;
+  int32_t* out_pos;
+  float* out_score;
+  int32_t* out_count;
+  int32_t* out_zero;
+  float* all_scores;  // optional: every candidate's score (cosine_similarity)
+  int64_t max_cand;   // largest per-query candidate count (sizes the sort buffer)
+  bool select;        // false: scores only
+};
+int launch_rerank(const RerankArgs& a, cudaStream_t stream);
+
+}  // namespace lshx

@@ -1,0 +1,81 @@
+"""Bucket-storage protocol and an in-process implementation.
+
+The reference keeps buckets in Redis (``RedisStorage``, reference
+lshrs/storage/redis.py) and that component stays on the host UNCHANGED: pass a
+reference ``RedisStorage`` instance as ``LSHRS(storage=...)`` and it is used as
+is.  This module only states the five-method protocol ``LSHRS`` relies on and
+provides a dict-backed implementation for tests, benches and single-process
+use.  ``bucket_key`` reproduces the reference's key format byte for byte
+(redis.py:225) -- it is the only consumer of the packed band bytes.
+"""
+
+from __future__ import annotations
+
+import threading
+from collections.abc import Iterable
+from typing import Protocol, runtime_checkable
+
+BucketOperation = tuple[int, bytes, int]  # (band_id, band bytes, vector index), as in the reference
+
+__all__ = ["BucketOperation", "BucketStorage", "InMemoryStorage", "bucket_key"]
+
+
+def bucket_key(prefix: str, band_id: int, hash_val: bytes) -> str:
+    """``"{prefix}:{band_id}:bucket:{hex}"`` -- lower-case hex, byte 0 first."""
+    return f"{prefix}:{band_id}:bucket:{hash_val.hex()}"
+
+
+@runtime_checkable
+class BucketStorage(Protocol):
+    """What ``LSHRS`` needs from a bucket store (the public surface of RedisStorage it calls)."""
+
+    def batch_add(self, operations: list[BucketOperation]) -> None: ...
+
+    def get_bucket(self, band_id: int, hash_val: bytes) -> set[int]: ...
+
+    def remove_indices(self, indices: list[int]) -> None: ...
+
+    def clear(self) -> None: ...
+
+    def close(self) -> None: ...
+
+
+class InMemoryStorage:
+    """Thread-safe dict of sets keyed exactly like the Redis keys."""
+
+    def __init__(self, prefix: str = "lsh") -> None:
+        self.prefix = prefix
+        self._buckets: dict[str, set[int]] = {}
+        self._lock = threading.Lock()
+
+    def bucket_key(self, band_id: int, hash_val: bytes) -> str:
+        return bucket_key(self.prefix, band_id, hash_val)
+
+    def batch_add(self, operations: Iterable[BucketOperation]) -> None:
+        with self._lock:
+            for band_id, hash_val, index in operations:
+                self._buckets.setdefault(self.bucket_key(band_id, hash_val), set()).add(int(index))
+
+    def add_to_bucket(self, band_id: int, hash_val: bytes, index: int) -> None:
+        self.batch_add([(band_id, hash_val, index)])
+
+    def get_bucket(self, band_id: int, hash_val: bytes) -> set[int]:
+        with self._lock:
+            return set(self._buckets.get(self.bucket_key(band_id, hash_val), ()))
+
+    def remove_indices(self, indices: Iterable[int]) -> None:
+        drop = {int(i) for i in indices}
+        with self._lock:
+            for members in self._buckets.values():
+                members -= drop
+
+    def clear(self) -> None:
+        with self._lock:
+            self._buckets.clear()
+
+    def close(self) -> None:
+        pass
+
+    def __len__(self) -> int:
+        with self._lock:
+            return sum(1 for m in self._buckets.values() if m)

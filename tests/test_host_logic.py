@@ -1,0 +1,134 @@
+"""Host-side logic that needs no GPU: value types, storage, validation order, sharding plan."""
+
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from lshrs_b200 import LSHRS, HashSignatures, InMemoryStorage, LSHHasher, bucket_key, l2_norm
+from lshrs_b200._config.config import signatures_from_packed
+from lshrs_b200.sharding import shard_bounds
+
+
+def test_hash_signatures_normalizes_iterables():
+    # reference tests/test_lshrs.py:92-97
+    sig = HashSignatures((b"\x00\x01", bytearray(b"\x02\x03")))  # type: ignore[arg-type]
+    assert sig.as_tuple() == (b"\x00\x01", b"\x02\x03")
+    assert list(sig) == [b"\x00\x01", b"\x02\x03"]
+    assert len(sig) == 2 and sig[1] == b"\x02\x03"
+    assert hash(sig) == hash(HashSignatures((b"\x00\x01", b"\x02\x03")))
+    with pytest.raises(Exception):
+        sig.bands = ()  # frozen
+
+
+def test_signatures_from_packed_layout():
+    packed = np.arange(2 * 3 * 2, dtype=np.uint8).reshape(2, 3, 2)
+    sigs = signatures_from_packed(packed, 2)
+    assert sigs[0].as_tuple() == (b"\x00\x01", b"\x02\x03", b"\x04\x05")
+    assert sigs[1].as_tuple() == (b"\x06\x07", b"\x08\x09", b"\x0a\x0b")
+    assert HashSignatures.from_packed(packed[1].reshape(-1), 2) == sigs[1]
+
+
+@pytest.mark.parametrize("nb, r, dim", [(0, 1, 1), (1, 0, 1), (1, 1, 0)])
+def test_lsh_hasher_invalid_init_parameters(nb, r, dim):
+    # reference tests/test_lshrs.py:18-28
+    with pytest.raises(ValueError):
+        LSHHasher(num_bands=nb, rows_per_band=r, dim=dim)
+
+
+def test_hasher_projections_are_the_reference_stream():
+    from oracle import lshrs_oracle as oracle
+
+    h = LSHHasher(16, 16, 768, seed=42)
+    want = oracle.make_projections(16, 16, 768, 42)
+    assert len(h.projections) == 16
+    for a, b in zip(h.projections, want):
+        assert a.dtype == np.float32 and a.shape == (16, 768)
+        np.testing.assert_array_equal(a, b)
+    assert h.bytes_per_band == 2 and h.signature_bytes == 32
+    assert LSHHasher(16, 4, 128).signature_bytes == 16 and LSHHasher(3, 20, 5).bytes_per_band == 3
+
+
+def test_hasher_validation_runs_before_any_device_work():
+    h = LSHHasher(2, 3, 4)
+    with pytest.raises(ValueError):
+        h.hash_vector(np.arange(5, dtype=np.float32))
+    with pytest.raises(ValueError, match="2D"):
+        h.hash_batch(np.arange(3, dtype=np.float32))
+    with pytest.raises(ValueError):
+        h.hash_batch(np.ones((2, 5), dtype=np.float32))
+    assert h.hash_batch(np.empty((0, 4), dtype=np.float32)) == []
+    assert h.hash_batch_packed(np.empty((0, 4), dtype=np.float32)).shape == (0, 2, 1)
+
+
+def test_l2_norm():
+    # reference tests/test_lshrs.py:100-112
+    out = l2_norm([3.0, 4.0])
+    np.testing.assert_allclose(out, [0.6, 0.8], atol=1e-7)
+    assert out.dtype == np.float32
+    with pytest.raises(ValueError, match="zero vector"):
+        l2_norm(np.zeros(3))
+
+
+def test_in_memory_storage_and_bucket_key():
+    st = InMemoryStorage(prefix="lsh")
+    assert bucket_key("lsh", 5, b"\xab\xcd") == "lsh:5:bucket:abcd" == st.bucket_key(5, b"\xab\xcd")
+    st.batch_add([(0, b"\x01", 7), (0, b"\x01", 8), (1, b"\x01", 7)])
+    assert st.get_bucket(0, b"\x01") == {7, 8} and st.get_bucket(1, b"\x01") == {7}
+    assert st.get_bucket(2, b"\x01") == set()
+    st.remove_indices([7])
+    assert st.get_bucket(0, b"\x01") == {8} and st.get_bucket(1, b"\x01") == set()
+    st.clear()
+    assert st.get_bucket(0, b"\x01") == set()
+
+
+def _lsh(**kw):
+    args = dict(dim=32, num_perm=16, num_bands=4, rows_per_band=4, storage=InMemoryStorage())
+    args.update(kw)
+    return LSHRS(**args)
+
+
+def test_lshrs_constructor_validation():
+    # reference tests/test_core.py:16-35
+    with pytest.raises(ValueError, match="dimensionality"):
+        _lsh(dim=0)
+    with pytest.raises(ValueError, match="num_perm"):
+        _lsh(num_perm=0)
+    with pytest.raises(ValueError, match="buffer_size"):
+        _lsh(buffer_size=0)
+    with pytest.raises(ValueError, match="must equal num_perm"):
+        _lsh(num_bands=3, rows_per_band=4, num_perm=16)
+    auto = LSHRS(dim=768, num_perm=256, storage=InMemoryStorage())
+    assert (auto.stats()["num_bands"], auto.stats()["rows_per_band"]) == (16, 16)
+
+
+def test_lshrs_rejects_bad_input_before_hashing():
+    lsh = _lsh()
+    with pytest.raises(ValueError, match="non-negative"):
+        lsh.ingest(-1, np.ones(32, dtype=np.float32))
+    with pytest.raises(ValueError, match="Cannot index zero vector"):
+        lsh.ingest(0, np.zeros(32, dtype=np.float32))
+    with pytest.raises(ValueError, match="dimension"):
+        lsh.ingest(0, np.ones(31, dtype=np.float32))
+    with pytest.raises(ValueError, match="zero vector"):
+        lsh.get_top_k(np.zeros(32, dtype=np.float32))
+    with pytest.raises(ValueError, match="shape"):
+        lsh.index([0, 1], np.ones((2, 31), dtype=np.float32))
+    with pytest.raises(ValueError, match="does not match"):
+        lsh.index([0, 1, 2], np.ones((2, 32), dtype=np.float32))
+    with pytest.raises(RuntimeError, match="vector_fetch_fn"):
+        lsh.index([0, 1])
+    lsh.index([])  # no-op
+    assert lsh.stats()["dimension"] == 32
+
+
+def test_shard_bounds_cover_and_align():
+    for n in (0, 1, 127, 128, 129, 1000, 100_000, 12_500_001):
+        for world in (1, 2, 3, 4, 8):
+            b = shard_bounds(n, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(b, b[1:]):
+                assert hi == lo2 and lo <= hi
+            assert all(lo % 128 == 0 for lo, _ in b if lo < n)
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 128 + (128 - 1)
