@@ -1,0 +1,497 @@
+#!/usr/bin/env python
+"""Benchmark of the lshrs hot path on B200: vectors hashed/s (dim 768, 256 bits) and rerank queries/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One process per GPU; the work list is partitioned (weak scaling: every rank
+hashes its own resident shard of ``--rows`` vectors, 12.5 M = 100 M / 8 by
+default -- BASELINE.json config 2 at N = 8), the projection matrix is
+replicated, nothing is exchanged on the data path.  A "step" is one pass of the
+hot path over one resident shard: the projection kernel over every chunk of
+the shard plus the D2H of the signatures into pinned host memory, overlapped on
+a copy stream.  Timed with CUDA events on the launching stream, max over ranks.
+
+The JSON line carries, beside the contract keys:
+  roofline      dominant (projection) kernel: executed tensor flops / its own
+                CUDA-event time inside the timed region vs the measured peak
+  e2e           same metric through the C ABI with HOST pinned buffers (H2D of
+                the vectors and D2H of the signatures inside the timed region)
+  cpu_baseline  the oracle port of the reference's numpy path timed on this
+                box's host cores on a bounded sample (rank 0, N = 1 only)
+  parity        band-key comparison of the GPU output with the oracle on that sample
+  rerank        config 4 (8192 queries x 2000 candidates x 768, k=10 and p=0.2)
+``--impl reference`` times the reference's CPU algorithm (oracle port; the
+reference is pure Python and cannot travel to the GPU box) on bounded samples.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+DIM, NUM_BANDS, ROWS_PER_BAND, SEED = 768, 16, 16, 42
+NUM_PERM = NUM_BANDS * ROWS_PER_BAND
+SIG_BYTES = NUM_BANDS * ((ROWS_PER_BAND + 7) // 8)
+METRIC = "vectors hashed/sec (dim=768, num_perm=256)"
+UNIT = "vectors/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks() -> tuple[dict, str]:
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            d = json.loads(p.read_text())
+            if "hbm_gbs" in d and "bf16_tflops" in d:
+                d.setdefault("bf16_tflops_sustained", d["bf16_tflops"])
+                return d, "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# reference arm: the reference's CPU algorithm (oracle port) on this box's host cores
+# --------------------------------------------------------------------------------------
+
+def cpu_hash_sample(rows: int, seed: int = 0) -> np.ndarray:
+    return np.random.default_rng(seed).standard_normal((rows, DIM)).astype(np.float32)
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    from oracle import lshrs_oracle as oracle
+
+    projs = oracle.make_projections(NUM_BANDS, ROWS_PER_BAND, DIM, SEED)
+    sample = 16384
+    X = cpu_hash_sample(sample)
+    for _ in range(args.warmup):
+        oracle.hash_batch_packed(projs, X[:1024])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.hash_batch_packed(projs, X)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    # not reference code: one sgemm + packbits over every BLAS thread, for honesty
+    Xv = cpu_hash_sample(131072, seed=1)
+    oracle.hash_batch_vectorized(projs, Xv[:4096])
+    t1 = time.perf_counter()
+    oracle.hash_batch_vectorized(projs, Xv)
+    vec_value = Xv.shape[0] / (time.perf_counter() - t1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{sample} Gaussian vectors x {args.steps} steps through the oracle's "
+                                   "per-vector, per-band sgemv loop (the reference's LSHHasher.hash_batch path; "
+                                   "single Python thread by construction)",
+                         "host_cores": os.cpu_count(), "numpy": np.__version__,
+                         "vectorized_numpy_not_reference": {"value": vec_value, "unit": UNIT,
+                                                            "cores": len(os.sched_getaffinity(0))}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args) -> dict:
+    return {
+        "workload": f"LSHHasher dim={DIM} num_perm={NUM_PERM} ({NUM_BANDS}x{ROWS_PER_BAND}); "
+                    f"{args.rows} synthetic Gaussian float32 vectors resident per GPU "
+                    f"(BASELINE config 2: 100M vectors / 8 GPUs = 12.5M per GPU, weak scaling)",
+        "rows_per_gpu": args.rows, "dim": DIM, "num_perm": NUM_PERM, "signature_bytes": SIG_BYTES,
+        "chunk_rows": args.chunk, "e2e_rows_per_gpu": args.e2e_rows,
+        "l2": "inputs larger than L2 (38 GB resident shard, each row read once per step)",
+        "parallelism": f"row-sharded x{args.gpus}, projections replicated, no collective",
+    }
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+
+def run_b200(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from lshrs_b200 import LSHHasher, _native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    peaks, peak_src = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    hasher = LSHHasher(NUM_BANDS, ROWS_PER_BAND, DIM, seed=SEED, device=local)
+    if args.kernel != "auto":
+        hasher._ensure_handle()
+        hasher.set_kernel(args.kernel)
+
+    # ---- resident shard, generated on device (seeded per rank) --------------------------
+    rows, chunk = args.rows, args.chunk
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    X = torch.empty((rows, DIM), dtype=torch.float32, device=dev)
+    for r0 in range(0, rows, 1 << 20):
+        r1 = min(rows, r0 + (1 << 20))
+        X[r0:r1].normal_(generator=gen)
+    out_host = torch.empty((rows, SIG_BYTES), dtype=torch.uint8, pin_memory=True)
+    out_dev = [torch.empty((chunk, SIG_BYTES), dtype=torch.uint8, device=dev) for _ in range(2)]
+    chunks = [(r0, min(rows, r0 + chunk)) for r0 in range(0, rows, chunk)]
+    compute = torch.cuda.Stream(device=dev)
+    copy = torch.cuda.Stream(device=dev)
+
+    def one_step(kernel_events=None):
+        """Hash every chunk on `compute`, D2H each chunk's signatures on `copy` (double-buffered)."""
+        copied = [None, None]
+        for ci, (r0, r1) in enumerate(chunks):
+            slot = ci & 1
+            if copied[slot] is not None:
+                compute.wait_event(copied[slot])  # out_dev[slot] is free again
+            if kernel_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(compute)
+            hasher.hash_into(X[r0:r1], r1 - r0, out_dev[slot], x_on_device=True, out_on_device=True,
+                             stream=compute.cuda_stream)
+            done = torch.cuda.Event()
+            if kernel_events is not None:
+                e1.record(compute)
+                kernel_events.append((e0, e1, r1 - r0))
+            done.record(compute)
+            copy.wait_event(done)
+            with torch.cuda.stream(copy):
+                out_host[r0:r1].copy_(out_dev[slot][: r1 - r0], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            copied[slot] = ev
+        compute.wait_stream(copy)
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _native.launch_count()
+    kernel_events: list = []
+    start = torch.cuda.Event(enable_timing=True); stop = torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record(compute)
+    for _ in range(args.steps):
+        one_step(kernel_events)
+    stop.record(compute)
+    barrier()
+    elapsed_ms = max_ranks(start.elapsed_time(stop))
+    launches = _native.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in kernel_events)
+    kern_rows = sum(r for _, _, r in kernel_events)
+    value = rows * world * args.steps / (elapsed_ms * 1e-3)
+    kernel_name = hasher.last_kernel
+
+    # ---- e2e: host pinned buffers through the C ABI (H2D + kernel + D2H per step) --------
+    e2e_rows = args.e2e_rows
+    xh = torch.empty((e2e_rows, DIM), dtype=torch.float32, pin_memory=True)
+    xh.copy_(X[:e2e_rows])
+    oh = torch.empty((e2e_rows, SIG_BYTES), dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def e2e_step():
+        hasher.hash_into(xh, e2e_rows, oh, x_on_device=False, out_on_device=False)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    s2 = torch.cuda.Event(enable_timing=True); t2 = torch.cuda.Event(enable_timing=True)
+    s2.record()
+    for _ in range(args.steps):
+        e2e_step()
+    t2.record()
+    barrier()
+    e2e_ms = max_ranks(s2.elapsed_time(t2))
+    e2e_value = e2e_rows * world * args.steps / (e2e_ms * 1e-3)
+    # the e2e path must produce the same bytes as the resident path
+    same = bool(torch.equal(oh, out_host[:e2e_rows]))
+
+    # ---- roofline of the projection kernel ------------------------------------------------
+    ncols = SIG_BYTES * 8
+    useful_flop = 2.0 * DIM * ncols
+    mma_passes = 3 if kernel_name == "tcgen05" else 1
+    per_kernel_ms = kern_ms / max(1, len(kernel_events))
+    achieved_tflops = useful_flop * mma_passes * kern_rows / (kern_ms * 1e-3) / 1e12
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0  # dense TF32 = half of dense BF16 on the tensor pipe
+    roofline = {
+        "bound": "tensor", "kernel": f"hash_{kernel_name}",
+        "achieved": achieved_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / tf32_peak,
+        "traffic": None,
+        "peak_source": f"{peak_src}: bf16_tflops_sustained / 2 (TF32 dense rate)",
+        "flops_counted": f"{mma_passes} x 2*dim*ncols per vector ({'3xTF32 split: hi*hi + hi*lo + lo*hi' if mma_passes == 3 else 'FP32 FFMA, one pass'})",
+        "useful_tflops": useful_flop * kern_rows / (kern_ms * 1e-3) / 1e12,
+        "avg_launch_ms": per_kernel_ms, "launches_timed": len(kernel_events),
+        "kernel_share_of_step": kern_ms / (start.elapsed_time(stop)),
+        "hbm_gbs_achieved": (4.0 * DIM + SIG_BYTES) * kern_rows / (kern_ms * 1e-3) / 1e9,
+        "hbm_frac": (4.0 * DIM + SIG_BYTES) * kern_rows / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+    }
+
+    # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1 only) ---------------------
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import lshrs_oracle as oracle
+
+        projs = oracle.make_projections(NUM_BANDS, ROWS_PER_BAND, DIM, SEED)
+        sample = args.cpu_sample
+        idx = torch.linspace(0, rows - 1, sample, device=dev).long()
+        Xs = X[idx].cpu().numpy()
+        t0 = time.perf_counter()
+        ref = oracle.hash_batch_packed(projs, Xs)
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        oracle.hash_batch_vectorized(projs, Xs)
+        dtv = time.perf_counter() - t1
+        got = out_host[idx.cpu()].numpy().reshape(sample, NUM_BANDS, -1)
+        parity = oracle.compare_packed(got, ref, oracle.projection_margins(projs, Xs), 1e-5)
+        parity["sample_rows"] = sample
+        parity["e2e_equals_resident"] = same
+        cpu_baseline = {
+            "value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{sample} rows of the same shard through the oracle's per-vector, per-band sgemv loop "
+                      f"(reference LSHHasher.hash_batch path, single Python thread by construction), {dt:.1f} s",
+            "host_cores": os.cpu_count(), "numpy": np.__version__,
+            "vectorized_numpy_not_reference": {"value": sample / dtv, "unit": UNIT,
+                                               "cores": len(os.sched_getaffinity(0))},
+        }
+
+    # ---- rerank (config 4) ------------------------------------------------------------------
+    rerank = None
+    if not args.no_rerank:
+        del X, out_dev
+        torch.cuda.empty_cache()
+        rerank = run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "tf32x3" if kernel_name == "tcgen05" else "f32",
+            "data": "synthetic", "config": workload_config(args), "impl": "b200", "kernel": kernel_name,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_rows * DIM * 4,
+                    "d2h_bytes_per_step": e2e_rows * SIG_BYTES, "rows_per_step_per_gpu": e2e_rows,
+                    "ms_per_step": e2e_ms / args.steps,
+                    "api": "lshx_hash_batch(host pinned X -> host pinned signatures)"},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
+            "cpu_baseline": cpu_baseline, "parity": parity, "rerank": rerank,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> dict:
+    """BASELINE config 4: 8192 queries x 2000 candidates x 768 from a 1M-row corpus resident in HBM."""
+    import torch
+
+    from lshrs_b200 import _native
+    from lshrs_b200.utils.similarity import _get_reranker
+
+    N, nq, nc = args.corpus, args.queries, 2000
+    gen = torch.Generator(device=dev).manual_seed(1)
+    corpus = torch.empty((N, DIM), dtype=torch.float32, device=dev)
+    corpus.normal_(generator=gen)
+    Q = torch.empty((nq, DIM), dtype=torch.float32, device=dev).normal_(generator=gen)
+    # 2000 DISTINCT corpus rows per query: random start, random stride < N / nc
+    first = torch.randint(0, N, (nq, 1), generator=gen, device=dev, dtype=torch.int64)
+    stride = torch.randint(1, max(2, N // nc), (nq, 1), generator=gen, device=dev, dtype=torch.int64)
+    ids = ((first + stride * torch.arange(nc, device=dev, dtype=torch.int64)[None, :]) % N).contiguous()
+    offs = torch.arange(nq + 1, device=dev, dtype=torch.int64) * nc
+    rer = _get_reranker(DIM, dev.index)
+    lib = _native.lib()
+    out = {}
+    for tag, k, p in (("k10", 10, 0.0), ("p0.2", 0, 0.2)):
+        limit = k if k > 0 else int(np.ceil(nc * p))
+        pos = torch.empty((nq, limit), dtype=torch.int32, device=dev)
+        score = torch.empty((nq, limit), dtype=torch.float32, device=dev)
+        count = torch.empty(nq, dtype=torch.int32, device=dev)
+        zero = torch.empty(nq, dtype=torch.int32, device=dev)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+
+        def step():
+            _native.check(lib.lshx_rerank_topk(
+                rer._handle, Q.data_ptr(), nq, corpus.data_ptr(), N, offs.data_ptr(), ids.data_ptr(), nc,
+                k, p, limit, pos.data_ptr(), score.data_ptr(), count.data_ptr(), zero.data_ptr(), 1, stream))
+
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        s = torch.cuda.Event(enable_timing=True); t = torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.steps):
+            step()
+        t.record()
+        barrier()
+        ms = max_ranks(s.elapsed_time(t)) / args.steps
+        bytes_per_q = nc * (4 * DIM + 8) + 4 * DIM + 8 * limit
+        gbs = bytes_per_q * nq / (ms * 1e-3) / 1e9
+        # e2e: host queries / ids / results, corpus resident (on_device = 2)
+        Qh, idh, offh = Q.cpu().numpy(), ids.cpu().numpy().reshape(-1), offs.cpu().numpy()
+        for _ in range(2):
+            rer.topk(Qh, corpus, offh, idh, k=k, p=p, vectors_on_device=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ph, sh, ch, zh = rer.topk(Qh, corpus, offh, idh, k=k, p=p, vectors_on_device=True)
+        torch.cuda.synchronize()
+        e2e_ms = max_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        entry = {
+            "value": nq * world / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "results_per_query": limit,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "bytes_per_query": bytes_per_q},
+            "e2e": {"value": nq * world / (e2e_ms * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": int(Qh.nbytes + idh.nbytes + offh.nbytes),
+                    "d2h_bytes_per_step": int(ph.nbytes + sh.nbytes + ch.nbytes + zh.nbytes)},
+            "device_equals_e2e": bool(np.array_equal(ph, pos.cpu().numpy())),
+        }
+        if rank == 0 and world == 1 and not args.no_cpu:
+            from oracle import lshrs_oracle as oracle
+
+            nref = 64
+            Ch = corpus.cpu().numpy()
+            t1 = time.perf_counter()
+            bad = 0
+            for i in range(nref):
+                ref = oracle.top_k_cosine(Qh[i], Ch[idh[i * nc:(i + 1) * nc]], k=limit)
+                got_pos = ph[i, :limit]
+                ref_scores = np.array([sc for _, sc in ref])
+                if not np.allclose(sh[i, :limit], ref_scores, atol=1e-5, rtol=0):
+                    bad += 1
+                elif set(got_pos.tolist()) != {pp for pp, _ in ref}:
+                    bad += 1
+            dt = time.perf_counter() - t1
+            entry["cpu_baseline"] = {"value": nref / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+                                     "sample": f"{nref} queries through the oracle's top_k_cosine"}
+            entry["parity"] = {"queries_checked": nref, "mismatching_queries": bad, "score_tol": 1e-5}
+            del Ch
+        out[tag] = entry
+    out["config"] = {"workload": f"top_k_cosine rerank: {nq} queries x {nc} candidates, dim={DIM}, corpus {N} rows "
+                                 "resident in HBM, CSR int64 candidate ids", "l2": "6.1 MB of gathers per query, "
+                                 f"{nq * nc * DIM * 4 / 1e9:.1f} GB per step (larger than L2)"}
+    return out
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
+    ap.add_argument("--rows", type=int, default=12_500_000, help="resident vectors per GPU")
+    ap.add_argument("--chunk", type=int, default=1_562_500, help="rows per kernel launch / D2H copy")
+    ap.add_argument("--e2e-rows", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample", type=int, default=65_536)
+    ap.add_argument("--kernel", choices=("auto", "ffma", "tcgen05"), default="auto")
+    ap.add_argument("--corpus", type=int, default=1_000_000)
+    ap.add_argument("--queries", type=int, default=8192)
+    ap.add_argument("--no-rerank", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.steps = max(1, args.steps)
+    args.warmup = max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,236 @@
+"""GPU parity tests of the hash path (through the C ABI) against the oracle and the golden vectors.
+
+Bar (BASELINE.json north_star): band keys bit-exact for every projection whose
+|x.r| exceeds 1e-5 * ||x|| * ||r||; flips inside that margin are counted and
+reported, padding bits are always zero.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import pytest
+from conftest import hash_case_names, load_golden, projections_for
+
+from oracle import lshrs_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = ("ffma", "tcgen05")
+REL_MARGIN = 1e-5  # north_star exempt margin
+
+
+def _hasher(nb, r, dim, seed=42, kernel="ffma"):
+    from lshrs_b200 import LSHHasher, LshxError
+
+    h = LSHHasher(nb, r, dim, seed=seed)
+    try:
+        h._ensure_handle()
+        h.set_kernel(kernel)
+    except LshxError as exc:
+        if kernel == "tcgen05" and "does not support" in str(exc):
+            pytest.skip(f"tcgen05 kernel does not take this shape: {exc}")
+        raise
+    return h
+
+
+def _assert_parity(got, X, projs, what=""):
+    want = oracle.hash_batch_vectorized(projs, X)
+    rep = oracle.compare_packed(got, want, oracle.projection_margins(projs, X), REL_MARGIN)
+    assert rep["flips_outside_margin"] == 0, (what, rep)
+    assert rep["nonzero_pad_bits"] == 0, (what, rep)
+    # flips inside the margin must be rare: no more than the bits that lie inside it
+    assert rep["flips_inside_margin"] <= rep["bits_inside_margin"], (what, rep)
+    return rep
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("name", hash_case_names())
+def test_golden_signatures(name, kernel):
+    case = load_golden(name)
+    nb, r, dim, seed = (int(case[k]) for k in ("num_bands", "rows_per_band", "dim", "seed"))
+    projs = projections_for(case)
+    h = _hasher(nb, r, dim, seed, kernel)
+    got = h.hash_batch_packed(case["X"])
+    assert h.last_kernel == kernel
+    assert got.shape == case["signatures"].shape and got.dtype == np.uint8
+    finite = np.isfinite(case["X"]).all(axis=1)
+    rep = oracle.compare_packed(got[finite], case["signatures"][finite],
+                                oracle.projection_margins(projs, case["X"][finite]), REL_MARGIN)
+    assert rep["flips_outside_margin"] == 0 and rep["nonzero_pad_bits"] == 0, rep
+    if name.startswith("hash_kat") or name.startswith("hash_tiny"):
+        np.testing.assert_array_equal(got, case["signatures"])  # well-conditioned: byte for byte
+    # NaN rows: every projection is NaN, `> 0` is False -> all-zero bytes like the reference
+    nan_rows = np.isnan(case["X"]).all(axis=1)
+    assert not got[nan_rows].any()
+    # object API == packed API
+    sigs = h.hash_batch(case["X"])
+    assert [s.as_tuple() for s in sigs] == [tuple(bytes(b) for b in row) for row in got]
+    first = h.hash_vector(case["X"][0])
+    assert first.as_tuple() == sigs[0].as_tuple()
+    assert all(isinstance(b, bytes) and len(b) == math.ceil(r / 8) for b in first)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize(
+    "nb, r, dim, n, dist",
+    [
+        (16, 16, 768, 20_000, "gauss"),     # BASELINE config 1 / 2 shape
+        (16, 32, 1536, 4_096, "gauss"),     # config 3 shape
+        (16, 4, 128, 50_000, "sift"),       # config 5 shape (non-negative SIFT-like)
+        (8, 16, 128, 10_000, "gauss"),
+        (128, 8, 64, 3_000, "gauss"),       # 1024 bits: many column tiles
+        (5, 20, 100, 2_000, "gauss"),       # ragged rows_per_band, dim % 32 != 0
+        (3, 5, 7, 1_000, "gauss"),          # unaligned dim (no float4 path)
+    ],
+)
+def test_parity_with_oracle(nb, r, dim, n, dist, kernel):
+    rng = np.random.default_rng(1234)
+    if dist == "gauss":
+        X = rng.standard_normal((n, dim)).astype(np.float32)
+    else:
+        X = np.minimum(255.0, np.floor(np.abs(rng.standard_normal((n, dim))) * 40.0)).astype(np.float32)
+    h = _hasher(nb, r, dim, 42, kernel)
+    got = h.hash_batch_packed(X)
+    rep = _assert_parity(got, X, h.projections, f"{nb}x{r}x{dim}")
+    # the faithful per-vector reference loop on a slice (one sgemv per band, lsh.py:200)
+    sl = slice(0, 256)
+    rep2 = oracle.compare_packed(got[sl], oracle.hash_batch_packed(h.projections, X[sl]),
+                                 oracle.projection_margins(h.projections, X[sl]), REL_MARGIN)
+    assert rep2["flips_outside_margin"] == 0, rep2
+    print(f"[parity {kernel} {nb}x{r} dim={dim} n={n}] {rep}")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 255, 257, 1000])
+def test_ragged_batch_sizes(n, kernel):
+    h = _hasher(16, 16, 768, 42, kernel)
+    X = np.random.default_rng(n).standard_normal((n, 768)).astype(np.float32)
+    _assert_parity(h.hash_batch_packed(X), X, h.projections, f"n={n}")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_zero_flag_is_prepare_vector_test(kernel):
+    h = _hasher(4, 4, 32, 42, kernel)
+    X = np.random.default_rng(0).standard_normal((300, 32)).astype(np.float32)
+    X[3] = 0.0
+    X[17] = 1e-9
+    X[40] = 0.0
+    X[40, 5] = 2e-8           # above atol: not a zero vector
+    X[41] = 0.0
+    X[41, 31] = np.nan        # np.allclose is False for NaN
+    X[299] = -1e-8            # exactly atol: zero vector
+    sig, flag = h.hash_batch_packed(X, return_zero_flag=True)
+    want = np.array([oracle.is_zero_vector(x) for x in X], dtype=np.uint8)
+    np.testing.assert_array_equal(flag, want)
+    assert flag[[3, 17, 299]].all() and not flag[[40, 41]].any()
+    assert not sig[3].any()   # zero vector straight into the hasher -> all-zero bytes, no error
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_device_resident_path_and_properties(kernel):
+    """Size-independent properties at a size the oracle would not finish: 1M x 768."""
+    import torch
+
+    h = _hasher(16, 16, 768, 42, kernel)
+    n = 1_000_000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((n, 768), generator=g, device="cuda", dtype=torch.float32)
+    s1 = h.hash_device(x)
+    torch.cuda.synchronize()
+    assert s1.shape == (n, 16, 2) and s1.dtype == torch.uint8
+    # determinism
+    assert torch.equal(s1, h.hash_device(x))
+    # positive power-of-two scaling is exact in fp32 -> identical keys
+    assert torch.equal(s1, h.hash_device(x * 4.0))
+    # row permutation commutes with hashing
+    perm = torch.randperm(n, device="cuda", generator=g)
+    assert torch.equal(h.hash_device(x[perm].contiguous()), s1[perm])
+    # negation complements every bit whose projection is non-zero: popcount(s ^ s_neg) ~ all 256 bits
+    sneg = h.hash_device(-x)
+    # a bit cannot be set for x and for -x (up to near-zero projections inside the exempt margin)
+    both = int((s1 & sneg).count_nonzero())
+    assert both <= n * 256 * 1e-5, both
+    neither = int(torch.bitwise_not(s1 | sneg).count_nonzero())
+    assert neither <= n * 256 * 1e-5, neither
+    # ~50% of bits set on Gaussian data
+    sample = s1[:4096].cpu().numpy()
+    frac = np.unpackbits(sample).mean()
+    assert 0.49 < frac < 0.51, frac
+    # a sampled slice against the oracle
+    idx = np.random.default_rng(0).choice(n, 2048, replace=False)
+    Xs = x[torch.from_numpy(idx).cuda()].cpu().numpy()
+    _assert_parity(s1.cpu().numpy()[idx], Xs, h.projections, "sample of 1M")
+    # host-out path from a device input equals the device output
+    out = np.empty((n, 32), dtype=np.uint8)
+    h.hash_into(x, n, out, x_on_device=True, out_on_device=False)
+    np.testing.assert_array_equal(out.reshape(n, 16, 2), s1.cpu().numpy())
+
+
+def test_kernels_agree_with_each_other():
+    X = np.random.default_rng(5).standard_normal((5000, 768)).astype(np.float32)
+    a = _hasher(16, 16, 768, 42, "ffma").hash_batch_packed(X)
+    b = _hasher(16, 16, 768, 42, "tcgen05").hash_batch_packed(X)
+    projs = oracle.make_projections(16, 16, 768, 42)
+    rep = oracle.compare_packed(a, b, oracle.projection_margins(projs, X), REL_MARGIN)
+    assert rep["flips_outside_margin"] == 0, rep
+
+
+def test_projections_rebinding_reuploads():
+    # LSHRS.load_from_disk / __setstate__ assign hasher.projections (reference main.py:981, 1044)
+    h = _hasher(4, 8, 16, seed=1)
+    X = np.random.default_rng(0).standard_normal((64, 16)).astype(np.float32)
+    before = h.hash_batch_packed(X)
+    other = oracle.make_projections(4, 8, 16, seed=2)
+    h.projections = other
+    after = h.hash_batch_packed(X)
+    np.testing.assert_array_equal(after, oracle.hash_batch_vectorized(other, X))
+    assert not np.array_equal(before, after)
+
+
+def test_same_seed_same_signatures_different_seed_differs():
+    # reference tests/test_core.py:392-414
+    X = np.random.default_rng(0).standard_normal((8, 32)).astype(np.float32)
+    a = _hasher(4, 4, 32, seed=42).hash_batch(X)
+    b = _hasher(4, 4, 32, seed=42).hash_batch(X)
+    c = _hasher(4, 4, 32, seed=43).hash_batch(X)
+    assert [s.as_tuple() for s in a] == [s.as_tuple() for s in b]
+    assert [s.as_tuple() for s in a] != [s.as_tuple() for s in c]
+
+
+def test_project_and_pack_single_band():
+    h = _hasher(2, 10, 12, seed=3)
+    v = np.random.default_rng(1).standard_normal(12).astype(np.float32)
+    for proj in h.projections:
+        assert h._project_and_pack(proj, v) == oracle.project_and_pack(proj, v)
+
+
+def test_hashing_is_reentrant_from_threads():
+    # reference tests/test_concurrency.py: many threads call ingest() -> hash_vector concurrently
+    import threading
+
+    h = _hasher(4, 4, 32)
+    X = np.random.default_rng(0).standard_normal((100, 32)).astype(np.float32)
+    want = [s.as_tuple() for s in h.hash_batch(X)]
+    got: list = [None] * 100
+
+    def work(t):
+        for i in range(t * 10, t * 10 + 10):
+            got[i] = h.hash_vector(X[i]).as_tuple()
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(10)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert got == want
+
+
+def test_sharded_hasher_uses_every_visible_gpu():
+    from lshrs_b200.sharding import ShardedHasher
+
+    sh = ShardedHasher(16, 16, 768, seed=42)
+    X = np.random.default_rng(2).standard_normal((3000, 768)).astype(np.float32)
+    got = sh.hash_batch_packed(X)
+    _assert_parity(got, X, sh.projections, "sharded")
