@@ -26,9 +26,10 @@
  *     serialised by an internal mutex (the reference hasher is called from
  *     many Python threads, tests/test_concurrency.py:31-42); use one handle
  *     per GPU for multi-GPU sharding.
- *   - `stream` is a cudaStream_t passed as void* (NULL = the handle's own
- *     stream).  Calls taking HOST buffers are synchronous; calls whose buffers
- *     are all DEVICE pointers only enqueue work on `stream`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the CUDA default
+ *     stream, which is also torch's default stream).  Calls taking HOST
+ *     buffers are synchronous; calls whose buffers are all DEVICE pointers
+ *     only enqueue work on `stream`.
  *   - there is NO CPU fallback: without a usable sm_100 device *_create fails.
  */
 #ifndef LSHX_H_

@@ -1,12 +1,557 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 projection-and-sign kernel (sm_100a): 3xTF32 split, TMA-staged, accumulators in TMEM.
+//
+// Replaces LSHHasher._project_and_pack (reference lshrs/hash/lsh.py:200-211) for a whole
+// batch, like hash_ffma.cu, but on the 5th-generation tensor cores:
+//
+//     x = x_hi + x_lo, r = r_hi + r_lo   (hi = round-to-nearest TF32, lo = TF32 of the residual)
+//     x.r ~= x_lo.r_hi + x_hi.r_lo + x_hi.r_hi      (three kind::tf32 MMAs, fp32 accumulate)
+//
+// which keeps ~22 significand bits per operand (the dropped x_lo.r_lo term and the rounding of
+// the lo parts are each <= 2^-22 relative), i.e. the accuracy of an fp32 sgemm with a different
+// summation order -- far inside the 1e-5 relative margin the parity contract allows, where
+// single-pass TF32 is not.
+//
+// Data flow per CTA (persistent, one CTA per SM, 384 threads):
+//
+//   warp 0      TMA producer: X tile chunks (128 rows x 32 floats, SWIZZLE_128B) and the matching
+//               chunks of the pre-split projections R_hi / R_lo (128 columns x 32 floats each)
+//   warps 4-7   converters: thread t owns row t of the tile; reads its 128 B of the X chunk from
+//               shared memory, splits hi/lo, writes them to TMEM with tcgen05.st (A operand lives
+//               in TMEM, so the MMA never re-reads X from shared memory); fuses the zero-vector
+//               test of LSHRS._prepare_vector (reference lshrs/core/main.py:1083)
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8,
+//               A from TMEM, B (projection chunk) from shared memory via a SWIZZLE_128B descriptor
+//   warps 8-11  epilogue: tcgen05.ld the fp32 accumulators, strict `> 0`, one bit per column into
+//               per-row words, 16 B of signature per 128 columns, coalesced store
+//   warp 2      TMEM allocation
+//
+// TMEM (512 columns): accumulators in columns [0,256) (two 128-column tiles, or two stages of one
+// tile), A-operand stages in [256,512): 4 stages x (32 hi + 32 lo) columns.
+// Shared memory: 4 X stages x 16 KB + 4 projection stages x 32 KB = 192 KB.
+
+#include <cstdio>
+
 #include "lshx_common.cuh"
+
 namespace lshx {
-struct TcPlan {};
-bool tc_shape_supported(const HashShape&) { return false; }
-int tc_plan_create(const HashShape&, const float*, TcPlan** out) { *out = nullptr; return LSHX_OK; }
-void tc_plan_destroy(TcPlan*) {}
-int launch_hash_tc(const HashShape&, TcPlan*, const float*, int64_t, uint8_t*, uint8_t*, cudaStream_t) {
-  set_error("tcgen05 kernel not built");
-  return LSHX_ERR_INVALID_ARG;
+
+namespace {
+
+constexpr int TC_THREADS = 384;
+constexpr int TM = 128;          // rows per tile
+constexpr int TK = 32;           // floats per K chunk (128 B: one SWIZZLE_128B row)
+constexpr int TN = 128;          // columns per MMA / per projection stage
+constexpr int XS = 4;            // X stages
+constexpr int BS = 4;            // projection stages
+constexpr int AS = 4;            // A-operand TMEM stages
+constexpr uint32_t X_STAGE_BYTES = TM * TK * 4;        // 16384
+constexpr uint32_t B_HALF_BYTES = TN * TK * 4;         // 16384 (hi or lo)
+constexpr uint32_t B_STAGE_BYTES = 2 * B_HALF_BYTES;   // 32768
+constexpr uint32_t SMEM_BYTES = XS * X_STAGE_BYTES + BS * B_STAGE_BYTES;  // 196608
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t A_COL0 = 256;
+constexpr uint32_t A_STAGE_COLS = 64;
+
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
+                           ((uint32_t)(TM >> 4) << 24);
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
 }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst,
+                                            int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]; kind::tf32, M=128 N=128 K=8
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B,
+// 8-row swizzle atoms 1024 B apart (SBO), LBO unused for swizzled K-major, version 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+
+// round-to-nearest (ties away) to TF32, as cvt.rna.tf32.f32 does, with integer ops
+__device__ __forceinline__ uint32_t tf32_rna(uint32_t u) { return (u + 0x1000u) & 0xFFFFE000u; }
+
+struct Ring {  // stage index + phase bit of one mbarrier ring
+  uint32_t idx = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n) {
+    if (++idx == n) {
+      idx = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+struct TcParams {
+  int64_t n;        // rows
+  int kc;           // K chunks = dim_pad / 32
+  int nt;           // 128-column tiles per pass (1 or 2)
+  int npass;        // passes over X (ncols_pad / (128 * nt))
+  int64_t mtiles;   // ceil(n / 128)
+  int sig_bytes;
+  int out_vec_ok;   // 16-byte stores allowed
+  uint8_t* out;
+  uint8_t* zero_flag;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_rhi,
+               const __grid_constant__ CUtensorMap tm_rlo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[XS * 2 + BS * 2 + AS * 2 + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024 B alignment
+  const uint32_t x_smem = smem_base;
+  const uint32_t b_smem = smem_base + XS * X_STAGE_BYTES;
+  const uint32_t bar0 = smem_u32(bars);
+  auto x_full = [&](uint32_t i) { return bar0 + 8u * i; };
+  auto x_empty = [&](uint32_t i) { return bar0 + 8u * (XS + i); };
+  auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS + i); };
+  auto b_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS + BS + i); };
+  auto a_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS + 2 * BS + i); };
+  auto a_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS + 2 * BS + AS + i); };
+  auto d_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS + 2 * BS + 2 * AS + i); };
+  auto d_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS + 2 * BS + 2 * AS + 2 + i); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t dstages = (p.nt == 1) ? 2u : 1u;
+  const int64_t work_items = p.mtiles * p.npass;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_rhi);
+    tma_prefetch_desc(&tm_rlo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t i = 0; i < XS; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 4); }
+    for (uint32_t i = 0; i < BS; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (uint32_t i = 0; i < AS; ++i) { mbar_init(a_full(i), 4); mbar_init(a_empty(i), 1); }
+    for (uint32_t i = 0; i < 2; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      Ring xr, br;
+      for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+        const int64_t mt = w / p.npass;
+        const int pass = (int)(w % p.npass);
+        const int row0 = (int)(mt * TM);
+        for (int kc = 0; kc < p.kc; ++kc) {
+          mbar_wait(x_empty(xr.idx), xr.phase ^ 1);
+          mbar_arrive_expect_tx(x_full(xr.idx), X_STAGE_BYTES);
+          tma_load_2d(&tm_x, x_full(xr.idx), x_smem + xr.idx * X_STAGE_BYTES, kc * TK, row0);
+          xr.advance(XS);
+          for (int j = 0; j < p.nt; ++j) {
+            const int col0 = (pass * p.nt + j) * TN;
+            mbar_wait(b_empty(br.idx), br.phase ^ 1);
+            mbar_arrive_expect_tx(b_full(br.idx), B_STAGE_BYTES);
+            const uint32_t dst = b_smem + br.idx * B_STAGE_BYTES;
+            tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK, col0);
+            tma_load_2d(&tm_rlo, b_full(br.idx), dst + B_HALF_BYTES, kc * TK, col0);
+            br.advance(BS);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      Ring ar, br, dr;
+      for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+        mbar_wait(d_empty(dr.idx), dr.phase ^ 1);  // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + dr.idx * TN;  // dstages == 2 only when nt == 1
+        for (int kc = 0; kc < p.kc; ++kc) {
+          mbar_wait(a_full(ar.idx), ar.phase);
+          const uint32_t a_hi = tmem_base + A_COL0 + ar.idx * A_STAGE_COLS;
+          const uint32_t a_lo = a_hi + 32;
+          for (int j = 0; j < p.nt; ++j) {
+            mbar_wait(b_full(br.idx), br.phase);
+            tc_fence_after();
+            const uint32_t bs = b_smem + br.idx * B_STAGE_BYTES;
+            const uint64_t desc_hi = make_b_desc(bs);
+            const uint64_t desc_lo = make_b_desc(bs + B_HALF_BYTES);
+            const uint32_t d = d_base + j * TN;
+#pragma unroll
+            for (int s = 0; s < TK / 8; ++s) {
+              // +32 B per K step inside the 128 B swizzle row: start-address field += 2
+              const uint64_t bh = desc_hi + (uint64_t)(2 * s);
+              const uint64_t bl = desc_lo + (uint64_t)(2 * s);
+              tc_mma_ts(d, a_lo + 8 * s, bh, (kc > 0 || s > 0) ? 1u : 0u);  // small terms first
+              tc_mma_ts(d, a_hi + 8 * s, bl, 1u);
+              tc_mma_ts(d, a_hi + 8 * s, bh, 1u);
+            }
+            tc_commit(b_empty(br.idx));
+            br.advance(BS);
+          }
+          tc_commit(a_empty(ar.idx));
+          ar.advance(AS);
+        }
+        tc_commit(d_full(dr.idx));
+        dr.advance(dstages);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converters: X fp32 (smem) -> hi/lo TF32 (TMEM) =====================
+    const int t = (warp - 4) * 32 + lane;                 // row within the tile == TMEM lane
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    Ring xr, ar;
+    for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+      const int64_t mt = w / p.npass;
+      const int pass = (int)(w % p.npass);
+      bool viol = false;  // some |x| > 1e-8 (or NaN): not a zero vector
+      for (int kc = 0; kc < p.kc; ++kc) {
+        mbar_wait(x_full(xr.idx), xr.phase);
+        const uint32_t row = x_smem + xr.idx * X_STAGE_BYTES + (uint32_t)t * 128u;
+        mbar_wait(a_empty(ar.idx), ar.phase ^ 1);
+        tc_fence_after();
+        const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {   // two halves of 16 floats keep the register count down
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int chunk = h * 4 + c;                       // logical 16 B chunk of the row
+            const uint32_t addr = row + (uint32_t)((chunk ^ (t & 7)) << 4);  // SWIZZLE_128B
+            float4 v;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                         : "r"(addr));
+            const float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float x = f[e];
+              viol |= !(fabsf(x) <= 1e-8f);
+              const uint32_t hu = tf32_rna(__float_as_uint(x));
+              const float hf = __uint_as_float(hu);
+              // residual is exact in fp32; an infinite hi has no residual (inf - inf would be NaN)
+              const float lf = (fabsf(hf) == INFINITY) ? 0.f : (x - hf);
+              hi[c * 4 + e] = hu;
+              lo[c * 4 + e] = tf32_rna(__float_as_uint(lf));
+            }
+          }
+          tc_st16(a_dst + h * 16, hi);
+          tc_st16(a_dst + 32 + h * 16, lo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(a_full(ar.idx));
+          mbar_arrive(x_empty(xr.idx));
+        }
+        xr.advance(XS);
+        ar.advance(AS);
+      }
+      if (p.zero_flag != nullptr && pass == 0) {
+        const int64_t m = mt * TM + t;
+        if (m < p.n) p.zero_flag[m] = viol ? 0 : 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: accumulators -> sign bits -> signature bytes ==============
+    const int t = (warp - 8) * 32 + lane;
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    Ring dr;
+    for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+      const int64_t mt = w / p.npass;
+      const int pass = (int)(w % p.npass);
+      mbar_wait(d_full(dr.idx), dr.phase);
+      tc_fence_after();
+      uint32_t words[8];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t word = 0;
+          if (j < p.nt) {
+            uint32_t v[32];
+            tc_ld32(tmem_base + lane_field + dr.idx * TN + j * TN + c * 32, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) word |= (__uint_as_float(v[i]) > 0.f ? 1u : 0u) << i;
+          }
+          words[j * 4 + c] = word;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d_empty(dr.idx));
+      dr.advance(dstages);
+
+      const int64_t m = mt * TM + t;
+      if (m < p.n) {
+        const int byte0 = pass * p.nt * 16;  // 16 signature bytes per 128 columns
+        uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + byte0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if (j < p.nt) {
+            const int b = byte0 + j * 16;
+            if (p.out_vec_ok && b + 16 <= p.sig_bytes) {
+              *reinterpret_cast<uint4*>(dst + j * 16) =
+                  make_uint4(words[j * 4], words[j * 4 + 1], words[j * 4 + 2], words[j * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                if (b + q < p.sig_bytes) dst[j * 16 + q] = (uint8_t)(words[j * 4 + (q >> 2)] >> (8 * (q & 3)));
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// Rp [ncols_pad][dim] fp32 -> Rhi / Rlo [ncols_pad][dim_pad] TF32-rounded, zero K padding
+__global__ void split_projections_kernel(const float* __restrict__ Rp, float* __restrict__ hi,
+                                         float* __restrict__ lo, int ncols_pad, int dim, int dim_pad) {
+  const int64_t total = (int64_t)ncols_pad * dim_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / dim_pad), k = (int)(i % dim_pad);
+    float h = 0.f, l = 0.f;
+    if (k < dim) {
+      const float r = Rp[(int64_t)row * dim + k];
+      h = __uint_as_float(tf32_rna(__float_as_uint(r)));
+      const float res = (fabsf(h) == INFINITY) ? 0.f : (r - h);
+      l = __uint_as_float(tf32_rna(__float_as_uint(res)));
+    }
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* sym = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess || sym == nullptr) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  fn = reinterpret_cast<EncodeTiledFn>(sym);
+  return fn;
+}
+
+// 2-D row-major fp32 tensor [rows][cols], box = 32 floats x 128 rows, SWIZZLE_128B, zero OOB fill
+int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
+             CUtensorMapL2promotion promo) {
+  EncodeTiledFn enc = get_encode_fn();
+  LSHX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {pitch_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)TM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu pitch %llu)", (int)rc,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)pitch_bytes);
+    return LSHX_ERR_CUDA;
+  }
+  return LSHX_OK;
+}
+
+}  // namespace
+
+struct TcPlan {
+  float* d_hi = nullptr;
+  float* d_lo = nullptr;
+  CUtensorMap tm_rhi, tm_rlo;
+  int num_sms = 0;
+};
+
+bool tc_shape_supported(const HashShape& s) {
+  // TMA needs a 16-byte row pitch for X; everything else is padded by the plan
+  return s.dim % 4 == 0 && get_encode_fn() != nullptr;
+}
+
+int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
+  *out = nullptr;
+  TcPlan* pl = new TcPlan();
+  const size_t bytes = (size_t)s.ncols_pad * s.dim_pad * sizeof(float);
+  auto fail = [&](int code) {
+    tc_plan_destroy(pl);
+    return code;
+  };
+  if (cudaMalloc(&pl->d_hi, bytes) != cudaSuccess || cudaMalloc(&pl->d_lo, bytes) != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes for the split projections failed", bytes);
+    (void)cudaGetLastError();
+    return fail(LSHX_ERR_OOM);
+  }
+  split_projections_kernel<<<256, 256>>>(d_Rp, pl->d_hi, pl->d_lo, s.ncols_pad, s.dim, s.dim_pad);
+  count_launch();
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("split_projections_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(LSHX_ERR_CUDA);
+  }
+  const uint64_t pitch = (uint64_t)s.dim_pad * sizeof(float);
+  int rc = make_map(&pl->tm_rhi, pl->d_hi, (uint64_t)s.ncols_pad, (uint64_t)s.dim_pad, pitch,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc != LSHX_OK) return fail(rc);
+  rc = make_map(&pl->tm_rlo, pl->d_lo, (uint64_t)s.ncols_pad, (uint64_t)s.dim_pad, pitch,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc != LSHX_OK) return fail(rc);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaFuncSetAttribute(hash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(SMEM_BYTES + 1024)) != cudaSuccess) {
+    set_error("cannot reserve %u bytes of shared memory for the tcgen05 kernel", SMEM_BYTES + 1024);
+    (void)cudaGetLastError();
+    return fail(LSHX_ERR_CUDA);
+  }
+  *out = pl;
+  return LSHX_OK;
+}
+
+void tc_plan_destroy(TcPlan* p) {
+  if (!p) return;
+  if (p->d_hi) cudaFree(p->d_hi);
+  if (p->d_lo) cudaFree(p->d_lo);
+  delete p;
+}
+
+int launch_hash_tc(const HashShape& s, TcPlan* plan, const float* d_X, int64_t n, uint8_t* d_out,
+                   uint8_t* d_zero_flag, cudaStream_t stream) {
+  if (n <= 0) return LSHX_OK;
+  LSHX_REQUIRE((reinterpret_cast<uintptr_t>(d_X) & 15) == 0, "tcgen05 kernel needs 16-byte aligned vectors");
+  LSHX_REQUIRE(n < (1ll << 31), "hash batch of %lld rows exceeds one launch", (long long)n);
+  CUtensorMap tm_x;
+  int rc = make_map(&tm_x, d_X, (uint64_t)n, (uint64_t)s.dim, (uint64_t)s.dim * sizeof(float),
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  if (rc != LSHX_OK) return rc;
+  TcParams p;
+  p.n = n;
+  p.kc = s.dim_pad / TK;
+  const int ntiles = s.ncols_pad / TN;
+  p.nt = (ntiles % 2 == 0) ? 2 : 1;
+  p.npass = ntiles / p.nt;
+  p.mtiles = (n + TM - 1) / TM;
+  p.sig_bytes = s.sig_bytes;
+  p.out_vec_ok = (s.sig_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) ? 1 : 0;
+  p.out = d_out;
+  p.zero_flag = d_zero_flag;
+  const int64_t work = p.mtiles * p.npass;
+  const unsigned grid = (unsigned)(work < plan->num_sms ? work : plan->num_sms);
+  hash_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rlo, p);
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
+
 }  // namespace lshx

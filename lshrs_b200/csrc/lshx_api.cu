@@ -239,8 +239,7 @@ extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_
 
   // ---- everything on the device: one asynchronous launch ----------------------------
   if (x_is_device && out_is_device) {
-    cudaStream_t st = user ? user : h->streams[0];
-    return launch_hash(h, X, n, out, zero_flag, st);
+    return launch_hash(h, X, n, out, zero_flag, user);  // NULL = the default stream
   }
 
   // ---- at least one side on the host: chunked, two streams, synchronous -----------
@@ -261,8 +260,8 @@ extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_
     // inputs were produced on the caller's stream: order our streams after it
     LSHX_CUDA(cudaEventRecord(h->ev_in, user));
     for (int i = 0; i < 2; ++i) LSHX_CUDA(cudaStreamWaitEvent(h->streams[i], h->ev_in, 0));
-  } else if (user) {
-    LSHX_CUDA(cudaStreamSynchronize(user));
+  } else {
+    LSHX_CUDA(cudaStreamSynchronize(user));  // host inputs: nothing to order, just drain the caller's stream
   }
   int slot = 0;
   for (int64_t r0 = 0; r0 < n; r0 += chunk, slot ^= 1) {
@@ -409,7 +408,7 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
     a.out_pos = out_pos; a.out_score = out_score; a.out_count = out_count; a.out_zero = out_zero;
     a.all_scores = out_all;
     a.max_cand = max_candidates;
-    return launch_rerank(a, user ? user : r->stream);
+    return launch_rerank(a, user);  // NULL = the default stream
   }
 
   // host-side offsets: validate and size
@@ -428,7 +427,7 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
   a.max_cand = maxc;
 
   cudaStream_t st = r->stream;
-  if (user) LSHX_CUDA(cudaStreamSynchronize(user));
+  LSHX_CUDA(cudaStreamSynchronize(user));  // a device-resident corpus may still be being written there
   int rc;
   if ((rc = r->q.reserve((size_t)nq * dim * sizeof(float))) != LSHX_OK) return rc;
   if ((rc = r->offs.reserve((size_t)(nq + 1) * sizeof(int64_t))) != LSHX_OK) return rc;
