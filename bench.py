@@ -67,7 +67,7 @@ def load_peaks() -> tuple[dict, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms while the timed region runs."""
 
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
               "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -82,7 +82,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -290,17 +290,18 @@ def run_b200(args) -> None:
     def e2e_step():
         hasher.hash_into(xh, e2e_rows, oh, x_on_device=False, out_on_device=False)
 
-    for _ in range(args.warmup):
+    e2e_steps = 1 if args.no_e2e else args.steps
+    for _ in range(1 if args.no_e2e else args.warmup):
         e2e_step()
     barrier()
     s2 = torch.cuda.Event(enable_timing=True); t2 = torch.cuda.Event(enable_timing=True)
     s2.record()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         e2e_step()
     t2.record()
     barrier()
     e2e_ms = max_ranks(s2.elapsed_time(t2))
-    e2e_value = e2e_rows * world * args.steps / (e2e_ms * 1e-3)
+    e2e_value = e2e_rows * world * e2e_steps / (e2e_ms * 1e-3)
     # the e2e path must produce the same bytes as the resident path
     same = bool(torch.equal(oh, out_host[:e2e_rows]))
 
@@ -367,7 +368,7 @@ def run_b200(args) -> None:
             "data": "synthetic", "config": workload_config(args), "impl": "b200", "kernel": kernel_name,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_rows * DIM * 4,
                     "d2h_bytes_per_step": e2e_rows * SIG_BYTES, "rows_per_step_per_gpu": e2e_rows,
-                    "ms_per_step": e2e_ms / args.steps,
+                    "ms_per_step": e2e_ms / e2e_steps,
                     "api": "lshx_hash_batch(host pinned X -> host pinned signatures)"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
             "cpu_baseline": cpu_baseline, "parity": parity, "rerank": rerank,
@@ -472,7 +473,7 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> d
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--rows", type=int, default=12_500_000, help="resident vectors per GPU")
@@ -484,6 +485,7 @@ def main() -> None:
     ap.add_argument("--queries", type=int, default=8192)
     ap.add_argument("--no-rerank", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (profiling runs)")
     args = ap.parse_args()
     args.steps = max(1, args.steps)
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)

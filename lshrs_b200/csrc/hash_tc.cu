@@ -40,26 +40,41 @@ namespace {
 constexpr int TC_THREADS = 384;
 constexpr int TM = 128;          // rows per tile
 constexpr int TK = 32;           // floats per K chunk (128 B: one SWIZZLE_128B row)
-constexpr int TN = 128;          // columns per MMA / per projection stage
+constexpr int TN = 128;          // accumulator columns per column tile (16 signature bytes)
+constexpr int TKB = 16;          // floats per projection stage along K (64 B rows, SWIZZLE_64B)
 constexpr int XS = 4;            // X stages
 constexpr int BS = 4;            // projection stages
 constexpr int AS = 4;            // A-operand TMEM stages
 constexpr uint32_t X_STAGE_BYTES = TM * TK * 4;        // 16384
-constexpr uint32_t B_HALF_BYTES = TN * TK * 4;         // 16384 (hi or lo)
+constexpr uint32_t B_HALF_BYTES = 2 * TN * TKB * 4;    // 16384: up to 256 columns x 16 floats (hi or lo)
 constexpr uint32_t B_STAGE_BYTES = 2 * B_HALF_BYTES;   // 32768
 constexpr uint32_t SMEM_BYTES = XS * X_STAGE_BYTES + BS * B_STAGE_BYTES;  // 196608
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t A_COL0 = 256;
 constexpr uint32_t A_STAGE_COLS = 64;
 
-// instruction descriptor: D=F32, A=B=TF32, both K-major, N=128, M=128 (cute::UMMA::InstrDescriptor)
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) |
-                           ((uint32_t)(TM >> 4) << 24);
+// instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
+}
+// One lane of a fully converged warp (elect.sync): lets ptxas keep the operands of the uniform-datapath
+// instructions (UTMALDG, UTCHMMA, UTCBAR) in uniform registers instead of a per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync _|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
@@ -105,16 +120,16 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc]; kind::tf32, M=128 N=128 K=8
+// D[tmem] (+)= A[tmem] * B[smem desc]; kind::tf32, M=128, N from idesc, K=8
 __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                          uint32_t accumulate) {
+                                          uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(b_desc), "r"(IDESC), "r"(accumulate)
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
@@ -145,11 +160,12 @@ __device__ __forceinline__ void tc_wait_ld() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 B,
-// 8-row swizzle atoms 1024 B apart (SBO), LBO unused for swizzled K-major, version 1 (Blackwell).
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 64 B
+// (16 floats = two K=8 steps), 8-row swizzle atoms 512 B apart (SBO = 32 x 16 B), LBO unused for
+// swizzled K-major, version 1 (Blackwell), layout type 4 = SWIZZLE_64B.
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
-         (2ull << 61);
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) |
+         (4ull << 61);
 }
 
 // round-to-nearest (ties away) to TF32, as cvt.rna.tf32.f32 does, with integer ops
@@ -227,67 +243,73 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const uint32_t tmem_base = tmem_base_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      Ring xr, br;
-      for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
-        const int64_t mt = w / p.npass;
-        const int pass = (int)(w % p.npass);
-        const int row0 = (int)(mt * TM);
-        for (int kc = 0; kc < p.kc; ++kc) {
-          mbar_wait(x_empty(xr.idx), xr.phase ^ 1);
+    // ===================== TMA producer (whole warp runs the loops, one elected lane issues) ====
+    Ring xr, br;
+    for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+      const int64_t mt = w / p.npass;
+      const int pass = (int)(w % p.npass);
+      const int row0 = (int)(mt * TM);
+      for (int kc = 0; kc < p.kc; ++kc) {
+        mbar_wait(x_empty(xr.idx), xr.phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(x_full(xr.idx), X_STAGE_BYTES);
           tma_load_2d(&tm_x, x_full(xr.idx), x_smem + xr.idx * X_STAGE_BYTES, kc * TK, row0);
-          xr.advance(XS);
-          for (int j = 0; j < p.nt; ++j) {
-            const int col0 = (pass * p.nt + j) * TN;
-            mbar_wait(b_empty(br.idx), br.phase ^ 1);
-            mbar_arrive_expect_tx(b_full(br.idx), B_STAGE_BYTES);
+        }
+        __syncwarp();
+        xr.advance(XS);
+        for (int hk = 0; hk < TK / TKB; ++hk) {   // two 16-float halves of the chunk, all columns each
+          const int col0 = pass * p.nt * TN;
+          mbar_wait(b_empty(br.idx), br.phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(b_full(br.idx), 2u * (uint32_t)p.nt * TN * TKB * 4u);
             const uint32_t dst = b_smem + br.idx * B_STAGE_BYTES;
-            tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK, col0);
-            tma_load_2d(&tm_rlo, b_full(br.idx), dst + B_HALF_BYTES, kc * TK, col0);
-            br.advance(BS);
+            tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK + hk * TKB, col0);
+            tma_load_2d(&tm_rlo, b_full(br.idx), dst + B_HALF_BYTES, kc * TK + hk * TKB, col0);
           }
+          __syncwarp();
+          br.advance(BS);
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      Ring ar, br, dr;
-      for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
-        mbar_wait(d_empty(dr.idx), dr.phase ^ 1);  // epilogue has drained this accumulator stage
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + dr.idx * TN;  // dstages == 2 only when nt == 1
-        for (int kc = 0; kc < p.kc; ++kc) {
-          mbar_wait(a_full(ar.idx), ar.phase);
-          const uint32_t a_hi = tmem_base + A_COL0 + ar.idx * A_STAGE_COLS;
-          const uint32_t a_lo = a_hi + 32;
-          for (int j = 0; j < p.nt; ++j) {
-            mbar_wait(b_full(br.idx), br.phase);
-            tc_fence_after();
-            const uint32_t bs = b_smem + br.idx * B_STAGE_BYTES;
-            const uint64_t desc_hi = make_b_desc(bs);
-            const uint64_t desc_lo = make_b_desc(bs + B_HALF_BYTES);
-            const uint32_t d = d_base + j * TN;
+    // ===================== MMA issuer (whole warp runs the loops, one elected lane issues) =====
+    Ring ar, br, dr;
+    const uint32_t idesc = make_idesc((uint32_t)p.nt * TN);  // one MMA spans every column of the pass
+    for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+      mbar_wait(d_empty(dr.idx), dr.phase ^ 1);  // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + dr.idx * TN;  // dstages == 2 only when nt == 1
+      for (int kc = 0; kc < p.kc; ++kc) {
+        mbar_wait(a_full(ar.idx), ar.phase);
+        const uint32_t a_hi = tmem_base + A_COL0 + ar.idx * A_STAGE_COLS;
+        const uint32_t a_lo = a_hi + 32;
+        for (int hk = 0; hk < TK / TKB; ++hk) {
+          mbar_wait(b_full(br.idx), br.phase);
+          tc_fence_after();
+          const uint32_t bs = b_smem + br.idx * B_STAGE_BYTES;
+          const uint64_t desc_hi = make_b_desc(bs);
+          const uint64_t desc_lo = make_b_desc(bs + B_HALF_BYTES);
+          if (elect_one()) {
 #pragma unroll
-            for (int s = 0; s < TK / 8; ++s) {
-              // +32 B per K step inside the 128 B swizzle row: start-address field += 2
+            for (int s = 0; s < TKB / 8; ++s) {
+              // +32 B per K step inside the 64 B swizzle row: start-address field += 2
               const uint64_t bh = desc_hi + (uint64_t)(2 * s);
               const uint64_t bl = desc_lo + (uint64_t)(2 * s);
-              tc_mma_ts(d, a_lo + 8 * s, bh, (kc > 0 || s > 0) ? 1u : 0u);  // small terms first
-              tc_mma_ts(d, a_hi + 8 * s, bl, 1u);
-              tc_mma_ts(d, a_hi + 8 * s, bh, 1u);
+              const uint32_t ka = (uint32_t)(hk * TKB + 8 * s);  // column of this K step in the A stage
+              tc_mma_ts(d_base, a_lo + ka, bh, idesc, (kc > 0 || hk > 0 || s > 0) ? 1u : 0u);  // small terms first
+              tc_mma_ts(d_base, a_hi + ka, bl, idesc, 1u);
+              tc_mma_ts(d_base, a_hi + ka, bh, idesc, 1u);
             }
-            tc_commit(b_empty(br.idx));
-            br.advance(BS);
+            tc_commit(b_empty(br.idx));  // same thread as the MMAs: commit tracks its own async ops
+            if (hk == TK / TKB - 1) tc_commit(a_empty(ar.idx));
+            if (hk == TK / TKB - 1 && kc == p.kc - 1) tc_commit(d_full(dr.idx));
           }
-          tc_commit(a_empty(ar.idx));
-          ar.advance(AS);
+          __syncwarp();
+          br.advance(BS);
         }
-        tc_commit(d_full(dr.idx));
-        dr.advance(dstages);
+        ar.advance(AS);
       }
+      dr.advance(dstages);
     }
   } else if (warp >= 4 && warp < 8) {
     // ===================== converters: X fp32 (smem) -> hi/lo TF32 (TMEM) =====================
@@ -360,16 +382,22 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t word = 0;
+        for (int c = 0; c < 4; c += 2) {   // two 32-column loads in flight per wait
+          uint32_t w0 = 0, w1 = 0;
           if (j < p.nt) {
-            uint32_t v[32];
-            tc_ld32(tmem_base + lane_field + dr.idx * TN + j * TN + c * 32, v);
+            uint32_t v0[32], v1[32];
+            const uint32_t src = tmem_base + lane_field + dr.idx * TN + j * TN + c * 32;
+            tc_ld32(src, v0);
+            tc_ld32(src + 32, v1);
             tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) word |= (__uint_as_float(v[i]) > 0.f ? 1u : 0u) << i;
+            for (int i = 0; i < 32; ++i) {
+              w0 |= (__uint_as_float(v0[i]) > 0.f ? 1u : 0u) << i;
+              w1 |= (__uint_as_float(v1[i]) > 0.f ? 1u : 0u) << i;
+            }
           }
-          words[j * 4 + c] = word;
+          words[j * 4 + c] = w0;
+          words[j * 4 + c + 1] = w1;
         }
       }
       tc_fence_before();
@@ -446,17 +474,19 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D row-major fp32 tensor [rows][cols], box = 32 floats x 128 rows, SWIZZLE_128B, zero OOB fill
+// 2-D row-major fp32 tensor [rows][cols], box = box_cols floats x box_rows rows, swizzle span equal
+// to the box row (128 B or 64 B), zero OOB fill
 int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_bytes,
-             CUtensorMapL2promotion promo) {
+             uint32_t box_cols, uint32_t box_rows, CUtensorMapL2promotion promo) {
   EncodeTiledFn enc = get_encode_fn();
   LSHX_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t gdim[2] = {cols, rows};
   cuuint64_t gstride[1] = {pitch_bytes};
-  cuuint32_t box[2] = {(cuuint32_t)TK, (cuuint32_t)TM};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  const CUtensorMapSwizzle swz = (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   cuuint32_t estr[2] = {1, 1};
   CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, promo,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu pitch %llu)", (int)rc,
@@ -467,6 +497,9 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
 }
 
 }  // namespace
+
+// 128-column tiles handled per pass over X: 2 (one N=256 MMA) when the column count allows it
+static int tc_nt(const HashShape& s) { return ((s.ncols_pad / TN) % 2 == 0) ? 2 : 1; }
 
 struct TcPlan {
   float* d_hi = nullptr;
@@ -500,10 +533,11 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
     return fail(LSHX_ERR_CUDA);
   }
   const uint64_t pitch = (uint64_t)s.dim_pad * sizeof(float);
-  int rc = make_map(&pl->tm_rhi, pl->d_hi, (uint64_t)s.ncols_pad, (uint64_t)s.dim_pad, pitch,
+  const uint32_t brows = (uint32_t)tc_nt(s) * TN;  // columns per pass = rows of one projection box
+  int rc = make_map(&pl->tm_rhi, pl->d_hi, (uint64_t)s.ncols_pad, (uint64_t)s.dim_pad, pitch, TKB, brows,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc != LSHX_OK) return fail(rc);
-  rc = make_map(&pl->tm_rlo, pl->d_lo, (uint64_t)s.ncols_pad, (uint64_t)s.dim_pad, pitch,
+  rc = make_map(&pl->tm_rlo, pl->d_lo, (uint64_t)s.ncols_pad, (uint64_t)s.dim_pad, pitch, TKB, brows,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc != LSHX_OK) return fail(rc);
   int dev = 0;
@@ -532,15 +566,14 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, const float* d_X, int64_t n
   LSHX_REQUIRE((reinterpret_cast<uintptr_t>(d_X) & 15) == 0, "tcgen05 kernel needs 16-byte aligned vectors");
   LSHX_REQUIRE(n < (1ll << 31), "hash batch of %lld rows exceeds one launch", (long long)n);
   CUtensorMap tm_x;
-  int rc = make_map(&tm_x, d_X, (uint64_t)n, (uint64_t)s.dim, (uint64_t)s.dim * sizeof(float),
+  int rc = make_map(&tm_x, d_X, (uint64_t)n, (uint64_t)s.dim, (uint64_t)s.dim * sizeof(float), TK, TM,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (rc != LSHX_OK) return rc;
   TcParams p;
   p.n = n;
   p.kc = s.dim_pad / TK;
-  const int ntiles = s.ncols_pad / TN;
-  p.nt = (ntiles % 2 == 0) ? 2 : 1;
-  p.npass = ntiles / p.nt;
+  p.nt = tc_nt(s);
+  p.npass = s.ncols_pad / TN / p.nt;
   p.mtiles = (n + TM - 1) / TM;
   p.sig_bytes = s.sig_bytes;
   p.out_vec_ok = (s.sig_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) ? 1 : 0;
