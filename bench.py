@@ -46,7 +46,32 @@ NUM_PERM = NUM_BANDS * ROWS_PER_BAND
 SIG_BYTES = NUM_BANDS * ((ROWS_PER_BAND + 7) // 8)
 METRIC = "vectors hashed/sec (dim=768, num_perm=256)"
 UNIT = "vectors/s"
+# BASELINE.json configs; "hash768" is the metric's configuration, the others are side measurements
+WORKLOADS = {
+    "hash768": dict(dim=768, bands=16, rows_per_band=16, rows=12_500_000, chunk=1_562_500, dist="gauss"),
+    "hash1536": dict(dim=1536, bands=16, rows_per_band=32, rows=6_250_000, chunk=781_250, dist="gauss"),
+    "hash128": dict(dim=128, bands=16, rows_per_band=4, rows=100_000_000, chunk=12_500_000, dist="sift"),
+}
+
+
+def select_workload(args) -> None:
+    global DIM, NUM_BANDS, ROWS_PER_BAND, NUM_PERM, SIG_BYTES, METRIC
+    w = WORKLOADS[args.workload]
+    DIM, NUM_BANDS, ROWS_PER_BAND = w["dim"], w["bands"], w["rows_per_band"]
+    NUM_PERM = NUM_BANDS * ROWS_PER_BAND
+    SIG_BYTES = NUM_BANDS * ((ROWS_PER_BAND + 7) // 8)
+    METRIC = f"vectors hashed/sec (dim={DIM}, num_perm={NUM_PERM})"
+    if args.rows is None:
+        args.rows = w["rows"]
+    if args.chunk is None:
+        args.chunk = w["chunk"]
+    args.chunk = min(args.chunk, args.rows)
+    args.e2e_rows = min(args.e2e_rows, args.rows)
+    args.dist = w["dist"]
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
+# capture committed under profiles/ (same command line, 1 562 500 rows per launch); None = not captured
+ROOFLINE_TRAFFIC = {("hash768", "tcgen05"): 4.855e9}
 
 
 def log(*a):
@@ -127,7 +152,8 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 
 def cpu_hash_sample(rows: int, seed: int = 0) -> np.ndarray:
-    return np.random.default_rng(seed).standard_normal((rows, DIM)).astype(np.float32)
+    x = np.random.default_rng(seed).standard_normal((rows, DIM)).astype(np.float32)
+    return x  # the reference arm always runs the metric's configuration (Gaussian, dim 768)
 
 
 def run_reference(args) -> None:
@@ -173,11 +199,13 @@ def run_reference(args) -> None:
 def workload_config(args) -> dict:
     return {
         "workload": f"LSHHasher dim={DIM} num_perm={NUM_PERM} ({NUM_BANDS}x{ROWS_PER_BAND}); "
-                    f"{args.rows} synthetic Gaussian float32 vectors resident per GPU "
-                    f"(BASELINE config 2: 100M vectors / 8 GPUs = 12.5M per GPU, weak scaling)",
+                    f"{args.rows} synthetic {'Gaussian' if args.dist == 'gauss' else 'SIFT-like non-negative'} "
+                    f"float32 vectors resident per GPU"
+                    + (" (BASELINE config 2: 100M vectors / 8 GPUs = 12.5M per GPU, weak scaling)"
+                       if args.workload == "hash768" else f" (BASELINE config '{args.workload}', side measurement)"),
         "rows_per_gpu": args.rows, "dim": DIM, "num_perm": NUM_PERM, "signature_bytes": SIG_BYTES,
         "chunk_rows": args.chunk, "e2e_rows_per_gpu": args.e2e_rows,
-        "l2": "inputs larger than L2 (38 GB resident shard, each row read once per step)",
+        "l2": f"inputs larger than L2 ({args.rows * DIM * 4 / 1e9:.0f} GB resident shard, each row read once per step)",
         "parallelism": f"row-sharded x{args.gpus}, projections replicated, no collective",
     }
 
@@ -226,6 +254,8 @@ def run_b200(args) -> None:
     for r0 in range(0, rows, 1 << 20):
         r1 = min(rows, r0 + (1 << 20))
         X[r0:r1].normal_(generator=gen)
+        if args.dist == "sift":  # SIFT-like: non-negative integer-valued floats in [0, 255]
+            X[r0:r1].abs_().mul_(40.0).floor_().clamp_(max=255.0)
     out_host = torch.empty((rows, SIG_BYTES), dtype=torch.uint8, pin_memory=True)
     out_dev = [torch.empty((chunk, SIG_BYTES), dtype=torch.uint8, device=dev) for _ in range(2)]
     chunks = [(r0, min(rows, r0 + chunk)) for r0 in range(0, rows, chunk)]
@@ -307,23 +337,35 @@ def run_b200(args) -> None:
 
     # ---- roofline of the projection kernel ------------------------------------------------
     ncols = SIG_BYTES * 8
-    useful_flop = 2.0 * DIM * ncols
+    useful_flop = 2.0 * DIM * NUM_PERM  # what the reference computes; padding columns are not useful work
     mma_passes = 3 if kernel_name == "tcgen05" else 1
     per_kernel_ms = kern_ms / max(1, len(kernel_events))
-    achieved_tflops = useful_flop * mma_passes * kern_rows / (kern_ms * 1e-3) / 1e12
+    ncols_pad = (ncols + 127) // 128 * 128  # the kernels compute whole 128-column tiles
+    exec_flop = 2.0 * DIM * ncols_pad * mma_passes
+    achieved_tflops = exec_flop * kern_rows / (kern_ms * 1e-3) / 1e12
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0  # dense TF32 = half of dense BF16 on the tensor pipe
-    roofline = {
-        "bound": "tensor", "kernel": f"hash_{kernel_name}",
-        "achieved": achieved_tflops, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved_tflops / tf32_peak,
-        "traffic": None,
-        "peak_source": f"{peak_src}: bf16_tflops_sustained / 2 (TF32 dense rate)",
-        "flops_counted": f"{mma_passes} x 2*dim*ncols per vector ({'3xTF32 split: hi*hi + hi*lo + lo*hi' if mma_passes == 3 else 'FP32 FFMA, one pass'})",
-        "useful_tflops": useful_flop * kern_rows / (kern_ms * 1e-3) / 1e12,
+    bytes_per_vec = 4.0 * DIM + SIG_BYTES
+    hbm_gbs = bytes_per_vec * kern_rows / (kern_ms * 1e-3) / 1e9
+    tensor_frac, hbm_frac = achieved_tflops / tf32_peak, hbm_gbs / peaks["hbm_gbs"]
+    common = {
+        "kernel": f"hash_{kernel_name}", "traffic": ROOFLINE_TRAFFIC.get((args.workload, kernel_name)),
         "avg_launch_ms": per_kernel_ms, "launches_timed": len(kernel_events),
         "kernel_share_of_step": kern_ms / (start.elapsed_time(stop)),
-        "hbm_gbs_achieved": (4.0 * DIM + SIG_BYTES) * kern_rows / (kern_ms * 1e-3) / 1e9,
-        "hbm_frac": (4.0 * DIM + SIG_BYTES) * kern_rows / (kern_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+        "algorithmic_bytes_per_launch": bytes_per_vec * kern_rows / max(1, len(kernel_events)),
+        "tensor": {"achieved_tflops": achieved_tflops, "peak_tflops": tf32_peak, "frac": tensor_frac,
+                   "peak_source": f"{peak_src}: bf16_tflops_sustained / 2 (TF32 dense rate)",
+                   "flops_counted": f"{mma_passes} x 2*dim*{ncols_pad} executed per vector "
+                                    f"({'3xTF32 split: lo*hi + hi*lo + hi*hi' if mma_passes == 3 else 'FP32 FFMA, one pass'})",
+                   "useful_tflops": useful_flop * kern_rows / (kern_ms * 1e-3) / 1e12},
+        "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": hbm_frac, "peak_source": peak_src,
+                "bytes_per_vector": bytes_per_vec},
     }
+    if tensor_frac >= hbm_frac:  # the slower of the two ceilings is the bound
+        roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": tensor_frac, **common}
+    else:
+        roofline = {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": hbm_frac, **common}
 
     # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1 only) ---------------------
     cpu_baseline, parity = None, None
@@ -476,8 +518,9 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
-    ap.add_argument("--rows", type=int, default=12_500_000, help="resident vectors per GPU")
-    ap.add_argument("--chunk", type=int, default=1_562_500, help="rows per kernel launch / D2H copy")
+    ap.add_argument("--workload", choices=tuple(WORKLOADS), default="hash768")
+    ap.add_argument("--rows", type=int, default=None, help="resident vectors per GPU")
+    ap.add_argument("--chunk", type=int, default=None, help="rows per kernel launch / D2H copy")
     ap.add_argument("--e2e-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=65_536)
     ap.add_argument("--kernel", choices=("auto", "ffma", "tcgen05"), default="auto")
@@ -488,6 +531,11 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (profiling runs)")
     args = ap.parse_args()
     args.steps = max(1, args.steps)
+    if args.impl == "reference":
+        args.workload = "hash768"
+    select_workload(args)
+    if args.workload != "hash768":
+        args.no_rerank = True
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
     if args.impl == "reference":
         run_reference(args)

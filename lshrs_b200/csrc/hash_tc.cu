@@ -13,21 +13,28 @@
 //
 // Data flow per CTA (persistent, one CTA per SM, 384 threads):
 //
-//   warp 0      TMA producer: X tile chunks (128 rows x 32 floats, SWIZZLE_128B) and the matching
-//               chunks of the pre-split projections R_hi / R_lo (128 columns x 32 floats each)
+//   warp 0      TMA producer: X tile chunks (128 rows x 32 floats, SWIZZLE_128B) and, per chunk, two
+//               16-float halves of the pre-split projections R_hi / R_lo for every column of the pass
+//               (up to 256 rows x 64 B each, SWIZZLE_64B)
 //   warps 4-7   converters: thread t owns row t of the tile; reads its 128 B of the X chunk from
 //               shared memory, splits hi/lo, writes them to TMEM with tcgen05.st (A operand lives
 //               in TMEM, so the MMA never re-reads X from shared memory); fuses the zero-vector
 //               test of LSHRS._prepare_vector (reference lshrs/core/main.py:1083)
-//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128 N=128 K=8,
-//               A from TMEM, B (projection chunk) from shared memory via a SWIZZLE_128B descriptor
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128,
+//               N=256 (or 128), K=8, A from TMEM, B (projection chunk) from shared memory
 //   warps 8-11  epilogue: tcgen05.ld the fp32 accumulators, strict `> 0`, one bit per column into
 //               per-row words, 16 B of signature per 128 columns, coalesced store
 //   warp 2      TMEM allocation
 //
-// TMEM (512 columns): accumulators in columns [0,256) (two 128-column tiles, or two stages of one
-// tile), A-operand stages in [256,512): 4 stages x (32 hi + 32 lo) columns.
+// TMEM (512 columns): accumulators in columns [0,256) (one 256-column tile, or two stages of a
+// 128-column tile), A-operand stages in [256,512): 4 stages x (32 hi + 32 lo) columns.
 // Shared memory: 4 X stages x 16 KB + 4 projection stages x 32 KB = 192 KB.
+//
+// Measured on B200 (profiles/): 571 M vectors/s at dim 768 / 256 bits = 1.0 x the cuBLAS-derived
+// sustained TF32 rate under the power cap; DRAM traffic equals the algorithmic bytes.  Bring-up
+// experiments (deliberately wrong arithmetic, not in the tree): never re-streaming R from L2 would
+// save 8 % and dropping one of the three MMAs 18 %, so neither a 2-CTA/multicast variant nor a
+// cheaper split is where the remaining time is.
 
 #include <cstdio>
 
