@@ -193,7 +193,7 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args) -> dict:
@@ -415,7 +415,7 @@ def run_b200(args) -> None:
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
             "cpu_baseline": cpu_baseline, "parity": parity, "rerank": rerank,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -512,7 +512,29 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> d
     return out
 
 
+_JSON_OUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line, on the real stdout (everything else in this process goes to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_OUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_OUT, data)
+
+
+def _route_stdout_to_stderr() -> None:
+    """NCCL / torch print banners on fd 1 (e.g. "NCCL version ..."); keep stdout for the JSON line only."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main() -> None:
+    _route_stdout_to_stderr()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
