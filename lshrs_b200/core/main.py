@@ -146,6 +146,27 @@ class LSHRS:
                 f"rows_per_band={c['rows_per_band']}, redis_prefix='{self._redis_config['prefix']}')")
 
     # ------------------------------------------------------------------ ingestion
+    def create_signatures(self, *, format: str = "postgres", **loader_kwargs: Any) -> None:
+        """Stream ``(indices, vectors)`` batches from a loader into :meth:`index` (reference main.py:315-384)."""
+        loader = self._resolve_loader(format)
+        for indices, vectors in loader(**loader_kwargs):
+            self.index(indices, vectors)
+
+    @staticmethod
+    def _resolve_loader(format: str):
+        normalized = format.lower()
+        if normalized in {"parquet", "pq"}:
+            from lshrs_b200.io.parquet import iter_parquet_vectors
+
+            return iter_parquet_vectors
+        if normalized in {"postgres", "pg"}:
+            try:  # the PostgreSQL loader stays in the reference package, unchanged
+                from lshrs.io.postgres import iter_postgres_vectors  # type: ignore
+            except ImportError as exc:
+                raise ImportError("the PostgreSQL loader lives in the reference package (lshrs.io.postgres)") from exc
+            return iter_postgres_vectors
+        raise ValueError(f"Unsupported signature creation format '{format}'")
+
     def ingest(self, index: int, vector: np.ndarray) -> None:
         """Hash one vector and buffer its ``num_bands`` bucket operations."""
         if index < 0:

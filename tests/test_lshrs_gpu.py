@@ -228,3 +228,20 @@ def test_full_size_config_autoconfig_and_bucket_keys():
     for row, keys in zip((10, 11), manifest["bucket_keys_768"]):
         for key in keys:
             assert row in st._buckets[key]
+
+
+def test_create_signatures_from_parquet(tmp_path, rng):
+    pa = pytest.importorskip("pyarrow")
+    import pyarrow.parquet as pq
+
+    data = rng.standard_normal((300, 32)).astype(np.float32)
+    path = tmp_path / "vectors.parquet"
+    pq.write_table(pa.table({"index": pa.array(np.arange(300), pa.int64()),
+                             "vector": pa.array(data.tolist(), pa.list_(pa.float32()))}), path)
+    st = RecordingStorage()
+    lsh = make_lsh(st)
+    lsh.create_signatures(format="parquet", source=path, batch_size=128)
+    assert len(st.all_operations) == 300 * 4
+    assert [len(b) for b in st.batches] == [128 * 4, 128 * 4, 44 * 4]   # one flush per loader batch
+    for probe in (0, 150, 299):
+        assert probe in lsh.get_top_k(data[probe], topk=5)
