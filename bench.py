@@ -376,7 +376,9 @@ def run_b200(args) -> None:
     useful_flop = 2.0 * DIM * NUM_PERM  # what the reference computes; padding columns are not useful work
     mma_passes = 3 if kernel_name == "tcgen05" else 1
     per_kernel_ms = kern_ms / max(1, len(kernel_events))
-    ncols_pad = (ncols + 127) // 128 * 128  # the kernels compute whole 128-column tiles
+    ncols_pad = (ncols + 127) // 128 * 128  # the FFMA kernel computes whole 128-column tiles of padded bands
+    if kernel_name == "tcgen05" and ROWS_PER_BAND % 8 != 0:
+        ncols_pad = (NUM_PERM + 15) // 16 * 16  # compact columns: only the real bits (one pass shapes)
     exec_flop = 2.0 * DIM * ncols_pad * mma_passes
     achieved_tflops = exec_flop * kern_rows / (kern_ms * 1e-3) / 1e12
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0  # dense TF32 = half of dense BF16 on the tensor pipe

@@ -37,6 +37,7 @@
 // cheaper split is where the remaining time is.
 
 #include <cstdio>
+#include <vector>
 
 #include "lshx_common.cuh"
 
@@ -49,13 +50,11 @@ constexpr int TM = 128;          // rows per tile
 constexpr int TK = 32;           // floats per K chunk (128 B: one SWIZZLE_128B row)
 constexpr int TN = 128;          // accumulator columns per column tile (16 signature bytes)
 constexpr int TKB = 16;          // floats per projection stage along K (64 B rows, SWIZZLE_64B)
-constexpr int XS = 4;            // X stages
+constexpr int XS_MAX = 10;       // X stages: as many 16 KB stages as fit beside the projection stages
 constexpr int BS = 4;            // projection stages
 constexpr int AS = 4;            // A-operand TMEM stages
 constexpr uint32_t X_STAGE_BYTES = TM * TK * 4;        // 16384
-constexpr uint32_t B_HALF_BYTES = 2 * TN * TKB * 4;    // 16384: up to 256 columns x 16 floats (hi or lo)
-constexpr uint32_t B_STAGE_BYTES = 2 * B_HALF_BYTES;   // 32768
-constexpr uint32_t SMEM_BYTES = XS * X_STAGE_BYTES + BS * B_STAGE_BYTES;  // 196608
+constexpr uint32_t SMEM_BYTES = 196608;                // 4 x 16 KB of X + 4 x 32 KB of projections at N = 256
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t A_COL0 = 256;
 constexpr uint32_t A_STAGE_COLS = 64;
@@ -191,8 +190,14 @@ struct Ring {  // stage index + phase bit of one mbarrier ring
 struct TcParams {
   int64_t n;        // rows
   int kc;           // K chunks = dim_pad / 32
-  int nt;           // 128-column tiles per pass (1 or 2)
-  int npass;        // passes over X (ncols_pad / (128 * nt))
+  int ncols_pass;   // accumulator columns per pass = N of the MMA (multiple of 16, <= 256)
+  int xs;           // X stages in use (4 at N = 256, up to XS_MAX for narrow shapes: more bytes in flight)
+  int b_resident;   // 1: the whole split projection matrix of the (single) pass stays in shared memory
+                    //    for the life of the CTA (small shapes); 0: streamed through BS stages per tile
+  int npass;        // passes over X
+  int repack;       // 1: columns are compact (band b = columns [b*r, (b+1)*r) of its pass) and the
+                    //    epilogue expands every band to whole bytes (rows_per_band % 8 != 0)
+  int r, bpb, bpp, num_bands;  // rows per band, bytes per band, bands per pass (repack mode)
   int64_t mtiles;   // ceil(n / 128)
   int sig_bytes;
   int out_vec_ok;   // 16-byte stores allowed
@@ -204,25 +209,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_rhi,
                const __grid_constant__ CUtensorMap tm_rlo, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[XS * 2 + BS * 2 + AS * 2 + 4];
+  __shared__ __align__(8) uint64_t bars[XS_MAX * 2 + BS * 2 + AS * 2 + 4];
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024 B alignment
   const uint32_t x_smem = smem_base;
+  const uint32_t XS = (uint32_t)p.xs;
+  const uint32_t B_HALF_BYTES = (uint32_t)p.ncols_pass * TKB * 4u;   // hi (or lo) rows of one stage: N x 64 B
+  const uint32_t B_STAGE_BYTES = 2u * B_HALF_BYTES;
   const uint32_t b_smem = smem_base + XS * X_STAGE_BYTES;
   const uint32_t bar0 = smem_u32(bars);
   auto x_full = [&](uint32_t i) { return bar0 + 8u * i; };
-  auto x_empty = [&](uint32_t i) { return bar0 + 8u * (XS + i); };
-  auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS + i); };
-  auto b_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS + BS + i); };
-  auto a_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS + 2 * BS + i); };
-  auto a_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS + 2 * BS + AS + i); };
-  auto d_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS + 2 * BS + 2 * AS + i); };
-  auto d_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS + 2 * BS + 2 * AS + 2 + i); };
+  auto x_empty = [&](uint32_t i) { return bar0 + 8u * (XS_MAX + i); };
+  auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + i); };
+  auto b_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + BS + i); };
+  auto a_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + 2 * BS + i); };
+  auto a_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + 2 * BS + AS + i); };
+  auto d_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + 2 * BS + 2 * AS + i); };
+  auto d_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + 2 * BS + 2 * AS + 2 + i); };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t dstages = (p.nt == 1) ? 2u : 1u;
+  __shared__ uint32_t repack_sm[TM * 9];  // per-thread 8 words (+1 zero) of compact column bits
+  const uint32_t N = (uint32_t)p.ncols_pass;
+  const uint32_t dstages = (N <= (uint32_t)TN) ? 2u : 1u;
   const int64_t work_items = p.mtiles * p.npass;
 
   if (warp == 0 && lane == 0) {
@@ -231,7 +241,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     tma_prefetch_desc(&tm_rlo);
   }
   if (warp == 1 && lane == 0) {
-    for (uint32_t i = 0; i < XS; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 4); }
+    for (uint32_t i = 0; i < XS_MAX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 4); }
     for (uint32_t i = 0; i < BS; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
     for (uint32_t i = 0; i < AS; ++i) { mbar_init(a_full(i), 4); mbar_init(a_empty(i), 1); }
     for (uint32_t i = 0; i < 2; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }
@@ -252,6 +262,19 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   if (warp == 0) {
     // ===================== TMA producer (whole warp runs the loops, one elected lane issues) ====
     Ring xr, br;
+    if (p.b_resident && (int64_t)blockIdx.x < work_items) {
+      // small shape: load every K slice of R_hi / R_lo once; stage (kc, hk) lives at index 2*kc + hk
+      if (elect_one()) {
+        mbar_arrive_expect_tx(b_full(0), (uint32_t)p.kc * (TK / TKB) * B_STAGE_BYTES);
+        for (int kc = 0; kc < p.kc; ++kc)
+          for (int hk = 0; hk < TK / TKB; ++hk) {
+            const uint32_t dst = b_smem + (uint32_t)(kc * (TK / TKB) + hk) * B_STAGE_BYTES;
+            tma_load_2d(&tm_rhi, b_full(0), dst, kc * TK + hk * TKB, 0);
+            tma_load_2d(&tm_rlo, b_full(0), dst + B_HALF_BYTES, kc * TK + hk * TKB, 0);
+          }
+      }
+      __syncwarp();
+    }
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int64_t mt = w / p.npass;
       const int pass = (int)(w % p.npass);
@@ -264,11 +287,11 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         }
         __syncwarp();
         xr.advance(XS);
-        for (int hk = 0; hk < TK / TKB; ++hk) {   // two 16-float halves of the chunk, all columns each
-          const int col0 = pass * p.nt * TN;
+        for (int hk = 0; hk < (p.b_resident ? 0 : TK / TKB); ++hk) {   // two 16-float halves of the chunk
+          const int col0 = pass * (int)N;
           mbar_wait(b_empty(br.idx), br.phase ^ 1);
           if (elect_one()) {
-            mbar_arrive_expect_tx(b_full(br.idx), 2u * (uint32_t)p.nt * TN * TKB * 4u);
+            mbar_arrive_expect_tx(b_full(br.idx), B_STAGE_BYTES);
             const uint32_t dst = b_smem + br.idx * B_STAGE_BYTES;
             tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK + hk * TKB, col0);
             tma_load_2d(&tm_rlo, b_full(br.idx), dst + B_HALF_BYTES, kc * TK + hk * TKB, col0);
@@ -281,19 +304,26 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loops, one elected lane issues) =====
     Ring ar, br, dr;
-    const uint32_t idesc = make_idesc((uint32_t)p.nt * TN);  // one MMA spans every column of the pass
+    const uint32_t idesc = make_idesc(N);  // one MMA spans every column of the pass
+    if (p.b_resident && (int64_t)blockIdx.x < work_items) {
+      mbar_wait(b_full(0), 0);
+      tc_fence_after();
+    }
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
       mbar_wait(d_empty(dr.idx), dr.phase ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
-      const uint32_t d_base = tmem_base + dr.idx * TN;  // dstages == 2 only when nt == 1
+      const uint32_t d_base = tmem_base + dr.idx * TN;  // dstages == 2 only when N <= 128
       for (int kc = 0; kc < p.kc; ++kc) {
         mbar_wait(a_full(ar.idx), ar.phase);
         const uint32_t a_hi = tmem_base + A_COL0 + ar.idx * A_STAGE_COLS;
         const uint32_t a_lo = a_hi + 32;
         for (int hk = 0; hk < TK / TKB; ++hk) {
-          mbar_wait(b_full(br.idx), br.phase);
-          tc_fence_after();
-          const uint32_t bs = b_smem + br.idx * B_STAGE_BYTES;
+          if (!p.b_resident) {
+            mbar_wait(b_full(br.idx), br.phase);
+            tc_fence_after();
+          }
+          const uint32_t bs =
+              b_smem + (p.b_resident ? (uint32_t)(kc * (TK / TKB) + hk) : br.idx) * B_STAGE_BYTES;
           const uint64_t desc_hi = make_b_desc(bs);
           const uint64_t desc_lo = make_b_desc(bs + B_HALF_BYTES);
           if (elect_one()) {
@@ -307,7 +337,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
               tc_mma_ts(d_base, a_hi + ka, bl, idesc, 1u);
               tc_mma_ts(d_base, a_hi + ka, bh, idesc, 1u);
             }
-            tc_commit(b_empty(br.idx));  // same thread as the MMAs: commit tracks its own async ops
+            if (!p.b_resident) tc_commit(b_empty(br.idx));  // same thread as the MMAs (commit tracks its own ops)
             if (hk == TK / TKB - 1) tc_commit(a_empty(ar.idx));
             if (hk == TK / TKB - 1 && kc == p.kc - 1) tc_commit(d_full(dr.idx));
           }
@@ -387,25 +417,27 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       tc_fence_after();
       uint32_t words[8];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
+      for (int g = 0; g < 4; ++g) {   // 64 columns per step: two 32-column loads in flight per wait
+        uint32_t w0 = 0, w1 = 0;
+        if ((uint32_t)(g * 64) < N) {
+          uint32_t v0[32], v1[32];
+          const uint32_t src = tmem_base + lane_field + dr.idx * TN + g * 64;
+          tc_ld32(src, v0);
+          tc_ld32(src + 32, v1);
+          tc_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 4; c += 2) {   // two 32-column loads in flight per wait
-          uint32_t w0 = 0, w1 = 0;
-          if (j < p.nt) {
-            uint32_t v0[32], v1[32];
-            const uint32_t src = tmem_base + lane_field + dr.idx * TN + j * TN + c * 32;
-            tc_ld32(src, v0);
-            tc_ld32(src + 32, v1);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              w0 |= (__uint_as_float(v0[i]) > 0.f ? 1u : 0u) << i;
-              w1 |= (__uint_as_float(v1[i]) > 0.f ? 1u : 0u) << i;
-            }
+          for (int i = 0; i < 32; ++i) {
+            w0 |= (__uint_as_float(v0[i]) > 0.f ? 1u : 0u) << i;
+            w1 |= (__uint_as_float(v1[i]) > 0.f ? 1u : 0u) << i;
           }
-          words[j * 4 + c] = w0;
-          words[j * 4 + c + 1] = w1;
+          // columns at or past N were never written by this pass's MMAs
+          const uint32_t left = N - (uint32_t)(g * 64);
+          if (left < 32u) w0 &= (1u << left) - 1u;
+          if (left <= 32u) w1 = 0u;
+          else if (left < 64u) w1 &= (1u << (left - 32u)) - 1u;
         }
+        words[2 * g] = w0;
+        words[2 * g + 1] = w1;
       }
       tc_fence_before();
       __syncwarp();
@@ -413,12 +445,50 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       dr.advance(dstages);
 
       const int64_t m = mt * TM + t;
-      if (m < p.n) {
-        const int byte0 = pass * p.nt * 16;  // 16 signature bytes per 128 columns
+      if (p.repack) {
+        // compact column bits -> every band padded to whole bytes (np.packbits zero high bits)
+        uint32_t* mine = repack_sm + t * 9;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mine[i] = words[i];
+        mine[8] = 0u;
+        if (m < p.n) {
+          const int band0 = pass * p.bpp;
+          const int nb = (p.num_bands - band0 < p.bpp) ? (p.num_bands - band0) : p.bpp;
+          const int out_bytes = nb * p.bpb;                       // bytes this pass contributes to the row
+          uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + (int64_t)band0 * p.bpb;
+          const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+          int j = 0, q = 0;                                       // band within the pass, byte within the band
+          for (int ob = 0; ob < out_bytes; ob += 16) {            // 16 output bytes per step, in registers
+            uint32_t o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (ob + e < out_bytes) {
+                const int src = j * p.r + 8 * q;
+                const int nbits = (p.r - 8 * q < 8) ? (p.r - 8 * q) : 8;
+                const uint32_t v = __funnelshift_r(mine[src >> 5], mine[(src >> 5) + 1], src & 31) &
+                                   ((1u << nbits) - 1u);
+                o[e >> 2] |= v << (8 * (e & 3));
+                if (++q == p.bpb) {
+                  q = 0;
+                  ++j;
+                }
+              }
+            }
+            if (vec_ok && ob + 16 <= out_bytes) {
+              *reinterpret_cast<uint4*>(dst + ob) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (ob + e < out_bytes) dst[ob + e] = (uint8_t)(o[e >> 2] >> (8 * (e & 3)));
+            }
+          }
+        }
+      } else if (m < p.n) {
+        const int byte0 = pass * (int)(N / 8);  // 16 signature bytes per 128 columns
         uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + byte0;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          if (j < p.nt) {
+          if ((uint32_t)(j * TN) < N) {
             const int b = byte0 + j * 16;
             if (p.out_vec_ok && b + 16 <= p.sig_bytes) {
               *reinterpret_cast<uint4*>(dst + j * 16) =
@@ -443,16 +513,19 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   }
 }
 
-// Rp [ncols_pad][dim] fp32 -> Rhi / Rlo [ncols_pad][dim_pad] TF32-rounded, zero K padding
-__global__ void split_projections_kernel(const float* __restrict__ Rp, float* __restrict__ hi,
-                                         float* __restrict__ lo, int ncols_pad, int dim, int dim_pad) {
-  const int64_t total = (int64_t)ncols_pad * dim_pad;
+// Rp [.][dim] fp32 -> Rhi / Rlo [rows][dim_pad] TF32-rounded split; row i of the output is row
+// rowmap[i] of Rp (or a zero row when rowmap[i] < 0); K is zero-padded to dim_pad.
+__global__ void split_projections_kernel(const float* __restrict__ Rp, const int* __restrict__ rowmap,
+                                         float* __restrict__ hi, float* __restrict__ lo, int rows, int dim,
+                                         int dim_pad) {
+  const int64_t total = (int64_t)rows * dim_pad;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     const int row = (int)(i / dim_pad), k = (int)(i % dim_pad);
+    const int src = rowmap[row];
     float h = 0.f, l = 0.f;
-    if (k < dim) {
-      const float r = Rp[(int64_t)row * dim + k];
+    if (k < dim && src >= 0) {
+      const float r = Rp[(int64_t)src * dim + k];
       h = __uint_as_float(tf32_rna(__float_as_uint(r)));
       const float res = (fabsf(h) == INFINITY) ? 0.f : (r - h);
       l = __uint_as_float(tf32_rna(__float_as_uint(res)));
@@ -505,14 +578,13 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
 
 }  // namespace
 
-// 128-column tiles handled per pass over X: 2 (one N=256 MMA) when the column count allows it
-static int tc_nt(const HashShape& s) { return ((s.ncols_pad / TN) % 2 == 0) ? 2 : 1; }
-
 struct TcPlan {
   float* d_hi = nullptr;
   float* d_lo = nullptr;
   CUtensorMap tm_rhi, tm_rlo;
   int num_sms = 0;
+  // column layout of the split projections (see tc_plan_create)
+  int ncols_pass = 0, npass = 0, repack = 0, bpp = 0;
 };
 
 bool tc_shape_supported(const HashShape& s) {
@@ -523,28 +595,60 @@ bool tc_shape_supported(const HashShape& s) {
 int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   *out = nullptr;
   TcPlan* pl = new TcPlan();
-  const size_t bytes = (size_t)s.ncols_pad * s.dim_pad * sizeof(float);
   auto fail = [&](int code) {
     tc_plan_destroy(pl);
     return code;
   };
-  if (cudaMalloc(&pl->d_hi, bytes) != cudaSuccess || cudaMalloc(&pl->d_lo, bytes) != cudaSuccess) {
+  // Column layout.  rows_per_band % 8 == 0: the padded layout of lshx_common.cuh is already dense
+  // (column c = signature bit c), passes of 256 (or 128) columns.  Otherwise computing the zero
+  // padding columns would waste up to 8x of the tensor work (16 bands x 4 rows: 128 columns for 64
+  // bits), so the columns are COMPACT -- pass p holds bands [p*bpp, (p+1)*bpp) back to back, padded
+  // to a multiple of 16 columns with zero rows -- and the epilogue expands each band to bytes.
+  std::vector<int> rowmap;
+  if (s.rows_per_band % 8 == 0 || s.rows_per_band > 128) {
+    const int ntiles = s.ncols_pad / TN;
+    pl->ncols_pass = (ntiles % 2 == 0) ? 2 * TN : TN;
+    pl->npass = s.ncols_pad / pl->ncols_pass;
+    pl->repack = 0;
+    rowmap.resize((size_t)s.ncols_pad);
+    for (int i = 0; i < s.ncols_pad; ++i) rowmap[i] = i;
+  } else {
+    const int r = s.rows_per_band;
+    pl->bpp = (256 / r < s.num_bands) ? 256 / r : s.num_bands;
+    pl->npass = (s.num_bands + pl->bpp - 1) / pl->bpp;
+    pl->ncols_pass = (pl->bpp * r + 15) / 16 * 16;
+    pl->repack = 1;
+    rowmap.assign((size_t)pl->npass * pl->ncols_pass, -1);
+    for (int b = 0; b < s.num_bands; ++b)
+      for (int j = 0; j < r; ++j)
+        rowmap[(size_t)(b / pl->bpp) * pl->ncols_pass + (size_t)(b % pl->bpp) * r + j] = b * 8 * s.bpb + j;
+  }
+  const int rows = pl->npass * pl->ncols_pass;
+  const size_t bytes = (size_t)rows * s.dim_pad * sizeof(float);
+  int* d_rowmap = nullptr;
+  if (cudaMalloc(&pl->d_hi, bytes) != cudaSuccess || cudaMalloc(&pl->d_lo, bytes) != cudaSuccess ||
+      cudaMalloc(&d_rowmap, rowmap.size() * sizeof(int)) != cudaSuccess) {
     set_error("cudaMalloc of %zu bytes for the split projections failed", bytes);
     (void)cudaGetLastError();
+    if (d_rowmap) cudaFree(d_rowmap);
     return fail(LSHX_ERR_OOM);
   }
-  split_projections_kernel<<<256, 256>>>(d_Rp, pl->d_hi, pl->d_lo, s.ncols_pad, s.dim, s.dim_pad);
+  cudaMemcpy(d_rowmap, rowmap.data(), rowmap.size() * sizeof(int), cudaMemcpyHostToDevice);
+  split_projections_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_hi, pl->d_lo, rows, s.dim, s.dim_pad);
   count_launch();
-  if (cudaDeviceSynchronize() != cudaSuccess) {
-    set_error("split_projections_kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+  const cudaError_t serr = cudaDeviceSynchronize();
+  cudaFree(d_rowmap);
+  if (serr != cudaSuccess) {
+    set_error("split_projections_kernel failed: %s", cudaGetErrorString(serr));
+    (void)cudaGetLastError();
     return fail(LSHX_ERR_CUDA);
   }
   const uint64_t pitch = (uint64_t)s.dim_pad * sizeof(float);
-  const uint32_t brows = (uint32_t)tc_nt(s) * TN;  // columns per pass = rows of one projection box
-  int rc = make_map(&pl->tm_rhi, pl->d_hi, (uint64_t)s.ncols_pad, (uint64_t)s.dim_pad, pitch, TKB, brows,
+  const uint32_t brows = (uint32_t)pl->ncols_pass;  // columns per pass = rows of one projection box
+  int rc = make_map(&pl->tm_rhi, pl->d_hi, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, brows,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc != LSHX_OK) return fail(rc);
-  rc = make_map(&pl->tm_rlo, pl->d_lo, (uint64_t)s.ncols_pad, (uint64_t)s.dim_pad, pitch, TKB, brows,
+  rc = make_map(&pl->tm_rlo, pl->d_lo, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, brows,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc != LSHX_OK) return fail(rc);
   int dev = 0;
@@ -579,8 +683,21 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, const float* d_X, int64_t n
   TcParams p;
   p.n = n;
   p.kc = s.dim_pad / TK;
-  p.nt = tc_nt(s);
-  p.npass = s.ncols_pad / TN / p.nt;
+  p.ncols_pass = plan->ncols_pass;
+  {
+    const uint32_t b_stage = 2u * (uint32_t)plan->ncols_pass * TKB * 4u;
+    const uint32_t b_all = (uint32_t)p.kc * (TK / TKB) * b_stage;  // the whole split matrix of one pass
+    p.b_resident = (plan->npass == 1 && b_all <= SMEM_BYTES - 4 * X_STAGE_BYTES) ? 1 : 0;
+    const uint32_t b_bytes = p.b_resident ? b_all : BS * b_stage;
+    const uint32_t fit = (SMEM_BYTES - b_bytes) / X_STAGE_BYTES;
+    p.xs = (int)(fit < (uint32_t)XS_MAX ? fit : (uint32_t)XS_MAX);
+  }
+  p.npass = plan->npass;
+  p.repack = plan->repack;
+  p.r = s.rows_per_band;
+  p.bpb = s.bpb;
+  p.bpp = plan->bpp;
+  p.num_bands = s.num_bands;
   p.mtiles = (n + TM - 1) / TM;
   p.sig_bytes = s.sig_bytes;
   p.out_vec_ok = (s.sig_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) ? 1 : 0;

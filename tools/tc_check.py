@@ -31,6 +31,14 @@ CASES = [
     (16, 32, 1536, 2000),  # 512 columns: two passes
     (5, 20, 100, 2000),    # ragged
     (16, 16, 768, 200_000),
+    # compact-column (repack) shapes: rows_per_band % 8 != 0
+    (20, 5, 128, 3000),    # 100 bits -> N = 112
+    (7, 3, 64, 1000),      # 21 bits  -> N = 32
+    (2, 70, 64, 1000),     # 140 bits -> N = 144, 9 bytes per band
+    (40, 7, 32, 2000),     # 280 bits -> two passes of 36 + 4 bands
+    (200, 3, 16, 700),     # 600 bits -> three passes
+    (3, 100, 256, 1500),   # 300 bits, 13 bytes per band, two bands per pass
+    (16, 4, 128, 1_000_000),
 ]
 
 
