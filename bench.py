@@ -370,6 +370,14 @@ def run_b200(args) -> None:
     e2e_value = e2e_rows * world * e2e_steps / (e2e_ms * 1e-3)
     # the e2e path must produce the same bytes as the resident path
     same = bool(torch.equal(oh, out_host[:e2e_rows]))
+    # latency of the per-vector call LSHRS.ingest / query make (reference: one hash_vector per call)
+    one = xh[:1].numpy().copy()
+    for _ in range(20):
+        hasher.hash_vector(one[0])
+    t_lat = time.perf_counter()
+    for _ in range(200):
+        hasher.hash_vector(one[0])
+    single_us = (time.perf_counter() - t_lat) / 200 * 1e6
 
     # ---- roofline of the projection kernel ------------------------------------------------
     ncols = SIG_BYTES * 8
@@ -449,7 +457,8 @@ def run_b200(args) -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_rows * DIM * 4,
                     "d2h_bytes_per_step": e2e_rows * SIG_BYTES, "rows_per_step_per_gpu": e2e_rows,
                     "ms_per_step": e2e_ms / e2e_steps,
-                    "api": "lshx_hash_batch(host pinned X -> host pinned signatures)"},
+                    "api": "lshx_hash_batch(host pinned X -> host pinned signatures)",
+                    "single_vector_call_us": single_us},
             "kernel_only": {"value": kernel_only_value, "unit": UNIT,
                             "note": "signatures left in HBM (no D2H gather); value above includes the overlapped D2H "
                                     "of every signature into pinned host memory"},
@@ -506,16 +515,24 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> d
         ms = max_ranks(s.elapsed_time(t)) / args.steps
         bytes_per_q = nc * (4 * DIM + 8) + 4 * DIM + 8 * limit
         gbs = bytes_per_q * nq / (ms * 1e-3) / 1e9
-        # e2e: host queries / ids / results, corpus resident (on_device = 2)
-        Qh, idh, offh = Q.cpu().numpy(), ids.cpu().numpy().reshape(-1), offs.cpu().numpy()
+        # e2e: PINNED host queries / ids / results through the C ABI, corpus resident (on_device = 2)
+        def pinned(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            return h.numpy()
+
+        Qh, idh, offh = pinned(Q), pinned(ids).reshape(-1), pinned(offs)
+        outs = (pinned(pos), pinned(score), pinned(count), pinned(zero))
         for _ in range(2):
-            rer.topk(Qh, corpus, offh, idh, k=k, p=p, vectors_on_device=True)
+            rer.topk(Qh, corpus, offh, idh, k=k, p=p, vectors_on_device=True, out=outs)
         barrier()
-        t0 = time.perf_counter()
+        s3 = torch.cuda.Event(enable_timing=True); t3 = torch.cuda.Event(enable_timing=True)
+        s3.record()
         for _ in range(args.steps):
-            ph, sh, ch, zh = rer.topk(Qh, corpus, offh, idh, k=k, p=p, vectors_on_device=True)
+            ph, sh, ch, zh = rer.topk(Qh, corpus, offh, idh, k=k, p=p, vectors_on_device=True, out=outs)
+        t3.record()
         torch.cuda.synchronize()
-        e2e_ms = max_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+        e2e_ms = max_ranks(s3.elapsed_time(t3)) / args.steps
         entry = {
             "value": nq * world / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "results_per_query": limit,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",

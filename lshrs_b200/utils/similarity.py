@@ -68,12 +68,14 @@ class Reranker:
 
     # -- selection ---------------------------------------------------------------
     def topk(self, queries: np.ndarray, vectors, offsets: np.ndarray, ids: np.ndarray | None = None, *,
-             k: int = 0, p: float = 0.0, vectors_on_device: bool = False, n_vectors: int | None = None):
+             k: int = 0, p: float = 0.0, vectors_on_device: bool = False, n_vectors: int | None = None,
+             out: tuple | None = None):
         """Best candidates per query.
 
         Returns ``(pos int32[nq, stride], score float32[nq, stride], count int32[nq], zero int32[nq])``;
         row i holds ``count[i]`` valid entries, best first.  ``k`` > 0 keeps the k
         best; ``p`` in (0, 1] keeps ``max(1, ceil(n_i * p))`` (and at most ``k`` when both are given).
+        ``out`` may supply the four result arrays (e.g. views of pinned memory, so the D2H is a DMA).
         """
         q = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dim)
         nq = q.shape[0]
@@ -87,10 +89,18 @@ class Reranker:
         else:
             stride = int(k)
         stride = max(1, min(stride, max(maxc, 1)))
-        pos = np.empty((nq, stride), dtype=np.int32)
-        score = np.empty((nq, stride), dtype=np.float32)
-        count = np.zeros(nq, dtype=np.int32)
-        zero = np.zeros(nq, dtype=np.int32)
+        if out is not None:
+            pos, score, count, zero = out
+            if (pos.shape != (nq, stride) or score.shape != (nq, stride) or pos.dtype != np.int32
+                    or score.dtype != np.float32 or count.shape != (nq,) or zero.shape != (nq,)
+                    or count.dtype != np.int32 or zero.dtype != np.int32
+                    or not (pos.flags.c_contiguous and score.flags.c_contiguous)):
+                raise ValueError(f"out arrays must be C-contiguous int32/float32 ({nq}, {stride}) and int32 ({nq},)")
+        else:
+            pos = np.empty((nq, stride), dtype=np.int32)
+            score = np.empty((nq, stride), dtype=np.float32)
+            count = np.zeros(nq, dtype=np.int32)
+            zero = np.zeros(nq, dtype=np.int32)
         ids_arr = None if ids is None else np.ascontiguousarray(ids, dtype=np.int64)
         vptr, nvec = _vectors_ptr(vectors, vectors_on_device, n_vectors, self.dim)
         _native.check(

@@ -234,3 +234,26 @@ def test_sharded_hasher_uses_every_visible_gpu():
     X = np.random.default_rng(2).standard_normal((3000, 768)).astype(np.float32)
     got = sh.hash_batch_packed(X)
     _assert_parity(got, X, sh.projections, "sharded")
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("nb, r, dim, n", [(16, 16, 768, 129), (16, 4, 128, 130), (5, 20, 100, 257),
+                                           (16, 32, 1536, 200), (40, 7, 32, 300), (3, 100, 256, 77)])
+def test_no_writes_outside_the_output(nb, r, dim, n, kernel):
+    """Canary rows around the signature / zero-flag buffers stay untouched (compute-sanitizer is
+    closed on this pool, so out-of-bounds stores are caught this way)."""
+    import torch
+
+    h = _hasher(nb, r, dim, 42, kernel)
+    sig = h.signature_bytes
+    x = torch.randn((n, dim), device="cuda", dtype=torch.float32)
+    out = torch.full((n + 4, sig), 0xAB, dtype=torch.uint8, device="cuda")
+    flag = torch.full((n + 64,), 0xCD, dtype=torch.uint8, device="cuda")
+    h.hash_into(x, n, out[2:], x_on_device=True, out_on_device=True, zero_flag=flag[32:],
+                stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert bool((out[:2] == 0xAB).all()) and bool((out[n + 2:] == 0xAB).all())
+    assert bool((flag[:32] == 0xCD).all()) and bool((flag[32 + n:] == 0xCD).all())
+    assert not bool(flag[32:32 + n].any())
+    got = out[2:n + 2].cpu().numpy().reshape(n, nb, -1)
+    _assert_parity(got, x.cpu().numpy(), h.projections, "canary")
