@@ -198,6 +198,18 @@ int lshx_rerank_scores(lshx_reranker* r, const float* Q, int64_t nq,
                        int64_t total_candidates, float* out_scores, int32_t* out_zero,
                        int on_device, void* stream);
 
+/*
+ * Replaces l2_norm (reference lshrs/utils/norm.py:48-61) for n rows at once:
+ * out[i] = X[i] / ||X[i]||_2 in float32; zero_rows[i] = 1 where the norm is 0
+ * (l2_norm raises ValueError("Cannot normalize zero vector") there, norm.py:57;
+ * the host wrapper does the same).  on_device: 0 = host pointers (synchronous),
+ * 1 = device pointers (enqueued on `stream`).  The rerank kernel does NOT call
+ * this -- it fuses the normalisation; the entry point exists for the public
+ * helper.
+ */
+int lshx_l2_normalize(lshx_reranker* r, const float* X, int64_t n, float* out,
+                      int32_t* zero_rows, int on_device, void* stream);
+
 int lshx_rerank_destroy(lshx_reranker* r);
 
 #ifdef __cplusplus

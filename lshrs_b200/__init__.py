@@ -17,7 +17,7 @@ from lshrs_b200._native import LshxError, LshxUnavailable
 from lshrs_b200.core.main import LSHRS, lshrs
 from lshrs_b200.hash.lsh import LSHHasher
 from lshrs_b200.storage.memory import BucketOperation, InMemoryStorage, bucket_key
-from lshrs_b200.utils.norm import l2_norm
+from lshrs_b200.utils.norm import l2_norm, l2_norm_batch
 from lshrs_b200.utils.similarity import Reranker, cosine_similarity, top_k_cosine, top_k_cosine_batch
 
 __version__ = "0.1.0"
@@ -32,6 +32,7 @@ __all__ = [
     "top_k_cosine_batch",
     "Reranker",
     "l2_norm",
+    "l2_norm_batch",
     "InMemoryStorage",
     "BucketOperation",
     "bucket_key",

@@ -49,6 +49,7 @@ EXPORTED_SYMBOLS = (
     "lshx_rerank_create",
     "lshx_rerank_topk",
     "lshx_rerank_scores",
+    "lshx_l2_normalize",
     "lshx_rerank_destroy",
 )
 
@@ -112,6 +113,8 @@ def _declare(cdll: ctypes.CDLL) -> None:
                                       c_int, vp, vp, vp, vp, c_int, vp]
     cdll.lshx_rerank_scores.restype = c_int
     cdll.lshx_rerank_scores.argtypes = [vp, vp, c_int64, vp, c_int64, vp, vp, c_int64, vp, vp, c_int, vp]
+    cdll.lshx_l2_normalize.restype = c_int
+    cdll.lshx_l2_normalize.argtypes = [vp, vp, c_int64, vp, vp, c_int, vp]
     cdll.lshx_rerank_destroy.restype = c_int
     cdll.lshx_rerank_destroy.argtypes = [vp]
 

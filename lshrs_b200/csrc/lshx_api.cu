@@ -480,6 +480,33 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
   return LSHX_OK;
 }
 
+extern "C" int lshx_l2_normalize(lshx_reranker* r, const float* X, int64_t n, float* out,
+                                 int32_t* zero_rows, int on_device, void* stream) {
+  LSHX_REQUIRE(r != nullptr, "null handle");
+  LSHX_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0) return LSHX_OK;
+  LSHX_REQUIRE(X != nullptr && out != nullptr, "null buffer");
+  std::lock_guard<std::mutex> lk(r->mu);
+  DeviceGuard g(r->device);
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  if (on_device) return launch_l2_normalize(X, n, r->dim, out, zero_rows, user);
+  const size_t bytes = (size_t)n * r->dim * sizeof(float);
+  int rc;
+  if ((rc = r->q.reserve(bytes)) != LSHX_OK) return rc;
+  if ((rc = r->vecs.reserve(bytes)) != LSHX_OK) return rc;
+  if ((rc = r->zero.reserve((size_t)n * sizeof(int32_t))) != LSHX_OK) return rc;
+  cudaStream_t st = r->stream;
+  LSHX_CUDA(cudaMemcpyAsync(r->q.p, X, bytes, cudaMemcpyHostToDevice, st));
+  rc = launch_l2_normalize(static_cast<const float*>(r->q.p), n, r->dim, static_cast<float*>(r->vecs.p),
+                           static_cast<int32_t*>(r->zero.p), st);
+  if (rc != LSHX_OK) return rc;
+  LSHX_CUDA(cudaMemcpyAsync(out, r->vecs.p, bytes, cudaMemcpyDeviceToHost, st));
+  if (zero_rows)
+    LSHX_CUDA(cudaMemcpyAsync(zero_rows, r->zero.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  LSHX_CUDA(cudaStreamSynchronize(st));
+  return LSHX_OK;
+}
+
 extern "C" int lshx_rerank_topk(lshx_reranker* r, const float* Q, int64_t nq, const float* vectors,
                                 int64_t n_vectors, const int64_t* cand_offsets,
                                 const int64_t* cand_ids, int64_t max_candidates, int k, double p,

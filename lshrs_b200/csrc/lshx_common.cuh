@@ -87,5 +87,7 @@ struct RerankArgs {
   bool select;        // false: scores only
 };
 int launch_rerank(const RerankArgs& a, cudaStream_t stream);
+int launch_l2_normalize(const float* d_X, int64_t n, int dim, float* d_out, int32_t* d_zero,
+                        cudaStream_t stream);
 
 }  // namespace lshx

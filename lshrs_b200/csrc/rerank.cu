@@ -219,6 +219,27 @@ rerank_kernel(RerankArgs a, unsigned cap, int q_floats) {
   }
 }
 
+// out[i] = x[i] / ||x[i]||_2 for every row; zero[i] = 1 where the norm is 0 (reference l2_norm raises).
+// One warp per row, grid-stride.
+__global__ void __launch_bounds__(256)
+l2_normalize_kernel(const float* __restrict__ X, int64_t n, int dim, float* __restrict__ out,
+                    int32_t* __restrict__ zero) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+    const float* x = X + row * (int64_t)dim;
+    float ss = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+      const float v = __ldg(x + i);
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float norm = sqrtf(ss);
+    for (int i = lane; i < dim; i += 32) out[row * (int64_t)dim + i] = __ldg(x + i) / norm;
+    if (lane == 0 && zero != nullptr) zero[row] = (norm == 0.f) ? 1 : 0;
+  }
+}
+
 unsigned next_pow2(uint64_t v) {
   unsigned p = 2;
   while (p < v) p <<= 1;
@@ -226,6 +247,17 @@ unsigned next_pow2(uint64_t v) {
 }
 
 }  // namespace
+
+int launch_l2_normalize(const float* d_X, int64_t n, int dim, float* d_out, int32_t* d_zero,
+                        cudaStream_t stream) {
+  if (n <= 0) return LSHX_OK;
+  const int64_t blocks = (n + 7) / 8;
+  const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
+  l2_normalize_kernel<<<grid, 256, 0, stream>>>(d_X, n, dim, d_out, d_zero);
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
 
 int launch_rerank(const RerankArgs& a, cudaStream_t stream) {
   if (a.nq <= 0) return LSHX_OK;

@@ -5,7 +5,7 @@ from __future__ import annotations
 import numpy as np
 import pytest
 
-from lshrs_b200 import LSHRS, HashSignatures, InMemoryStorage, LSHHasher, bucket_key, l2_norm
+from lshrs_b200 import LSHRS, HashSignatures, InMemoryStorage, LSHHasher, bucket_key
 from lshrs_b200._config.config import signatures_from_packed
 from lshrs_b200.sharding import shard_bounds
 
@@ -59,15 +59,6 @@ def test_hasher_validation_runs_before_any_device_work():
         h.hash_batch(np.ones((2, 5), dtype=np.float32))
     assert h.hash_batch(np.empty((0, 4), dtype=np.float32)) == []
     assert h.hash_batch_packed(np.empty((0, 4), dtype=np.float32)).shape == (0, 2, 1)
-
-
-def test_l2_norm():
-    # reference tests/test_lshrs.py:100-112
-    out = l2_norm([3.0, 4.0])
-    np.testing.assert_allclose(out, [0.6, 0.8], atol=1e-7)
-    assert out.dtype == np.float32
-    with pytest.raises(ValueError, match="zero vector"):
-        l2_norm(np.zeros(3))
 
 
 def test_in_memory_storage_and_bucket_key():

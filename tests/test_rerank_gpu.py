@@ -166,3 +166,23 @@ def test_more_candidates_than_one_sort_buffer():
     _check_topk(top_k_cosine(q, C, k=8192), ref, 8192)
     with pytest.raises(LshxError, match="at most"):
         top_k_cosine(q, C, k=n)  # documented limit: fails loudly, no silent fallback
+
+
+def test_l2_norm_on_gpu():
+    from lshrs_b200 import l2_norm
+    from lshrs_b200.utils.norm import l2_norm_batch
+
+    # reference tests/test_lshrs.py:100-112
+    out = l2_norm([3.0, 4.0])
+    np.testing.assert_allclose(out, [0.6, 0.8], atol=1e-7)
+    assert out.dtype == np.float32 and out.shape == (2,)
+    with pytest.raises(ValueError, match="Cannot normalize zero vector"):
+        l2_norm(np.zeros(3))
+    rng = np.random.default_rng(0)
+    for dim in (1, 33, 768):
+        X = (rng.standard_normal((257, dim)) * np.logspace(-3, 3, 257)[:, None]).astype(np.float32)
+        got = l2_norm_batch(X)
+        want = np.stack([oracle.l2_norm(x) for x in X])
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
+    case = load_golden("rerank_gauss_300x768")
+    np.testing.assert_allclose(l2_norm(case["query"]), case["normalized_query"], rtol=2e-6, atol=1e-7)
