@@ -180,6 +180,55 @@ hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* _
   }
 }
 
+
+// ---- small batches (the per-vector calls of LSHRS.ingest / query) ----------------------------------
+// A handful of rows cannot fill a 128-row tile and the call is pure latency, so: one CTA per OUTPUT
+// BYTE, one warp per column (= signature bit), the rows in shared memory, fp32 FMA + shuffle
+// reduction, `> 0`, eight warps -> one byte per row.  Same arithmetic class as the tiled kernel.
+constexpr int SMALL_THREADS = 256;
+
+__global__ void __launch_bounds__(SMALL_THREADS)
+hash_small_kernel(const float* __restrict__ X, int n, int dim, const float* __restrict__ Rp,
+                  uint8_t* __restrict__ out, int sig_bytes, uint8_t* __restrict__ zero_flag) {
+  extern __shared__ float xs[];          // [n][dim]
+  __shared__ unsigned int sbits[32];     // one byte per row, built with atomicOr
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n * dim; i += SMALL_THREADS) xs[i] = X[i];
+  if (tid < 32) sbits[tid] = 0u;
+  __syncthreads();
+
+  const float* rrow = Rp + (int64_t)(blockIdx.x * 8 + warp) * dim;   // column of this warp
+  for (int i0 = 0; i0 < n; i0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int k = lane; k < dim; k += 32) {
+      const float rv = __ldg(rrow + k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + j < n) acc[j] = fmaf(rv, xs[(i0 + j) * dim + k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0 && i0 + j < n && v > 0.f) atomicOr(&sbits[i0 + j], 1u << warp);
+    }
+  }
+  __syncthreads();
+  if (tid < n) out[(int64_t)tid * sig_bytes + blockIdx.x] = (uint8_t)sbits[tid];
+
+  if (zero_flag != nullptr && blockIdx.x == 0) {
+    for (int i = warp; i < n; i += SMALL_THREADS / 32) {
+      bool viol = false;
+      for (int k = lane; k < dim; k += 32) viol |= !(fabsf(xs[i * dim + k]) <= 1e-8f);
+      const unsigned any = __ballot_sync(0xffffffffu, viol);
+      if (lane == 0) zero_flag[i] = any ? 0 : 1;
+    }
+  }
+}
+
 }  // namespace
 
 int launch_hash_ffma(const HashShape& s, const float* d_X, int64_t n, const float* d_Rp,
@@ -199,6 +248,29 @@ int launch_hash_ffma(const HashShape& s, const float* d_X, int64_t n, const floa
   else
     hash_ffma_kernel<false><<<grid, THREADS, 0, stream>>>(d_X, n, s.dim, d_Rp, s.ncols_pad, d_out,
                                                           s.sig_bytes, d_zero_flag, word_ok);
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
+
+}  // namespace lshx
+
+namespace lshx {
+
+int hash_small_max_rows(const HashShape& s) {
+  const int by_smem = (int)(65536 / ((size_t)s.dim * sizeof(float)));
+  return by_smem < 32 ? by_smem : 32;
+}
+
+int launch_hash_small(const HashShape& s, const float* d_X, int n, const float* d_Rp, uint8_t* out,
+                      uint8_t* zero_flag, cudaStream_t stream) {
+  if (n <= 0) return LSHX_OK;
+  LSHX_REQUIRE(n <= hash_small_max_rows(s), "small-batch kernel takes at most %d rows", hash_small_max_rows(s));
+  const size_t smem = (size_t)n * s.dim * sizeof(float);
+  if (smem > 48 * 1024)
+    LSHX_CUDA(cudaFuncSetAttribute(hash_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  hash_small_kernel<<<s.sig_bytes, SMALL_THREADS, smem, stream>>>(d_X, n, s.dim, d_Rp, out, s.sig_bytes,
+                                                                  zero_flag);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;

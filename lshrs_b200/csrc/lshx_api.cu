@@ -96,6 +96,11 @@ struct lshx_hasher {
   cudaStream_t streams[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr;
   DevBuf x_stage[2], out_stage[2], flag_stage[2];
+  // small-batch path (per-vector calls): pinned, device-mapped staging for up to small_rows rows
+  int small_rows = 0;
+  float* pin_x = nullptr;      // host, pinned
+  uint8_t* pin_out = nullptr;  // host, pinned + mapped: the kernel stores signatures / flags into it
+  float* d_small_x = nullptr;
   std::mutex mu;
 };
 
@@ -184,6 +189,17 @@ extern "C" int lshx_hasher_create(int device, int dim, int num_bands, int rows_p
   }
   rc = upload_projections(h, projections_host);
   if (rc != LSHX_OK) return fail(rc);
+  h->small_rows = hash_small_max_rows(s);
+  if (h->small_rows > 0) {
+    const size_t xb = (size_t)h->small_rows * dim * sizeof(float);
+    const size_t ob = (size_t)h->small_rows * (s.sig_bytes + 1);
+    if (cudaHostAlloc(&h->pin_x, xb, cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc(&h->pin_out, ob, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaMalloc(&h->d_small_x, xb) != cudaSuccess) {
+      (void)cudaGetLastError();
+      h->small_rows = 0;  // the chunked path still works without the staging buffers
+    }
+  }
   *out = h;
   return LSHX_OK;
 }
@@ -240,6 +256,24 @@ extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_
   // ---- everything on the device: one asynchronous launch ----------------------------
   if (x_is_device && out_is_device) {
     return launch_hash(h, X, n, out, zero_flag, user);  // NULL = the default stream
+  }
+
+  // ---- a few host rows (LSHRS.ingest / query hash ONE vector per call): latency path ------------
+  if (!x_is_device && !out_is_device && n <= h->small_rows && h->kernel_pref == LSHX_KERNEL_AUTO) {
+    cudaStream_t st = h->streams[0];
+    const size_t xb = (size_t)n * s.dim * sizeof(float);
+    std::memcpy(h->pin_x, X, xb);
+    LSHX_CUDA(cudaMemcpyAsync(h->d_small_x, h->pin_x, xb, cudaMemcpyHostToDevice, st));
+    uint8_t* d_out_map = nullptr;
+    LSHX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_out_map), h->pin_out, 0));
+    uint8_t* d_flag_map = zero_flag ? d_out_map + (size_t)h->small_rows * s.sig_bytes : nullptr;
+    h->last_kernel = LSHX_KERNEL_SMALL;
+    int rc = launch_hash_small(s, h->d_small_x, (int)n, h->d_Rp, d_out_map, d_flag_map, st);
+    if (rc != LSHX_OK) return rc;
+    LSHX_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(out, h->pin_out, (size_t)n * s.sig_bytes);
+    if (zero_flag) std::memcpy(zero_flag, h->pin_out + (size_t)h->small_rows * s.sig_bytes, (size_t)n);
+    return LSHX_OK;
   }
 
   // ---- at least one side on the host: chunked, two streams, synchronous -----------
@@ -318,6 +352,9 @@ extern "C" int lshx_hasher_destroy(lshx_hasher* h) {
       if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     }
     if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->pin_x) cudaFreeHost(h->pin_x);
+    if (h->pin_out) cudaFreeHost(h->pin_out);
+    if (h->d_small_x) cudaFree(h->d_small_x);
     (void)cudaGetLastError();
   }
   delete h;

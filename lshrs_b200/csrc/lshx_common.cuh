@@ -59,6 +59,12 @@ struct HashShape {
 int launch_hash_ffma(const HashShape& s, const float* d_X, int64_t n, const float* d_Rp,
                      uint8_t* d_out, uint8_t* d_zero_flag, cudaStream_t stream);
 
+// Small batches (<= hash_small_max_rows): one CTA per output byte, one warp per column.  `out` /
+// `zero_flag` may be mapped pinned host memory (the kernel stores straight into it).
+int hash_small_max_rows(const HashShape& s);
+int launch_hash_small(const HashShape& s, const float* d_X, int n, const float* d_Rp, uint8_t* out,
+                      uint8_t* zero_flag, cudaStream_t stream);
+
 struct TcPlan;  // opaque tcgen05 state (TMA descriptor of the split projections, ...)
 bool tc_shape_supported(const HashShape& s);
 int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out);

@@ -143,7 +143,7 @@ class LSHHasher:
         if self._handle is None:
             return "none"
         code = _native.lib().lshx_hasher_last_kernel(self._handle)
-        return {0: "none", 1: "ffma", 2: "tcgen05"}.get(code, str(code))
+        return {0: "none", 1: "ffma", 2: "tcgen05", 3: "small"}.get(code, str(code))
 
     @property
     def device(self) -> int:

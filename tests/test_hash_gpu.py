@@ -257,3 +257,29 @@ def test_no_writes_outside_the_output(nb, r, dim, n, kernel):
     assert not bool(flag[32:32 + n].any())
     got = out[2:n + 2].cpu().numpy().reshape(n, nb, -1)
     _assert_parity(got, x.cpu().numpy(), h.projections, "canary")
+
+
+@pytest.mark.parametrize("name", hash_case_names())
+def test_auto_kernel_and_per_vector_latency_path(name):
+    """AUTO: a handful of host rows (what LSHRS.ingest / query send) take the small-batch kernel,
+    larger batches the tiled kernels; both must reproduce the reference's bytes."""
+    case = load_golden(name)
+    nb, r, dim, seed = (int(case[k]) for k in ("num_bands", "rows_per_band", "dim", "seed"))
+    projs = projections_for(case)
+    h = _hasher(nb, r, dim, seed, "auto")
+    X = case["X"]
+    finite = np.isfinite(X).all(axis=1)
+    margins = oracle.projection_margins(projs, X[finite])
+    whole = h.hash_batch_packed(X)
+    rep = oracle.compare_packed(whole[finite], case["signatures"][finite], margins, REL_MARGIN)
+    assert rep["flips_outside_margin"] == 0 and rep["nonzero_pad_bits"] == 0, rep
+    # row by row (n = 1) and in threes: the latency path
+    rows = np.stack([np.frombuffer(b"".join(h.hash_vector(x).as_tuple()), dtype=np.uint8) for x in X])
+    assert h.last_kernel == "small"
+    rep1 = oracle.compare_packed(rows.reshape(whole.shape)[finite], case["signatures"][finite], margins, REL_MARGIN)
+    assert rep1["flips_outside_margin"] == 0 and rep1["nonzero_pad_bits"] == 0, rep1
+    sig3, flag3 = h.hash_batch_packed(X[:3], return_zero_flag=True)
+    rep3 = oracle.compare_packed(sig3[finite[:3]], case["signatures"][:3][finite[:3]],
+                                 oracle.projection_margins(projs, X[:3][finite[:3]]), REL_MARGIN)
+    assert rep3["flips_outside_margin"] == 0, rep3
+    np.testing.assert_array_equal(flag3, [oracle.is_zero_vector(x) for x in X[:3]])
