@@ -276,8 +276,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       __syncwarp();
     }
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
-      const int64_t mt = w / p.npass;
-      const int pass = (int)(w % p.npass);
+      const int64_t mt = (p.npass == 1) ? w : w / p.npass;   // (no 64-bit division on the common path)
+      const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
       const int row0 = (int)(mt * TM);
       for (int kc = 0; kc < p.kc; ++kc) {
         mbar_wait(x_empty(xr.idx), xr.phase ^ 1);
@@ -354,8 +354,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     Ring xr, ar;
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
-      const int64_t mt = w / p.npass;
-      const int pass = (int)(w % p.npass);
+      const int64_t mt = (p.npass == 1) ? w : w / p.npass;   // (no 64-bit division on the common path)
+      const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
       bool viol = false;  // some |x| > 1e-8 (or NaN): not a zero vector
       for (int kc = 0; kc < p.kc; ++kc) {
         mbar_wait(x_full(xr.idx), xr.phase);
@@ -411,8 +411,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     Ring dr;
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
-      const int64_t mt = w / p.npass;
-      const int pass = (int)(w % p.npass);
+      const int64_t mt = (p.npass == 1) ? w : w / p.npass;   // (no 64-bit division on the common path)
+      const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
       mbar_wait(d_full(dr.idx), dr.phase);
       tc_fence_after();
       uint32_t words[8];
@@ -445,7 +445,36 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       dr.advance(dstages);
 
       const int64_t m = mt * TM + t;
-      if (p.repack) {
+      if (p.repack && p.r == 4) {
+        // 4-row bands (BASELINE config 5): every nibble of the compact bits becomes one byte; pure
+        // register bit-spreading, 16 bits -> 4 bytes per step
+        if (m < p.n) {
+          const int band0 = pass * p.bpp;
+          const int nb = (p.num_bands - band0 < p.bpp) ? (p.num_bands - band0) : p.bpp;  // = output bytes
+          uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + band0;
+          const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {          // 64 compact bits -> 16 output bytes per step
+            if (g * 16 < nb) {
+              uint32_t o[4];
+#pragma unroll
+              for (int h = 0; h < 4; ++h) {
+                uint32_t x = (words[2 * g + (h >> 1)] >> (16 * (h & 1))) & 0xFFFFu;
+                x = (x | (x << 8)) & 0x00FF00FFu;
+                x = (x | (x << 4)) & 0x0F0F0F0Fu;
+                o[h] = x;
+              }
+              if (vec_ok && g * 16 + 16 <= nb) {
+                *reinterpret_cast<uint4*>(dst + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 16; ++e)
+                  if (g * 16 + e < nb) dst[g * 16 + e] = (uint8_t)(o[e >> 2] >> (8 * (e & 3)));
+              }
+            }
+          }
+        }
+      } else if (p.repack) {
         // compact column bits -> every band padded to whole bytes (np.packbits zero high bits)
         uint32_t* mine = repack_sm + t * 9;
 #pragma unroll
