@@ -48,7 +48,7 @@ METRIC = "vectors hashed/sec (dim=768, num_perm=256)"
 UNIT = "vectors/s"
 # BASELINE.json configs; "hash768" is the metric's configuration, the others are side measurements
 WORKLOADS = {
-    "hash768": dict(dim=768, bands=16, rows_per_band=16, rows=12_500_000, chunk=1_562_500, dist="gauss"),
+    "hash768": dict(dim=768, bands=16, rows_per_band=16, rows=12_500_000, chunk=781_250, dist="gauss"),
     "hash1536": dict(dim=1536, bands=16, rows_per_band=32, rows=6_250_000, chunk=781_250, dist="gauss"),
     "hash128": dict(dim=128, bands=16, rows_per_band=4, rows=100_000_000, chunk=12_500_000, dist="sift"),
 }
@@ -69,9 +69,10 @@ def select_workload(args) -> None:
     args.e2e_rows = min(args.e2e_rows, args.rows)
     args.dist = w["dist"]
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the ncu --set full
-# capture committed under profiles/ (same command line, 1 562 500 rows per launch); None = not captured
-ROOFLINE_TRAFFIC = {("hash768", "tcgen05"): 4.855e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel PER ROW, from the ncu --set full
+# captures committed under profiles/ (r1_hash_tc_ncu.csv: 4.803 GB + 0.053 GB over 1 562 500 rows;
+# r1_hash_tc_dim128_ncu.csv: 6.401 GB + 0.201 GB over 12 500 000 rows); scaled to the rows of one launch
+ROOFLINE_TRAFFIC_PER_ROW = {("hash768", "tcgen05"): 4.856e9 / 1_562_500, ("hash128", "tcgen05"): 6.602e9 / 12_500_000}
 
 
 def log(*a):
@@ -399,7 +400,8 @@ def run_b200(args) -> None:
     hbm_gbs = bytes_per_vec * kern_rows / (kern_ms * 1e-3) / 1e9
     tensor_frac, hbm_frac = achieved_tflops / useful_peak, hbm_gbs / peaks["hbm_gbs"]
     common = {
-        "kernel": f"hash_{kernel_name}", "traffic": ROOFLINE_TRAFFIC.get((args.workload, kernel_name)),
+        "kernel": f"hash_{kernel_name}", "traffic": (ROOFLINE_TRAFFIC_PER_ROW[(args.workload, kernel_name)] * kern_rows / max(1, len(kernel_events))
+                    if (args.workload, kernel_name) in ROOFLINE_TRAFFIC_PER_ROW else None),
         "avg_launch_ms": per_kernel_ms, "launches_timed": len(kernel_events),
         "kernel_share_of_step": kern_ms / (start.elapsed_time(stop)),
         "algorithmic_bytes_per_launch": bytes_per_vec * kern_rows / max(1, len(kernel_events)),

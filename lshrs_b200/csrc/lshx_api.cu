@@ -233,12 +233,19 @@ static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_o
       h->tc != nullptr && (h->kernel_pref == LSHX_KERNEL_TCGEN05 ||
                            (h->kernel_pref == LSHX_KERNEL_AUTO &&
                             (reinterpret_cast<uintptr_t>(d_X) & 15) == 0));
-  if (use_tc) {
-    h->last_kernel = LSHX_KERNEL_TCGEN05;
-    return launch_hash_tc(h->s, h->tc, d_X, n, d_out, d_flag, st);
+  h->last_kernel = use_tc ? LSHX_KERNEL_TCGEN05 : LSHX_KERNEL_FFMA;
+  // one launch takes < 2^31 rows (TMA coordinates / grid size are 32-bit): split larger batches
+  const int64_t piece = 1ll << 30;
+  for (int64_t r0 = 0; r0 < n; r0 += piece) {
+    const int64_t rows = (n - r0 < piece) ? (n - r0) : piece;
+    const float* x = d_X + r0 * h->s.dim;
+    uint8_t* o = d_out + r0 * h->s.sig_bytes;
+    uint8_t* f = d_flag ? d_flag + r0 : nullptr;
+    const int rc = use_tc ? launch_hash_tc(h->s, h->tc, x, rows, o, f, st)
+                          : launch_hash_ffma(h->s, x, rows, h->d_Rp, o, f, st);
+    if (rc != LSHX_OK) return rc;
   }
-  h->last_kernel = LSHX_KERNEL_FFMA;
-  return launch_hash_ffma(h->s, d_X, n, h->d_Rp, d_out, d_flag, st);
+  return LSHX_OK;
 }
 
 extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_is_device,
