@@ -283,3 +283,29 @@ def test_auto_kernel_and_per_vector_latency_path(name):
                                  oracle.projection_margins(projs, X[:3][finite[:3]]), REL_MARGIN)
     assert rep3["flips_outside_margin"] == 0, rep3
     np.testing.assert_array_equal(flag3, [oracle.is_zero_vector(x) for x in X[:3]])
+
+
+def _random_shapes(count, seed):
+    rng = np.random.default_rng(seed)
+    shapes = []
+    for _ in range(count):
+        nb = int(rng.integers(1, 41))
+        r = int(rng.choice([1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 17, 24, 31, 32, 33, 64, 70]))
+        dim = int(rng.choice([4, 8, 12, 20, 32, 36, 64, 100, 128, 132, 200, 256, 300]))
+        n = int(rng.integers(1, 700))
+        shapes.append((nb, r, dim, n))
+    return shapes
+
+
+@pytest.mark.parametrize("kernel", ("tcgen05", "ffma", "auto"))
+def test_random_shapes_against_oracle(kernel):
+    """Shape fuzz: band counts, ragged rows_per_band (compact / padded column layouts, one or more
+    passes), K padding, ragged batch sizes -- every combination must reproduce the oracle's bytes."""
+    for nb, r, dim, n in _random_shapes(40, seed=2024):
+        X = np.random.default_rng(nb * 1000 + r * 10 + dim).standard_normal((n, dim)).astype(np.float32)
+        h = _hasher(nb, r, dim, 7, kernel)
+        got, flag = h.hash_batch_packed(X, return_zero_flag=True)
+        assert got.shape == (n, nb, (r + 7) // 8)
+        _assert_parity(got, X, h.projections, f"{kernel} {nb}x{r} dim={dim} n={n}")
+        assert not flag.any()
+        h.close()
