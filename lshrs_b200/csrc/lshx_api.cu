@@ -375,7 +375,8 @@ extern "C" int lshx_hasher_destroy(lshx_hasher* h) {
 struct lshx_reranker {
   int device = 0;
   int dim = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;  // host-buffer calls alternate query chunks on the two
+  cudaEvent_t ev = nullptr;
   DevBuf q, vecs, offs, ids, pos, score, count, zero, all;
   std::mutex mu;
 };
@@ -390,9 +391,12 @@ extern "C" int lshx_rerank_create(int device, int dim, lshx_reranker** out) {
   lshx_reranker* r = new lshx_reranker();
   r->device = device;
   r->dim = dim;
-  if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&r->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&r->ev, cudaEventDisableTiming) != cudaSuccess) {
     set_error("cudaStreamCreate failed");
-    delete r;
+    (void)cudaGetLastError();
+    lshx_rerank_destroy(r);
     return LSHX_ERR_CUDA;
   }
   *out = r;
@@ -407,6 +411,8 @@ extern "C" int lshx_rerank_destroy(lshx_reranker* r) {
     for (DevBuf* b : {&r->q, &r->vecs, &r->offs, &r->ids, &r->pos, &r->score, &r->count, &r->zero, &r->all})
       b->release();
     if (r->stream) cudaStreamDestroy(r->stream);
+    if (r->stream2) cudaStreamDestroy(r->stream2);
+    if (r->ev) cudaEventDestroy(r->ev);
     (void)cudaGetLastError();
   }
   delete r;
@@ -470,58 +476,107 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
   if (!select) LSHX_REQUIRE(total_candidates >= end, "out_scores too small");
   a.max_cand = maxc;
 
-  cudaStream_t st = r->stream;
   LSHX_CUDA(cudaStreamSynchronize(user));  // a device-resident corpus may still be being written there
   int rc;
   if ((rc = r->q.reserve((size_t)nq * dim * sizeof(float))) != LSHX_OK) return rc;
   if ((rc = r->offs.reserve((size_t)(nq + 1) * sizeof(int64_t))) != LSHX_OK) return rc;
-  LSHX_CUDA(cudaMemcpyAsync(r->q.p, Q, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, st));
-  LSHX_CUDA(cudaMemcpyAsync(r->offs.p, cand_offsets, (size_t)(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-  a.Q = static_cast<const float*>(r->q.p);
-  a.offs = static_cast<const int64_t*>(r->offs.p);
-  if (cand_ids && end > 0) {
-    if ((rc = r->ids.reserve((size_t)end * sizeof(int64_t))) != LSHX_OK) return rc;
-    LSHX_CUDA(cudaMemcpyAsync(r->ids.p, cand_ids, (size_t)end * sizeof(int64_t), cudaMemcpyHostToDevice, st));
-    a.ids = static_cast<const int64_t*>(r->ids.p);
-  }
-  if (on_device == 2) {
-    a.V = vectors;
-  } else if (total > 0) {
-    // host vectors: packed candidates copy only the rows that are referenced
-    const int64_t rows = cand_ids ? n_vectors : end;
-    if ((rc = r->vecs.reserve((size_t)rows * dim * sizeof(float))) != LSHX_OK) return rc;
-    LSHX_CUDA(cudaMemcpyAsync(r->vecs.p, vectors, (size_t)rows * dim * sizeof(float), cudaMemcpyHostToDevice, st));
-    a.V = static_cast<const float*>(r->vecs.p);
-    a.n_vectors = rows;
-  }
+  if (cand_ids && end > 0 && (rc = r->ids.reserve((size_t)end * sizeof(int64_t))) != LSHX_OK) return rc;
+  const bool host_vectors = (on_device != 2) && total > 0;
+  const int64_t vec_rows = cand_ids ? n_vectors : end;
+  if (host_vectors && (rc = r->vecs.reserve((size_t)vec_rows * dim * sizeof(float))) != LSHX_OK) return rc;
   if (select) {
     if ((rc = r->pos.reserve((size_t)nq * out_stride * sizeof(int32_t))) != LSHX_OK) return rc;
     if ((rc = r->score.reserve((size_t)nq * out_stride * sizeof(float))) != LSHX_OK) return rc;
     if ((rc = r->count.reserve((size_t)nq * sizeof(int32_t))) != LSHX_OK) return rc;
-    a.out_pos = static_cast<int32_t*>(r->pos.p);
-    a.out_score = static_cast<float*>(r->score.p);
-    a.out_count = static_cast<int32_t*>(r->count.p);
   } else {
     if ((rc = r->all.reserve((size_t)(end > 0 ? end : 1) * sizeof(float))) != LSHX_OK) return rc;
-    a.all_scores = static_cast<float*>(r->all.p);
   }
   if ((rc = r->zero.reserve((size_t)nq * sizeof(int32_t))) != LSHX_OK) return rc;
-  a.out_zero = static_cast<int32_t*>(r->zero.p);
 
-  rc = launch_rerank(a, st);
-  if (rc != LSHX_OK) return rc;
+  float* d_q = static_cast<float*>(r->q.p);
+  int64_t* d_offs = static_cast<int64_t*>(r->offs.p);
+  int64_t* d_ids = cand_ids ? static_cast<int64_t*>(r->ids.p) : nullptr;
+  float* d_vecs = static_cast<float*>(r->vecs.p);
+  a.ids = (cand_ids && end > 0) ? d_ids : nullptr;
+  a.V = host_vectors ? d_vecs : vectors;
+  if (host_vectors) a.n_vectors = vec_rows;
 
-  if (select) {
-    LSHX_CUDA(cudaMemcpyAsync(out_pos, a.out_pos, (size_t)nq * out_stride * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    LSHX_CUDA(cudaMemcpyAsync(out_score, a.out_score, (size_t)nq * out_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
-    LSHX_CUDA(cudaMemcpyAsync(out_count, a.out_count, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  } else if (end > 0) {
-    LSHX_CUDA(cudaMemcpyAsync(out_all, a.all_scores, (size_t)end * sizeof(float), cudaMemcpyDeviceToHost, st));
+  // everything every chunk needs first: the offsets, and a host corpus that ids gather from
+  cudaStream_t streams[2] = {r->stream, r->stream2};
+  LSHX_CUDA(cudaMemcpyAsync(d_offs, cand_offsets, (size_t)(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                            streams[0]));
+  if (host_vectors && cand_ids)
+    LSHX_CUDA(cudaMemcpyAsync(d_vecs, vectors, (size_t)vec_rows * dim * sizeof(float), cudaMemcpyHostToDevice,
+                              streams[0]));
+  LSHX_CUDA(cudaEventRecord(r->ev, streams[0]));
+  LSHX_CUDA(cudaStreamWaitEvent(streams[1], r->ev, 0));
+
+  // query chunks alternate between two streams so the H2D of one overlaps the kernel of the other
+  const int64_t qchunk = (nq >= 1024) ? (nq + 7) / 8 : nq;
+  int slot = 0;
+  for (int64_t c0 = 0; c0 < nq; c0 += qchunk, slot ^= 1) {
+    const int64_t c1 = (c0 + qchunk < nq) ? c0 + qchunk : nq;
+    const int64_t s0 = cand_offsets[c0], s1 = cand_offsets[c1];  // candidate slots of this chunk
+    cudaStream_t st = streams[slot];
+    LSHX_CUDA(cudaMemcpyAsync(d_q + c0 * dim, Q + c0 * dim, (size_t)(c1 - c0) * dim * sizeof(float),
+                              cudaMemcpyHostToDevice, st));
+    if (a.ids && s1 > s0)
+      LSHX_CUDA(cudaMemcpyAsync(d_ids + s0, cand_ids + s0, (size_t)(s1 - s0) * sizeof(int64_t),
+                                cudaMemcpyHostToDevice, st));
+    if (host_vectors && !cand_ids && s1 > s0)  // packed candidates: the rows of this chunk's queries
+      LSHX_CUDA(cudaMemcpyAsync(d_vecs + s0 * dim, vectors + s0 * dim, (size_t)(s1 - s0) * dim * sizeof(float),
+                                cudaMemcpyHostToDevice, st));
+    RerankArgs c = a;
+    c.nq = c1 - c0;
+    c.Q = d_q + c0 * dim;
+    c.offs = d_offs + c0;
+    c.out_zero = static_cast<int32_t*>(r->zero.p) + c0;
+    if (select) {
+      c.out_pos = static_cast<int32_t*>(r->pos.p) + c0 * out_stride;
+      c.out_score = static_cast<float*>(r->score.p) + c0 * out_stride;
+      c.out_count = static_cast<int32_t*>(r->count.p) + c0;
+    } else {
+      c.all_scores = static_cast<float*>(r->all.p);
+    }
+    rc = launch_rerank(c, st);
+    if (rc != LSHX_OK) return rc;
+    if (select) {
+      LSHX_CUDA(cudaMemcpyAsync(out_pos + c0 * out_stride, c.out_pos, (size_t)(c1 - c0) * out_stride * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, st));
+      LSHX_CUDA(cudaMemcpyAsync(out_score + c0 * out_stride, c.out_score,
+                                (size_t)(c1 - c0) * out_stride * sizeof(float), cudaMemcpyDeviceToHost, st));
+      LSHX_CUDA(cudaMemcpyAsync(out_count + c0, c.out_count, (size_t)(c1 - c0) * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, st));
+    } else if (s1 > s0) {
+      LSHX_CUDA(cudaMemcpyAsync(out_all + s0, c.all_scores + s0, (size_t)(s1 - s0) * sizeof(float),
+                                cudaMemcpyDeviceToHost, st));
+    }
+    if (out_zero)
+      LSHX_CUDA(cudaMemcpyAsync(out_zero + c0, c.out_zero, (size_t)(c1 - c0) * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, st));
   }
-  if (out_zero)
-    LSHX_CUDA(cudaMemcpyAsync(out_zero, a.out_zero, (size_t)nq * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  LSHX_CUDA(cudaStreamSynchronize(st));
+  LSHX_CUDA(cudaStreamSynchronize(streams[0]));
+  LSHX_CUDA(cudaStreamSynchronize(streams[1]));
   return LSHX_OK;
+}
+
+extern "C" int lshx_rerank_topk(lshx_reranker* r, const float* Q, int64_t nq, const float* vectors,
+                                int64_t n_vectors, const int64_t* cand_offsets,
+                                const int64_t* cand_ids, int64_t max_candidates, int k, double p,
+                                int out_stride, int32_t* out_pos, float* out_score,
+                                int32_t* out_count, int32_t* out_zero, int on_device, void* stream) {
+  return rerank_common(r, Q, nq, vectors, n_vectors, cand_offsets, cand_ids, max_candidates, 0,
+                       true, k, p, out_stride, out_pos, out_score, out_count, nullptr, out_zero,
+                       on_device, stream);
+}
+
+extern "C" int lshx_rerank_scores(lshx_reranker* r, const float* Q, int64_t nq, const float* vectors,
+                                  int64_t n_vectors, const int64_t* cand_offsets,
+                                  const int64_t* cand_ids, int64_t total_candidates,
+                                  float* out_scores, int32_t* out_zero, int on_device, void* stream) {
+  return rerank_common(r, Q, nq, vectors, n_vectors, cand_offsets, cand_ids, 0, total_candidates,
+                       false, 0, 0.0, 0, nullptr, nullptr, nullptr, out_scores, out_zero, on_device,
+                       stream);
 }
 
 extern "C" int lshx_l2_normalize(lshx_reranker* r, const float* X, int64_t n, float* out,
@@ -551,21 +606,3 @@ extern "C" int lshx_l2_normalize(lshx_reranker* r, const float* X, int64_t n, fl
   return LSHX_OK;
 }
 
-extern "C" int lshx_rerank_topk(lshx_reranker* r, const float* Q, int64_t nq, const float* vectors,
-                                int64_t n_vectors, const int64_t* cand_offsets,
-                                const int64_t* cand_ids, int64_t max_candidates, int k, double p,
-                                int out_stride, int32_t* out_pos, float* out_score,
-                                int32_t* out_count, int32_t* out_zero, int on_device, void* stream) {
-  return rerank_common(r, Q, nq, vectors, n_vectors, cand_offsets, cand_ids, max_candidates, 0,
-                       true, k, p, out_stride, out_pos, out_score, out_count, nullptr, out_zero,
-                       on_device, stream);
-}
-
-extern "C" int lshx_rerank_scores(lshx_reranker* r, const float* Q, int64_t nq, const float* vectors,
-                                  int64_t n_vectors, const int64_t* cand_offsets,
-                                  const int64_t* cand_ids, int64_t total_candidates,
-                                  float* out_scores, int32_t* out_zero, int on_device, void* stream) {
-  return rerank_common(r, Q, nq, vectors, n_vectors, cand_offsets, cand_ids, 0, total_candidates,
-                       false, 0, 0.0, 0, nullptr, nullptr, nullptr, out_scores, out_zero, on_device,
-                       stream);
-}
