@@ -2,7 +2,7 @@
 
 from __future__ import annotations
 
-from collections.abc import Iterable, Iterator
+from collections.abc import Iterator
 from dataclasses import dataclass, field
 
 
@@ -56,4 +56,4 @@ def signatures_from_packed(packed, bytes_per_band: int) -> list[HashSignatures]:
     return out
 
 
-__all__ = ["HashSignatures", "signatures_from_packed", "Iterable"]
+__all__ = ["HashSignatures", "signatures_from_packed"]

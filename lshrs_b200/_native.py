@@ -11,7 +11,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_uint64, c_void_p
 from pathlib import Path
 
 __all__ = [
@@ -179,8 +179,3 @@ def device_count() -> int:
     """Usable sm_100 devices (0 on a CPU-only machine)."""
     return int(lib().lshx_device_count())
 
-
-# re-exported for type hints in the wrappers
-c_float_p = POINTER(c_float)
-c_uint8_p = POINTER(c_uint8)
-c_int32_p = POINTER(c_int32)

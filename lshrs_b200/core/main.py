@@ -20,7 +20,6 @@ once and reranks all of them in one launch.
 from __future__ import annotations
 
 import logging
-import math
 from collections.abc import Callable, Sequence
 from threading import Lock
 from typing import Any, Optional, Union
