@@ -357,6 +357,66 @@ class LSHRS:
             "similarity_threshold": c["similarity_threshold"], "redis_prefix": self._redis_config["prefix"],
         }
 
+    # ------------------------------------------------------------------ persistence
+    # Same on-disk / pickle formats as the reference (main.py:846-1044): metadata.json + projections.npz
+    # (arr_0 .. arr_{b-1}); bucket data lives in the storage backend and is not saved.
+    def save_to_disk(self, path) -> None:
+        import json
+        from pathlib import Path
+
+        self.flush()
+        out = Path(path)
+        out.mkdir(parents=True, exist_ok=True)
+        redis_cfg = dict(self._redis_config)
+        if "password" in redis_cfg:
+            redis_cfg["password"] = "<REDACTED>"
+        meta = {"version": "0.1.1a4", "config": self._config, "redis_config": redis_cfg}
+        (out / "metadata.json").write_text(json.dumps(meta, indent=2))
+        np.savez_compressed(out / "projections.npz", *self._hasher.projections)
+
+    @classmethod
+    def load_from_disk(cls, path, *, redis_config: Optional[dict[str, Any]] = None,
+                       vector_fetch_fn: Optional[VectorFetchFn] = None,
+                       storage: Optional[BucketStorage] = None) -> "LSHRS":
+        import json
+        from pathlib import Path
+
+        src = Path(path)
+        if not src.exists():
+            raise FileNotFoundError(f"Directory not found: {src}")
+        meta = json.loads((src / "metadata.json").read_text())
+        cfg = meta["config"]
+        red = dict(meta["redis_config"])
+        if redis_config:
+            red.update(redis_config)
+        inst = cls(dim=cfg["dim"], num_perm=cfg["num_perm"], num_bands=cfg["num_bands"],
+                   rows_per_band=cfg["rows_per_band"], similarity_threshold=cfg["similarity_threshold"],
+                   buffer_size=cfg["buffer_size"], vector_fetch_fn=vector_fetch_fn, storage=storage,
+                   redis_host=red["host"], redis_port=red["port"], redis_db=red["db"], redis_password=red["password"],
+                   redis_prefix=red["prefix"], decode_responses=red["decode_responses"], seed=cfg["seed"])
+        with np.load(src / "projections.npz") as data:
+            inst._hasher.projections = [data[f"arr_{i}"].astype(np.float32) for i in range(len(data.files))]
+        return inst
+
+    def __getstate__(self) -> dict[str, Any]:
+        self.flush()
+        return {
+            "config": dict(self._config), "redis_config": dict(self._redis_config),
+            "projections": [np.asarray(m, dtype=np.float32) for m in self._hasher.projections],
+            "storage": self._storage if not type(self._storage).__module__.startswith("lshrs.storage") else None,
+        }
+
+    def __setstate__(self, state: dict[str, Any]) -> None:
+        cfg, red = state["config"], state["redis_config"]
+        restored = self.__class__(
+            dim=cfg["dim"], num_perm=cfg["num_perm"], num_bands=cfg["num_bands"], rows_per_band=cfg["rows_per_band"],
+            similarity_threshold=cfg["similarity_threshold"], buffer_size=cfg["buffer_size"], vector_fetch_fn=None,
+            storage=state.get("storage"), redis_host=red["host"], redis_port=red["port"], redis_db=red["db"],
+            redis_password=red["password"], redis_prefix=red["prefix"], decode_responses=red["decode_responses"],
+            seed=cfg["seed"])
+        self.__dict__ = restored.__dict__
+        self._hasher.projections = [np.asarray(m, dtype=np.float32) for m in state["projections"]]
+
     # ------------------------------------------------------------------ helpers
     def _prepare_vector(self, vector: np.ndarray) -> np.ndarray:
         arr = np.asarray(vector, dtype=np.float32).reshape(-1)

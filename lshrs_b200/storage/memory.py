@@ -79,3 +79,12 @@ class InMemoryStorage:
     def __len__(self) -> int:
         with self._lock:
             return sum(1 for m in self._buckets.values() if m)
+
+    def __getstate__(self) -> dict:
+        with self._lock:
+            return {"prefix": self.prefix, "buckets": {k: set(v) for k, v in self._buckets.items()}}
+
+    def __setstate__(self, state: dict) -> None:
+        self.prefix = state["prefix"]
+        self._buckets = state["buckets"]
+        self._lock = threading.Lock()

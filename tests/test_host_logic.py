@@ -123,3 +123,27 @@ def test_shard_bounds_cover_and_align():
             assert all(lo % 128 == 0 for lo, _ in b if lo < n)
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 128 + (128 - 1)
+
+
+def test_save_load_and_pickle_round_trip(tmp_path):
+    # reference tests/test_persistence_security.py:15-70, 114-132 (formats are the reference's)
+    import json
+    import pickle
+
+    lsh = _lsh(redis_password="secret", seed=7)
+    lsh._hasher.projections = [m + 1.0 for m in lsh._hasher.projections]  # state that only a save carries
+    lsh.save_to_disk(tmp_path / "idx")
+    meta = json.loads((tmp_path / "idx" / "metadata.json").read_text())
+    assert meta["redis_config"]["password"] == "<REDACTED>" and meta["config"]["seed"] == 7
+    with np.load(tmp_path / "idx" / "projections.npz") as data:
+        assert sorted(data.files) == ["arr_0", "arr_1", "arr_2", "arr_3"]
+    back = LSHRS.load_from_disk(tmp_path / "idx", storage=InMemoryStorage())
+    assert back.stats() == lsh.stats()
+    for a, b in zip(back._hasher.projections, lsh._hasher.projections):
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(FileNotFoundError):
+        LSHRS.load_from_disk(tmp_path / "missing")
+    clone = pickle.loads(pickle.dumps(lsh))
+    assert clone.stats() == lsh.stats()
+    for a, b in zip(clone._hasher.projections, lsh._hasher.projections):
+        np.testing.assert_array_equal(a, b)
