@@ -7,10 +7,11 @@ reranker: ``ingest`` (main.py:386-411), ``index`` (442-518), ``flush``
 (1050-1143) -- same signatures, validation order, error types and messages,
 same ``(band_id, bytes, index)`` operations with the same flush boundaries.
 Bucket storage is NOT re-implemented: pass the reference's ``RedisStorage`` (or
-anything with its five methods) as ``storage=``; persistence, pickling and the
-Postgres/Parquet loaders are host control flow that stays in the reference
+anything with its five methods) as ``storage=``.  ``save_to_disk`` /
+``load_from_disk`` / pickling keep the reference's formats, ``create_signatures``
+takes the Arrow-buffer Parquet feed; the PostgreSQL loader stays in the reference
 (INTEGRATION.md shows the two-import patch that puts the reference's own
-``LSHRS`` on these kernels).
+``LSHRS`` on these kernels instead).
 
 What is new is batching: ``index()`` hashes the whole batch in ONE kernel call
 with the zero-vector test fused in, and ``query_batch`` hashes all queries at
