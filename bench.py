@@ -188,6 +188,35 @@ def cpu_hash_sample(rows: int, seed: int = 0) -> np.ndarray:
     return x  # the reference arm always runs the metric's configuration (Gaussian, dim 768)
 
 
+def _mp_hash_worker(job):
+    from oracle import lshrs_oracle as oracle
+
+    seed, rows = job
+    projs = oracle.make_projections(NUM_BANDS, ROWS_PER_BAND, DIM, SEED)
+    X = cpu_hash_sample(rows, seed=seed)
+    t0 = time.perf_counter()
+    oracle.hash_batch_packed(projs, X)
+    return time.perf_counter() - t0
+
+
+def multiprocess_port_rate(rows_per_worker: int = 4096) -> dict:
+    """The same per-vector loop sharded over every host core with one process each -- NOT something the
+    reference does (its API is one Python thread), printed so the single-thread figure is not the only one."""
+    import multiprocessing as mp
+
+    workers = len(os.sched_getaffinity(0))
+    try:
+        ctx = mp.get_context("fork")
+        t0 = time.perf_counter()
+        with ctx.Pool(workers) as pool:
+            pool.map(_mp_hash_worker, [(100 + i, rows_per_worker) for i in range(workers)])
+        wall = time.perf_counter() - t0
+        return {"value": workers * rows_per_worker / wall, "unit": UNIT, "cores": workers,
+                "sample": f"{workers} processes x {rows_per_worker} rows, wall clock incl. process start"}
+    except Exception as exc:  # noqa: BLE001
+        return {"value": None, "unit": UNIT, "cores": workers, "error": f"{type(exc).__name__}: {exc}"}
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -221,7 +250,8 @@ def run_reference(args) -> None:
                                    "single Python thread by construction)",
                          "host_cores": os.cpu_count(), "numpy": np.__version__,
                          "vectorized_numpy_not_reference": {"value": vec_value, "unit": UNIT,
-                                                            "cores": len(os.sched_getaffinity(0))}},
+                                                            "cores": len(os.sched_getaffinity(0))},
+                         "multiprocess_port_not_reference": multiprocess_port_rate()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
