@@ -83,6 +83,10 @@ def test_golden_signatures(name, kernel):
         (128, 8, 64, 3_000, "gauss"),       # 1024 bits: many column tiles
         (5, 20, 100, 2_000, "gauss"),       # ragged rows_per_band, dim % 32 != 0
         (3, 5, 7, 1_000, "gauss"),          # unaligned dim (no float4 path)
+        (64, 64, 256, 500, "gauss"),        # 4096 bits (reference PRECOMPUTED_CONFIGS shape): 16 passes
+        (16, 16, 4096, 300, "gauss"),       # long vectors: 128 K chunks
+        (2, 128, 64, 400, "gauss"),         # 128 rows per band: 16-byte band keys
+        (1, 1, 4, 100, "gauss"),            # smallest shape the TMA path takes
     ],
 )
 def test_parity_with_oracle(nb, r, dim, n, dist, kernel):
