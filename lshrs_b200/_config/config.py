@@ -45,14 +45,23 @@ class HashSignatures:
 
 
 def signatures_from_packed(packed, bytes_per_band: int) -> list[HashSignatures]:
-    """uint8[n, num_bands * bytes_per_band] (or [n, num_bands, bpb]) -> list of HashSignatures."""
-    arr = packed.reshape(packed.shape[0], -1)
-    blob = arr.tobytes()
-    stride = arr.shape[1]
+    """uint8[n, num_bands * bytes_per_band] (or [n, num_bands, bpb]) -> list of HashSignatures.
+
+    The band ``bytes`` objects are created in C by viewing the rows as fixed-width void items
+    (``tolist()`` of a ``V<bpb>`` array yields exact-length ``bytes``, trailing zeros included), and
+    the already-normalised tuples bypass ``__post_init__``: about 2x the per-object Python path.
+    """
+    import numpy as np
+
+    arr = np.ascontiguousarray(packed).reshape(packed.shape[0], -1)
+    rows = arr.view(f"V{bytes_per_band}").tolist()
+    new, set_field = object.__new__, object.__setattr__
     out = []
-    for i in range(arr.shape[0]):
-        base = i * stride
-        out.append(HashSignatures(tuple(blob[base + o : base + o + bytes_per_band] for o in range(0, stride, bytes_per_band))))
+    append = out.append
+    for row in rows:
+        sig = new(HashSignatures)
+        set_field(sig, "bands", tuple(row))
+        append(sig)
     return out
 
 
