@@ -213,19 +213,23 @@ class LSHRS:
             )
         packed, zero_flag = self._hasher.hash_batch_packed(arr, return_zero_flag=True)
         nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
-        blob = packed.tobytes()
-        stride = nb * bpb
+        # every band key as an exact-length bytes object, created in C (void-dtype tolist)
+        keys = np.ascontiguousarray(packed).reshape(len(indices), nb * bpb).view(f"V{bpb}").tolist()
+        flags = zero_flag.tolist()
+        band_ids = range(nb)
+        buffer, lock, limit = self._buffer, self._buffer_lock, self._buffer_size
         for row, idx in enumerate(indices):
             idx = int(idx)
             if idx < 0:
                 raise ValueError("index must be non-negative")
-            if zero_flag[row]:
+            if flags[row]:
                 raise ValueError(_ZERO_VECTOR_MSG)
-            base = row * stride
-            ops = [(b, blob[base + b * bpb : base + (b + 1) * bpb], idx) for b in range(nb)]
-            with self._buffer_lock:
-                self._buffer.extend(ops)
-            self._flush_buffer_if_needed()
+            ops = [(b, key, idx) for b, key in zip(band_ids, keys[row])]
+            with lock:
+                buffer.extend(ops)
+                due = len(buffer) >= limit
+            if due:
+                self.flush()
         self.flush()
 
     # ------------------------------------------------------------------ querying
