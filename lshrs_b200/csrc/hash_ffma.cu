@@ -84,16 +84,17 @@ hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* _
   const int KT = (dim + BK - 1) / BK;
   Frag4 xa, xb, ra, rb;
 
-  const float* px0 = (m0 + lrow < n) ? X + (m0 + lrow) * (int64_t)dim : nullptr;
-  const float* px1 = (m0 + lrow + 64 < n) ? X + (m0 + lrow + 64) * (int64_t)dim : nullptr;
-  const float* pr0 = Rp + (int64_t)(n0 + lrow) * dim;  // ncols_pad is a multiple of BN: in range
-  const float* pr1 = Rp + (int64_t)(n0 + lrow + 64) * dim;
+  // block-uniform 64-bit bases + per-thread 32-bit offsets (fewer live registers than four pointers)
+  const float* xbase = X + m0 * (int64_t)dim;
+  const float* rbase = Rp + (int64_t)n0 * dim;   // ncols_pad is a multiple of BN: always in range
+  const int o0 = lrow * dim, o1 = (lrow + 64) * dim;
+  const bool vx0 = (m0 + lrow < n), vx1 = (m0 + lrow + 64 < n);
   auto gload = [&](int kt) {
     const int k = kt * BK + lk;
-    xa = load4<VEC4>(px0, dim, k);
-    xb = load4<VEC4>(px1, dim, k);
-    ra = load4<VEC4>(pr0, dim, k);
-    rb = load4<VEC4>(pr1, dim, k);
+    xa = load4<VEC4>(vx0 ? xbase + o0 : nullptr, dim, k);
+    xb = load4<VEC4>(vx1 ? xbase + o1 : nullptr, dim, k);
+    ra = load4<VEC4>(rbase + o0, dim, k);
+    rb = load4<VEC4>(rbase + o1, dim, k);
   };
   auto sstore = [&](int buf) {
 #pragma unroll
