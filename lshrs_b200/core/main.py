@@ -301,14 +301,14 @@ class LSHRS:
         if zero_flag.any():
             raise ValueError(_ZERO_VECTOR_MSG)
         nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
-        blob = packed.tobytes()
-        stride = nb * bpb
+        # every (query, band) bucket in ONE storage round trip when the backend allows it
+        keys = np.ascontiguousarray(packed).reshape(nq, nb * bpb).view(f"V{bpb}").tolist()
+        buckets = self._fetch_buckets([(b, key) for row in keys for b, key in enumerate(row)])
         ordered_all: list[list[int]] = []
         for row in range(nq):
             counts: dict[int, int] = {}
-            base = row * stride
-            for b in range(nb):
-                for cand in self._storage.get_bucket(b, blob[base + b * bpb : base + (b + 1) * bpb]):
+            for members in buckets[row * nb:(row + 1) * nb]:
+                for cand in members:
                     counts[cand] = counts.get(cand, 0) + 1
             ordered = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))
             ordered_all.append([idx for idx, _ in ordered])
@@ -439,6 +439,32 @@ class LSHRS:
             for candidate in self._storage.get_bucket(band_id, hash_val):
                 counts[candidate] = counts.get(candidate, 0) + 1
         return counts
+
+    def _fetch_buckets(self, keys: list) -> list:
+        """Members of many ``(band_id, band_bytes)`` buckets, in order.
+
+        The reference asks Redis once per band per query (``get_bucket``: one SMEMBERS round trip each,
+        reference lshrs/core/main.py:1105-1109).  A batch of queries needs ``nq * num_bands`` buckets, so:
+        a backend with ``get_buckets`` gets one call; a reference ``RedisStorage`` gets ONE pipelined
+        round trip through its redis-py client; anything else falls back to per-bucket calls.
+        """
+        storage = self._storage
+        if hasattr(storage, "get_buckets"):
+            return storage.get_buckets(keys)
+        client = getattr(storage, "_client", None)
+        if client is not None and hasattr(client, "pipeline") and hasattr(storage, "bucket_key"):
+            out: list = []
+            for start in range(0, len(keys), 10_000):  # redis-py buffers the whole pipeline client-side
+                pipe = client.pipeline()
+                try:
+                    for band_id, hash_val in keys[start:start + 10_000]:
+                        pipe.smembers(storage.bucket_key(band_id, hash_val))
+                    replies = pipe.execute()
+                finally:
+                    pipe.reset()
+                out.extend({int(m) for m in reply} for reply in replies)
+            return out
+        return [storage.get_bucket(band_id, hash_val) for band_id, hash_val in keys]
 
     def _enqueue_operations(self, index: int, signatures: Union[HashSignatures, Sequence[bytes]]) -> None:
         ops = [(band_id, hash_val, int(index)) for band_id, hash_val in enumerate(signatures)]

@@ -63,6 +63,11 @@ class InMemoryStorage:
         with self._lock:
             return set(self._buckets.get(self.bucket_key(band_id, hash_val), ()))
 
+    def get_buckets(self, keys: Iterable[tuple[int, bytes]]) -> list[set[int]]:
+        """Many buckets in one call (the batched query path asks for nq * num_bands at once)."""
+        with self._lock:
+            return [set(self._buckets.get(self.bucket_key(b, h), ())) for b, h in keys]
+
     def remove_indices(self, indices: Iterable[int]) -> None:
         drop = {int(i) for i in indices}
         with self._lock:

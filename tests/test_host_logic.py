@@ -147,3 +147,68 @@ def test_save_load_and_pickle_round_trip(tmp_path):
     assert clone.stats() == lsh.stats()
     for a, b in zip(clone._hasher.projections, lsh._hasher.projections):
         np.testing.assert_array_equal(a, b)
+
+
+def test_fetch_buckets_strategies():
+    """query_batch asks for nq * num_bands buckets: one call / one pipelined round trip / per-key fallback."""
+    keys = [(0, b"\x01"), (1, b"\x02"), (0, b"\xff")]
+    mem = InMemoryStorage()
+    mem.batch_add([(0, b"\x01", 5), (1, b"\x02", 6), (1, b"\x02", 7)])
+    assert _lsh(storage=mem)._fetch_buckets(keys) == [{5}, {6, 7}, set()]
+
+    class FakePipe:
+        def __init__(self, data, log):
+            self.data, self.log, self.queued = data, log, []
+
+        def smembers(self, key):
+            self.queued.append(key)
+
+        def execute(self):
+            self.log.append(len(self.queued))
+            return [self.data.get(k, set()) for k in self.queued]
+
+        def reset(self):
+            self.queued = []
+
+    class FakeRedisStorage:  # the surface of the reference's RedisStorage that _fetch_buckets touches
+        prefix = "lsh"
+
+        def __init__(self):
+            self.round_trips = []
+            data = {"lsh:0:bucket:01": {b"5"}, "lsh:1:bucket:02": {b"6", b"7"}}
+            outer = self
+
+            class Client:
+                def pipeline(self):
+                    return FakePipe(data, outer.round_trips)
+
+            self._client = Client()
+
+        def bucket_key(self, band_id, hash_val):
+            return f"{self.prefix}:{band_id}:bucket:{hash_val.hex()}"
+
+        def batch_add(self, ops): ...
+        def get_bucket(self, b, h): raise AssertionError("per-key path must not be used")
+        def remove_indices(self, i): ...
+        def clear(self): ...
+        def close(self): ...
+
+    fake = FakeRedisStorage()
+    assert _lsh(storage=fake)._fetch_buckets(keys) == [{5}, {6, 7}, set()]
+    assert fake.round_trips == [3]  # one pipelined round trip
+
+    class PerKey:
+        def __init__(self):
+            self.calls = 0
+
+        def get_bucket(self, b, h):
+            self.calls += 1
+            return {b}
+
+        def batch_add(self, ops): ...
+        def remove_indices(self, i): ...
+        def clear(self): ...
+        def close(self): ...
+
+    pk = PerKey()
+    assert _lsh(storage=pk)._fetch_buckets(keys) == [{0}, {1}, {0}] and pk.calls == 3
