@@ -245,3 +245,24 @@ def test_create_signatures_from_parquet(tmp_path, rng):
     assert [len(b) for b in st.batches] == [128 * 4, 128 * 4, 44 * 4]   # one flush per loader batch
     for probe in (0, 150, 299):
         assert probe in lsh.get_top_k(data[probe], topk=5)
+
+
+def test_query_batch_with_device_resident_corpus(rng):
+    """vector_fetch_fn replaced by an id gather from a corpus held in HBM: same results."""
+    import torch
+
+    from lshrs_b200 import InMemoryStorage
+
+    data = rng.standard_normal((400, 32)).astype(np.float32)
+    data[200:] = data[:200] + 0.05 * rng.standard_normal((200, 32)).astype(np.float32)
+    lsh = make_lsh(InMemoryStorage(), vector_fetch_fn=lambda ids: data[np.asarray(ids)])
+    lsh.index(list(range(400)), data)
+    probes = data[[1, 50, 333, 399]]
+    host = lsh.query_batch(probes, top_k=None, top_p=0.5)
+    dev = lsh.query_batch(probes, top_k=None, top_p=0.5, corpus=torch.from_numpy(data).cuda())
+    assert [[i for i, _ in row] for row in dev] == [[i for i, _ in row] for row in host]
+    for a, b in zip(dev, host):
+        np.testing.assert_allclose([s for _, s in a], [s for _, s in b], atol=1e-6)
+    assert lsh.query_batch(probes, top_k=3, top_p=0.5, corpus=torch.from_numpy(data).cuda()) == [row[:3] for row in dev]
+    empty = make_lsh(InMemoryStorage())
+    assert empty.query_batch(probes, top_k=5) == [[], [], [], []]
