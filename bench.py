@@ -233,12 +233,21 @@ def run_reference(args) -> None:
         oracle.hash_batch_packed(projs, X)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    # not reference code: one sgemm + packbits over every BLAS thread, for honesty
+    # not reference code: one sgemm + packbits over every BLAS thread, for honesty (torchrun exports
+    # OMP_NUM_THREADS=1, so the BLAS pool is widened explicitly when threadpoolctl is there)
     Xv = cpu_hash_sample(131072, seed=1)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        blas_threads = threadpool_limits(limits=len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        blas_threads = None
     oracle.hash_batch_vectorized(projs, Xv[:4096])
     t1 = time.perf_counter()
     oracle.hash_batch_vectorized(projs, Xv)
     vec_value = Xv.shape[0] / (time.perf_counter() - t1)
+    if blas_threads is not None:
+        blas_threads.restore_original_limits()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
