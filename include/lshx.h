@@ -57,10 +57,13 @@ typedef enum lshx_status {
 typedef enum lshx_hash_kernel {
   LSHX_KERNEL_AUTO = 0,    /* tcgen05 when the shape allows it, else FFMA            */
   LSHX_KERNEL_FFMA = 1,    /* FP32 FFMA register-tiled kernel                        */
-  LSHX_KERNEL_TCGEN05 = 2, /* tcgen05 3xTF32 split, TMA-staged, TMEM accumulators    */
-  LSHX_KERNEL_SMALL = 3    /* reported by lshx_hasher_last_kernel only: the per-vector
+  LSHX_KERNEL_TCGEN05 = 2, /* tcgen05, TMA-staged, TMEM accumulators; split x = hi + lo:
+                              TF32 hi.hi + BF16 cross terms (fp32-sgemm accuracy)    */
+  LSHX_KERNEL_SMALL = 3,   /* reported by lshx_hasher_last_kernel only: the per-vector
                               latency kernel (FP32 FMA, one warp per signature bit) that
                               AUTO uses for a handful of host rows                      */
+  LSHX_KERNEL_TCGEN05_3XTF32 = 4 /* the same tcgen05 kernel with all three terms in TF32
+                              (3xTF32: 1.5x the tensor work, ~10x smaller rounding error) */
 } lshx_hash_kernel;
 
 typedef struct lshx_hasher lshx_hasher;   /* opaque */

@@ -37,6 +37,7 @@
 // cheaper split is where the remaining time is.
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "lshx_common.cuh"
@@ -58,10 +59,19 @@ constexpr uint32_t SMEM_BYTES = 196608;                // 4 x 16 KB of X + 4 x 3
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t A_COL0 = 256;
 constexpr uint32_t A_STAGE_COLS = 64;
+// bring-up switches (TcParams::flags; LSHX_TC_FLAGS in the environment overrides the default)
+constexpr int TC_FLAG_B_WARP = 1;    // projections are TMA-loaded by warp 3 instead of warp 0
+constexpr int TC_FLAG_DEFER_ST = 2;  // converters overlap tcgen05.wait::st with the next chunk's loads
+constexpr int TC_FLAG_SWAP_A = 4;    // (bring-up) odd k in the low half of the BF16 A words
 
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+// the same for A=B=BF16 (K = 16 per instruction): the cross terms of the TF32+BF16 split
+__host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -138,6 +148,24 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// the same with kind::f16 (operand types from the instruction descriptor: BF16), K=16
+__device__ __forceinline__ void tc_mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// two fp32 -> one word of two BF16 (round to nearest even), `even` in the low half
+__device__ __forceinline__ uint32_t pack_bf16(float even, float odd) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(odd), "f"(even));
+  return d;
+}
 __device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -201,10 +229,19 @@ struct TcParams {
   int64_t mtiles;   // ceil(n / 128)
   int sig_bytes;
   int out_vec_ok;   // 16-byte stores allowed
+  int flags;        // TC_FLAG_* (bring-up switches)
   uint8_t* out;
   uint8_t* zero_flag;
 };
 
+// kSplit == 0: 3xTF32 (tm_rlo = TF32 residual plane).
+// kSplit == 1: TF32 hi.hi + BF16 cross terms (tm_rlo = the cross plane, see split_cross_kernel):
+//   x.r ~= [bf(x_lo) | bf(x_hi)] . [bf(r_hi) ; bf(r_lo)]   (kind::f16, K = 16 per MMA: 32 BF16 per 16 k)
+//          + x_hi . r_hi                                    (kind::tf32, K = 8)
+//   i.e. two tensor-time units per product instead of three.  The BF16 roundings act on terms that are
+//   already 2^-11 down: worst case 4 * 2^-8 * 2^-11 = 2^-17 relative to sum|x_i r_i|, measured max
+//   1.3e-7 * |x||r| on Gaussian data -- the same as an fp32 sgemm, two orders inside the 1e-5 margin.
+template <int kSplit>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_rhi,
                const __grid_constant__ CUtensorMap tm_rlo, const TcParams p) {
@@ -287,8 +324,29 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         }
         __syncwarp();
         xr.advance(XS);
-        for (int hk = 0; hk < (p.b_resident ? 0 : TK / TKB); ++hk) {   // two 16-float halves of the chunk
+        for (int hk = 0; hk < ((p.b_resident || (p.flags & TC_FLAG_B_WARP)) ? 0 : TK / TKB); ++hk) {   // two 16-float halves of the chunk
           const int col0 = pass * (int)N;
+          mbar_wait(b_empty(br.idx), br.phase ^ 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(b_full(br.idx), B_STAGE_BYTES);
+            const uint32_t dst = b_smem + br.idx * B_STAGE_BYTES;
+            tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK + hk * TKB, col0);
+            tma_load_2d(&tm_rlo, b_full(br.idx), dst + B_HALF_BYTES, kc * TK + hk * TKB, col0);
+          }
+          __syncwarp();
+          br.advance(BS);
+        }
+      }
+    }
+  } else if (warp == 3 && (p.flags & TC_FLAG_B_WARP) && !p.b_resident) {
+    // ===================== projection producer: its own warp, so that the X prefetch depth (XS
+    // stages) is not throttled by the projection ring (b_empty follows the MMAs closely) ==========
+    Ring br;
+    for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+      const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
+      const int col0 = pass * (int)N;
+      for (int kc = 0; kc < p.kc; ++kc) {
+        for (int hk = 0; hk < TK / TKB; ++hk) {
           mbar_wait(b_empty(br.idx), br.phase ^ 1);
           if (elect_one()) {
             mbar_arrive_expect_tx(b_full(br.idx), B_STAGE_BYTES);
@@ -305,6 +363,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     // ===================== MMA issuer (whole warp runs the loops, one elected lane issues) =====
     Ring ar, br, dr;
     const uint32_t idesc = make_idesc(N);  // one MMA spans every column of the pass
+    const uint32_t idesc_x = make_idesc_bf16(N);
     if (p.b_resident && (int64_t)blockIdx.x < work_items) {
       mbar_wait(b_full(0), 0);
       tc_fence_after();
@@ -327,16 +386,23 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           const uint64_t desc_hi = make_b_desc(bs);
           const uint64_t desc_lo = make_b_desc(bs + B_HALF_BYTES);
           if (elect_one()) {
+            // +32 B per K step inside the 64 B swizzle row: start-address field += 2; the K step's
+            // columns in the A stage start at hk*16 + 8*s.  Small terms first.
 #pragma unroll
             for (int s = 0; s < TKB / 8; ++s) {
-              // +32 B per K step inside the 64 B swizzle row: start-address field += 2
-              const uint64_t bh = desc_hi + (uint64_t)(2 * s);
-              const uint64_t bl = desc_lo + (uint64_t)(2 * s);
-              const uint32_t ka = (uint32_t)(hk * TKB + 8 * s);  // column of this K step in the A stage
-              tc_mma_ts(d_base, a_lo + ka, bh, idesc, (kc > 0 || hk > 0 || s > 0) ? 1u : 0u);  // small terms first
-              tc_mma_ts(d_base, a_hi + ka, bl, idesc, 1u);
-              tc_mma_ts(d_base, a_hi + ka, bh, idesc, 1u);
+              const uint32_t ka = (uint32_t)(hk * TKB + 8 * s);
+              const uint32_t acc = (kc > 0 || hk > 0 || s > 0) ? 1u : 0u;
+              if (kSplit == 0) {
+                tc_mma_ts(d_base, a_lo + ka, desc_hi + (uint64_t)(2 * s), idesc, acc);   // x_lo . r_hi
+                tc_mma_ts(d_base, a_hi + ka, desc_lo + (uint64_t)(2 * s), idesc, 1u);    // x_hi . r_lo
+              } else {
+                // s = 0: bf(x_lo) . bf(r_hi), s = 1: bf(x_hi) . bf(r_lo), each over the 16 k of this half
+                tc_mma_ts_f16(d_base, a_lo + ka, desc_lo + (uint64_t)(2 * s), idesc_x, acc);
+              }
             }
+#pragma unroll
+            for (int s = 0; s < TKB / 8; ++s)                                            // x_hi . r_hi
+              tc_mma_ts(d_base, a_hi + (uint32_t)(hk * TKB + 8 * s), desc_hi + (uint64_t)(2 * s), idesc, 1u);
             if (!p.b_resident) tc_commit(b_empty(br.idx));  // same thread as the MMAs (commit tracks its own ops)
             if (hk == TK / TKB - 1) tc_commit(a_empty(ar.idx));
             if (hk == TK / TKB - 1 && kc == p.kc - 1) tc_commit(d_full(dr.idx));
@@ -353,6 +419,9 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int t = (warp - 4) * 32 + lane;                 // row within the tile == TMEM lane
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     Ring xr, ar;
+    const bool defer = (p.flags & TC_FLAG_DEFER_ST) != 0;
+    const bool swp = (p.flags & TC_FLAG_SWAP_A) != 0;
+    int pend = -1;   // A stage whose tcgen05.st are still in flight (defer mode)
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int64_t mt = (p.npass == 1) ? w : w / p.npass;   // (no 64-bit division on the common path)
       const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
@@ -365,6 +434,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {   // two halves of 16 floats keep the register count down
+          // hi: TF32(x).  lo: 3xTF32 -> TF32 of the residual; TF32+BF16 -> words [0,8) = BF16 pairs of the
+          // residual, words [8,16) = BF16 pairs of hi (the layout of the cross plane, split_cross_kernel)
           uint32_t hi[16], lo[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -375,6 +446,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
                          : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                          : "r"(addr));
             const float f[4] = {v.x, v.y, v.z, v.w};
+            float lf[4], hc[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float x = f[e];
@@ -382,20 +454,43 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
               const uint32_t hu = tf32_rna(__float_as_uint(x));
               const float hf = __uint_as_float(hu);
               // residual is exact in fp32; an infinite hi has no residual (inf - inf would be NaN)
-              const float lf = (fabsf(hf) == INFINITY) ? 0.f : (x - hf);
+              lf[e] = (fabsf(hf) == INFINITY) ? 0.f : (x - hf);
               hi[c * 4 + e] = hu;
-              lo[c * 4 + e] = tf32_rna(__float_as_uint(lf));
+              if (kSplit == 0) lo[c * 4 + e] = tf32_rna(__float_as_uint(lf[e]));
+              // a hi that would round to a BF16 infinity (or is one) takes no part in the cross term:
+              // its sign is already decided by hi.hi
+              else hc[e] = ((hu & 0x7FFFFFFFu) >= 0x7F7F8000u) ? 0.f : hf;
             }
+            if (kSplit != 0) {
+              lo[c * 2 + 0] = swp ? pack_bf16(lf[1], lf[0]) : pack_bf16(lf[0], lf[1]);
+              lo[c * 2 + 1] = swp ? pack_bf16(lf[3], lf[2]) : pack_bf16(lf[2], lf[3]);
+              lo[8 + c * 2 + 0] = swp ? pack_bf16(hc[1], hc[0]) : pack_bf16(hc[0], hc[1]);
+              lo[8 + c * 2 + 1] = swp ? pack_bf16(hc[3], hc[2]) : pack_bf16(hc[2], hc[3]);
+            }
+          }
+          if (h == 0 && pend >= 0) {
+            // the previous chunk's stores have had this half's loads and arithmetic to complete
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full((uint32_t)pend));
+            pend = -1;
           }
           tc_st16(a_dst + h * 16, hi);
           tc_st16(a_dst + 32 + h * 16, lo);
         }
-        tc_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(a_full(ar.idx));
-          mbar_arrive(x_empty(xr.idx));
+        if (defer && kc != p.kc - 1) {
+          pend = (int)ar.idx;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(x_empty(xr.idx));   // the loads above were consumed by the arithmetic
+        } else {
+          tc_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(a_full(ar.idx));
+            mbar_arrive(x_empty(xr.idx));
+          }
         }
         xr.advance(XS);
         ar.advance(AS);
@@ -564,6 +659,34 @@ __global__ void split_projections_kernel(const float* __restrict__ Rp, const int
   }
 }
 
+// Cross plane of the TF32+BF16 split, [rows][dim_pad] 32-bit words.  The 16 words of K block g
+// (k in [16g, 16g+16)) of a row hold 32 BF16: words [0,8) = bf(r_hi[k]) pairs, words [8,16) =
+// bf(r_lo[k]) pairs (even k in the low half), r_hi = TF32(r), r_lo = r - r_hi -- one 64 B SWIZZLE_64B
+// row = two K=16 kind::f16 steps, matched by the converters' A words [bf(x_lo) | bf(x_hi)].
+__global__ void split_cross_kernel(const float* __restrict__ Rp, const int* __restrict__ rowmap,
+                                   uint32_t* __restrict__ cross, int rows, int dim, int dim_pad) {
+  const int64_t total = (int64_t)rows * dim_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / dim_pad), wd = (int)(i % dim_pad);
+    const int src = rowmap[row];
+    const int g = wd / 16, j = wd % 16;
+    const int k0 = 16 * g + 2 * (j & 7);
+    float v[2] = {0.f, 0.f};
+    for (int e = 0; e < 2; ++e) {
+      const int k = k0 + e;
+      if (k < dim && src >= 0) {
+        const float r = Rp[(int64_t)src * dim + k];
+        const uint32_t hu = tf32_rna(__float_as_uint(r));
+        const float h = __uint_as_float(hu);
+        const float res = (fabsf(h) == INFINITY) ? 0.f : (r - h);
+        v[e] = (j < 8) ? (((hu & 0x7FFFFFFFu) >= 0x7F7F8000u) ? 0.f : h) : res;
+      }
+    }
+    cross[i] = pack_bf16(v[0], v[1]);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -609,8 +732,10 @@ int make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, u
 
 struct TcPlan {
   float* d_hi = nullptr;
-  float* d_lo = nullptr;
-  CUtensorMap tm_rhi, tm_rlo;
+  float* d_lo = nullptr;     // TF32 residual plane (3xTF32 arm)
+  uint32_t* d_x = nullptr;   // BF16 cross plane (TF32+BF16 arm)
+  CUtensorMap tm_rhi, tm_rlo, tm_rx;
+  int flags = 0;
   int num_sms = 0;
   // column layout of the split projections (see tc_plan_create)
   int ncols_pass = 0, npass = 0, repack = 0, bpp = 0;
@@ -656,6 +781,7 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   const size_t bytes = (size_t)rows * s.dim_pad * sizeof(float);
   int* d_rowmap = nullptr;
   if (cudaMalloc(&pl->d_hi, bytes) != cudaSuccess || cudaMalloc(&pl->d_lo, bytes) != cudaSuccess ||
+      cudaMalloc(&pl->d_x, bytes) != cudaSuccess ||
       cudaMalloc(&d_rowmap, rowmap.size() * sizeof(int)) != cudaSuccess) {
     set_error("cudaMalloc of %zu bytes for the split projections failed", bytes);
     (void)cudaGetLastError();
@@ -664,7 +790,8 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   }
   cudaMemcpy(d_rowmap, rowmap.data(), rowmap.size() * sizeof(int), cudaMemcpyHostToDevice);
   split_projections_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_hi, pl->d_lo, rows, s.dim, s.dim_pad);
-  count_launch();
+  split_cross_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_x, rows, s.dim, s.dim_pad);
+  count_launch(2);
   const cudaError_t serr = cudaDeviceSynchronize();
   cudaFree(d_rowmap);
   if (serr != cudaSuccess) {
@@ -680,10 +807,17 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   rc = make_map(&pl->tm_rlo, pl->d_lo, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, brows,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc != LSHX_OK) return fail(rc);
+  rc = make_map(&pl->tm_rx, pl->d_x, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, brows,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc != LSHX_OK) return fail(rc);
+  pl->flags = TC_FLAG_B_WARP;
+  if (const char* e = getenv("LSHX_TC_FLAGS")) pl->flags = atoi(e);
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaFuncSetAttribute(hash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if (cudaFuncSetAttribute(hash_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(SMEM_BYTES + 1024)) != cudaSuccess ||
+      cudaFuncSetAttribute(hash_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(SMEM_BYTES + 1024)) != cudaSuccess) {
     set_error("cannot reserve %u bytes of shared memory for the tcgen05 kernel", SMEM_BYTES + 1024);
     (void)cudaGetLastError();
@@ -697,10 +831,11 @@ void tc_plan_destroy(TcPlan* p) {
   if (!p) return;
   if (p->d_hi) cudaFree(p->d_hi);
   if (p->d_lo) cudaFree(p->d_lo);
+  if (p->d_x) cudaFree(p->d_x);
   delete p;
 }
 
-int launch_hash_tc(const HashShape& s, TcPlan* plan, const float* d_X, int64_t n, uint8_t* d_out,
+int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X, int64_t n, uint8_t* d_out,
                    uint8_t* d_zero_flag, cudaStream_t stream) {
   if (n <= 0) return LSHX_OK;
   LSHX_REQUIRE((reinterpret_cast<uintptr_t>(d_X) & 15) == 0, "tcgen05 kernel needs 16-byte aligned vectors");
@@ -732,9 +867,13 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, const float* d_X, int64_t n
   p.out_vec_ok = (s.sig_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0) ? 1 : 0;
   p.out = d_out;
   p.zero_flag = d_zero_flag;
+  p.flags = plan->flags;
   const int64_t work = p.mtiles * p.npass;
   const unsigned grid = (unsigned)(work < plan->num_sms ? work : plan->num_sms);
-  hash_tc_kernel<<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rlo, p);
+  if (split == 0)
+    hash_tc_kernel<0><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rlo, p);
+  else
+    hash_tc_kernel<1><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rx, p);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;

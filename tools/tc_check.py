@@ -10,6 +10,7 @@ how many bits differ from the oracle and where, and survives a hung kernel.
 
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 import time
@@ -50,7 +51,7 @@ def run_case(i: int) -> int:
     X = np.random.default_rng(i).standard_normal((n, dim)).astype(np.float32)
     h = LSHHasher(nb, r, dim, seed=42)
     h._ensure_handle()
-    h.set_kernel("tcgen05")
+    h.set_kernel(os.environ.get("TC_KERNEL", "tcgen05"))
     t0 = time.perf_counter()
     got, flag = h.hash_batch_packed(X, return_zero_flag=True)
     dt = time.perf_counter() - t0
