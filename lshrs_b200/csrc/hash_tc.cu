@@ -63,6 +63,9 @@ constexpr uint32_t A_STAGE_COLS = 64;
 constexpr int TC_FLAG_B_WARP = 1;    // projections are TMA-loaded by warp 3 instead of warp 0
 constexpr int TC_FLAG_DEFER_ST = 2;  // converters overlap tcgen05.wait::st with the next chunk's loads
 constexpr int TC_FLAG_SWAP_A = 4;    // (bring-up) odd k in the low half of the BF16 A words
+constexpr int TC_FLAG_CG2 = 8;       // 2-CTA kernel (cta_group::2) where the shape allows it
+constexpr int TC_FLAG_SWAP_BHALF = 16;  // (bring-up) cluster rank 1 stages the FIRST half of the columns
+constexpr int TC_FLAG_CG2_ALWAYS = 32;  // (bring-up) 2-CTA kernel even for batches smaller than one wave
 
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
@@ -72,6 +75,10 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
 // the same for A=B=BF16 (K = 16 per instruction): the cross terms of the TF32+BF16 split
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+// and for A=B=FP16 (format 0): the scaled FP16x3 split
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t n) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
 // ---- PTX wrappers -----------------------------------------------------------------------------
@@ -233,6 +240,352 @@ struct TcParams {
   uint8_t* out;
   uint8_t* zero_flag;
 };
+
+// One half (16 floats) of thread t's 128 B row of an X chunk in shared memory -> A-operand words.
+// hi: TF32(x).  lo: 3xTF32 -> TF32 of the residual; TF32+BF16 -> words [0,8) = BF16 pairs of the residual,
+// words [8,16) = BF16 pairs of hi (the layout of the cross plane, split_cross_kernel).  `viol` collects
+// the zero-vector test of LSHRS._prepare_vector (some |x| > 1e-8, or NaN).
+template <int kSplit>
+__device__ __forceinline__ void convert_half(uint32_t row, int t, int h, bool swp, uint32_t (&hi)[16],
+                                             uint32_t (&lo)[16], bool& viol) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int chunk = h * 4 + c;                       // logical 16 B chunk of the row
+    const uint32_t addr = row + (uint32_t)((chunk ^ (t & 7)) << 4);  // SWIZZLE_128B
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    float lf[4], hc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float x = f[e];
+      viol |= !(fabsf(x) <= 1e-8f);
+      const uint32_t hu = tf32_rna(__float_as_uint(x));
+      const float hf = __uint_as_float(hu);
+      // residual is exact in fp32; an infinite hi has no residual (inf - inf would be NaN)
+      lf[e] = (fabsf(hf) == INFINITY) ? 0.f : (x - hf);
+      hi[c * 4 + e] = hu;
+      if (kSplit == 0) lo[c * 4 + e] = tf32_rna(__float_as_uint(lf[e]));
+      // a hi that would round to a BF16 infinity (or is one) takes no part in the cross term:
+      // its sign is already decided by hi.hi
+      else hc[e] = ((hu & 0x7FFFFFFFu) >= 0x7F7F8000u) ? 0.f : hf;
+    }
+    if (kSplit != 0) {
+      lo[c * 2 + 0] = swp ? pack_bf16(lf[1], lf[0]) : pack_bf16(lf[0], lf[1]);
+      lo[c * 2 + 1] = swp ? pack_bf16(lf[3], lf[2]) : pack_bf16(lf[2], lf[3]);
+      lo[8 + c * 2 + 0] = swp ? pack_bf16(hc[1], hc[0]) : pack_bf16(hc[0], hc[1]);
+      lo[8 + c * 2 + 1] = swp ? pack_bf16(hc[3], hc[2]) : pack_bf16(hc[2], hc[3]);
+    }
+  }
+}
+
+// two fp32 -> one word of two FP16 (round to nearest even), `even` in the low half
+__device__ __forceinline__ uint32_t pack_f16(float even, float odd) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(odd), "f"(even));
+  return d;
+}
+__device__ __forceinline__ void unpack_f16(uint32_t w, float& even, float& odd) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+      : "=f"(even), "=f"(odd)
+      : "r"(w));
+}
+
+// ---- scaled FP16x3 split (kSplit == 2) ------------------------------------------------------------
+// Only the SIGN of x.r is kept, and it is invariant under a positive scale per vector and per projection
+// row.  With power-of-two scales (exact) that bring the operands into FP16's range,
+//     y = s_x * x = y_hi + y_lo,  q = s_r * r = q_hi + q_lo     (hi = FP16(.), lo = FP16 of the residual)
+//     y.q ~= y_lo.q_hi + y_hi.q_lo + y_hi.q_hi                  (three kind::f16 MMAs, K = 16 each)
+// keeps 11 + 11 significand bits per operand like 3xTF32 (measured max error 1.5e-8 |x||r|) at HALF the
+// tensor time per term: 1.5 tensor-time units per product, and half the projection bytes.
+//   s_r: per projection row, from its largest |r| (static, split_f16_kernel).
+//   s_x: per vector, fixed by the first K chunk that holds a non-zero element so that its largest |x|
+//        lands in [2^5, 2^6): later elements may be up to 2^10 times larger before FP16 overflows, and
+//        elements more than 2^19 below it lose precision that is negligible against |x|.  A vector that
+//        does overflow (or whose scale is not representable: |x| < 2^-121) is flagged in TcParams::redo
+//        and recomputed by the FP32 FFMA kernel right after this one (launch_hash_tc) -- never silently
+//        wrong.
+
+// largest |x| of thread t's 32 floats of an X chunk
+__device__ __forceinline__ float chunk_absmax(uint32_t row, int t) {
+  float m = 0.f;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint32_t addr = row + (uint32_t)((c ^ (t & 7)) << 4);
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));   // fmaxf drops NaN
+  }
+  return m;
+}
+// power of two s with m * s in [2^5, 2^6); 0 when it is not representable (m tiny, inf)
+__device__ __forceinline__ float row_scale_for(float m) {
+  const int e = (int)((__float_as_uint(m) >> 23) & 0xFFu);
+  const int se = 254 + 5 - e;                       // biased exponent of the scale
+  return (e >= 5 && e < 255 && se >= 1) ? __uint_as_float((uint32_t)se << 23) : 0.f;
+}
+// One half (16 floats) of a row -> 16 A-operand words: [0,8) = FP16 pairs of y_hi, [8,16) = pairs of y_lo.
+__device__ __forceinline__ void convert_half_f16(uint32_t row, int t, int h, float sc, uint32_t (&w)[16],
+                                                 bool& viol, bool& redo) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int chunk = h * 4 + c;
+    const uint32_t addr = row + (uint32_t)((chunk ^ (t & 7)) << 4);  // SWIZZLE_128B
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    float y[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      viol |= !(fabsf(f[e]) <= 1e-8f);
+      y[e] = f[e] * sc;
+      redo |= fabsf(y[e]) > 65504.f;               // would round to an FP16 infinity (or is one)
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const uint32_t hw = pack_f16(y[2 * q], y[2 * q + 1]);
+      float h0, h1;
+      unpack_f16(hw, h0, h1);
+      // residuals are exact in fp32; rows with an infinite hi are recomputed anyway
+      w[c * 2 + q] = hw;
+      w[8 + c * 2 + q] = pack_f16(y[2 * q] - h0, y[2 * q + 1] - h1);
+    }
+  }
+}
+
+// Accumulator row of this thread (TMEM lane) -> one sign bit per column: words[c >> 5] bit (c & 31) = D[c] > 0.
+__device__ __forceinline__ void read_sign_words(uint32_t tmem_row, uint32_t N, uint32_t (&words)[8]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {   // 64 columns per step: two 32-column loads in flight per wait
+    uint32_t w0 = 0, w1 = 0;
+    if ((uint32_t)(g * 64) < N) {
+      uint32_t v0[32], v1[32];
+      const uint32_t src = tmem_row + g * 64;
+      tc_ld32(src, v0);
+      tc_ld32(src + 32, v1);
+      tc_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        w0 |= (__uint_as_float(v0[i]) > 0.f ? 1u : 0u) << i;
+        w1 |= (__uint_as_float(v1[i]) > 0.f ? 1u : 0u) << i;
+      }
+      // columns at or past N were never written by this pass's MMAs
+      const uint32_t left = N - (uint32_t)(g * 64);
+      if (left < 32u) w0 &= (1u << left) - 1u;
+      if (left <= 32u) w1 = 0u;
+      else if (left < 64u) w1 &= (1u << (left - 32u)) - 1u;
+    }
+    words[2 * g] = w0;
+    words[2 * g + 1] = w1;
+  }
+}
+
+// Sign words of row m (thread t of the tile), pass `pass` -> signature bytes in the reference's layout.
+__device__ __forceinline__ void store_signature(const TcParams& p, uint32_t N, int pass, int64_t m, int t,
+                                                const uint32_t (&words)[8], uint32_t* repack_sm) {
+  if (p.repack && p.r == 4) {
+    // 4-row bands (BASELINE config 5): every nibble of the compact bits becomes one byte; pure
+    // register bit-spreading, 16 bits -> 4 bytes per step
+    if (m < p.n) {
+      const int band0 = pass * p.bpp;
+      const int nb = (p.num_bands - band0 < p.bpp) ? (p.num_bands - band0) : p.bpp;  // = output bytes
+      uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + band0;
+      const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {          // 64 compact bits -> 16 output bytes per step
+        if (g * 16 < nb) {
+          uint32_t o[4];
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            uint32_t x = (words[2 * g + (h >> 1)] >> (16 * (h & 1))) & 0xFFFFu;
+            x = (x | (x << 8)) & 0x00FF00FFu;
+            x = (x | (x << 4)) & 0x0F0F0F0Fu;
+            o[h] = x;
+          }
+          if (vec_ok && g * 16 + 16 <= nb) {
+            *reinterpret_cast<uint4*>(dst + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              if (g * 16 + e < nb) dst[g * 16 + e] = (uint8_t)(o[e >> 2] >> (8 * (e & 3)));
+          }
+        }
+      }
+    }
+  } else if (p.repack) {
+    // compact column bits -> every band padded to whole bytes (np.packbits zero high bits)
+    uint32_t* mine = repack_sm + t * 9;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mine[i] = words[i];
+    mine[8] = 0u;
+    if (m < p.n) {
+      const int band0 = pass * p.bpp;
+      const int nb = (p.num_bands - band0 < p.bpp) ? (p.num_bands - band0) : p.bpp;
+      const int out_bytes = nb * p.bpb;                       // bytes this pass contributes to the row
+      uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + (int64_t)band0 * p.bpb;
+      const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+      int j = 0, q = 0;                                       // band within the pass, byte within the band
+      for (int ob = 0; ob < out_bytes; ob += 16) {            // 16 output bytes per step, in registers
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          if (ob + e < out_bytes) {
+            const int src = j * p.r + 8 * q;
+            const int nbits = (p.r - 8 * q < 8) ? (p.r - 8 * q) : 8;
+            const uint32_t v = __funnelshift_r(mine[src >> 5], mine[(src >> 5) + 1], src & 31) &
+                               ((1u << nbits) - 1u);
+            o[e >> 2] |= v << (8 * (e & 3));
+            if (++q == p.bpb) {
+              q = 0;
+              ++j;
+            }
+          }
+        }
+        if (vec_ok && ob + 16 <= out_bytes) {
+          *reinterpret_cast<uint4*>(dst + ob) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (ob + e < out_bytes) dst[ob + e] = (uint8_t)(o[e >> 2] >> (8 * (e & 3)));
+        }
+      }
+    }
+  } else if (m < p.n) {
+    const int byte0 = pass * (int)(N / 8);  // 16 signature bytes per 128 columns
+    uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + byte0;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if ((uint32_t)(j * TN) < N) {
+        const int b = byte0 + j * 16;
+        if (p.out_vec_ok && b + 16 <= p.sig_bytes) {
+          *reinterpret_cast<uint4*>(dst + j * 16) =
+              make_uint4(words[j * 4], words[j * 4 + 1], words[j * 4 + 2], words[j * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (b + q < p.sig_bytes) dst[j * 16 + q] = (uint8_t)(words[j * 4 + (q >> 2)] >> (8 * (q & 3)));
+        }
+      }
+    }
+  }
+}
+
+constexpr int BS2 = 6;            // projection stages of (N/2) x 64 B x 2 planes (16 KB at N = 256)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// address of the same shared-memory location in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+// Arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope), as
+// CUTLASS's ClusterBarrier::arrive(cta_id) does: what the waiter must see are TMEM writes, ordered by
+// tcgen05.wait::st + tcgen05.fence::before_thread_sync, not generic-proxy stores.  (A
+// .release.cluster arrive costs MEMBAR.ALL + ERRBAR per call -- half of the converters' time when it
+// was tried -- and .acquire.cluster waits invalidate L1 on every pass.)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are counted on a barrier of the
+// leader CTA (`bar_cluster` is a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* map, uint32_t bar_cluster, uint32_t dst,
+                                                int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs once the MMAs issued so far are done
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma2_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// MMAs of one K half (16 k) of a chunk.  kCG = cta_group (1: M = 128, 2: M = 256 over the CTA pair).
+// a_stage: first TMEM column of the A stage; bs: shared-memory address of the projection stage;
+// plane_bytes: size of one plane of it.  +32 B per K step inside a 64 B swizzle row = start-address
+// field += 2.  Small terms first.
+template <int kSplit, int kCG>
+__device__ __forceinline__ void issue_khalf(uint32_t d_base, uint32_t a_stage, int hk, uint32_t bs,
+                                            uint32_t plane_bytes, uint32_t N, bool first) {
+  constexpr uint32_t MSEL = (uint32_t)((kCG * TM) >> 4) << 24;
+  const uint32_t mmask = ~(31u << 24);
+  auto mma_tf32 = [&](uint32_t a, uint64_t b, uint32_t acc) {
+    const uint32_t id = (make_idesc(N) & mmask) | MSEL;
+    if (kCG == 1) tc_mma_ts(d_base, a, b, id, acc); else tc_mma2_ts(d_base, a, b, id, acc);
+  };
+  auto mma_16 = [&](uint32_t a, uint64_t b, uint32_t id0, uint32_t acc) {
+    const uint32_t id = (id0 & mmask) | MSEL;
+    if (kCG == 1) tc_mma_ts_f16(d_base, a, b, id, acc); else tc_mma2_ts_f16(d_base, a, b, id, acc);
+  };
+  const uint32_t acc0 = first ? 0u : 1u;
+  if (kSplit == 2) {
+    // A words of this half: [0,8) = y_hi, [8,16) = y_lo; projection row: [0,32 B) = q_hi, [32,64 B) = q_lo
+    const uint64_t desc = make_b_desc(bs);
+    const uint32_t a_hi = a_stage + (uint32_t)(hk * TKB), a_lo = a_hi + 8;
+    mma_16(a_lo, desc, make_idesc_f16(N), acc0);        // y_lo . q_hi
+    mma_16(a_hi, desc + 2, make_idesc_f16(N), 1u);      // y_hi . q_lo
+    mma_16(a_hi, desc, make_idesc_f16(N), 1u);          // y_hi . q_hi
+  } else {
+    const uint64_t desc_hi = make_b_desc(bs);
+    const uint64_t desc_lo = make_b_desc(bs + plane_bytes);
+    const uint32_t a_hi = a_stage, a_lo = a_stage + 32;
+#pragma unroll
+    for (int s = 0; s < TKB / 8; ++s) {
+      const uint32_t ka = (uint32_t)(hk * TKB + 8 * s);
+      const uint32_t acc = (first && s == 0) ? 0u : 1u;
+      if (kSplit == 0) {
+        mma_tf32(a_lo + ka, desc_hi + (uint64_t)(2 * s), acc);   // x_lo . r_hi
+        mma_tf32(a_hi + ka, desc_lo + (uint64_t)(2 * s), 1u);    // x_hi . r_lo
+      } else {
+        // s = 0: bf(x_lo) . bf(r_hi), s = 1: bf(x_hi) . bf(r_lo), each over the 16 k of this half
+        mma_16(a_lo + ka, desc_lo + (uint64_t)(2 * s), make_idesc_bf16(N), acc);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < TKB / 8; ++s)                            // x_hi . r_hi
+      mma_tf32(a_hi + (uint32_t)(hk * TKB + 8 * s), desc_hi + (uint64_t)(2 * s), 1u);
+  }
+}
 
 // kSplit == 0: 3xTF32 (tm_rlo = TF32 residual plane).
 // kSplit == 1: TF32 hi.hi + BF16 cross terms (tm_rlo = the cross plane, see split_cross_kernel):
@@ -434,40 +787,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {   // two halves of 16 floats keep the register count down
-          // hi: TF32(x).  lo: 3xTF32 -> TF32 of the residual; TF32+BF16 -> words [0,8) = BF16 pairs of the
-          // residual, words [8,16) = BF16 pairs of hi (the layout of the cross plane, split_cross_kernel)
           uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const int chunk = h * 4 + c;                       // logical 16 B chunk of the row
-            const uint32_t addr = row + (uint32_t)((chunk ^ (t & 7)) << 4);  // SWIZZLE_128B
-            float4 v;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "r"(addr));
-            const float f[4] = {v.x, v.y, v.z, v.w};
-            float lf[4], hc[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float x = f[e];
-              viol |= !(fabsf(x) <= 1e-8f);
-              const uint32_t hu = tf32_rna(__float_as_uint(x));
-              const float hf = __uint_as_float(hu);
-              // residual is exact in fp32; an infinite hi has no residual (inf - inf would be NaN)
-              lf[e] = (fabsf(hf) == INFINITY) ? 0.f : (x - hf);
-              hi[c * 4 + e] = hu;
-              if (kSplit == 0) lo[c * 4 + e] = tf32_rna(__float_as_uint(lf[e]));
-              // a hi that would round to a BF16 infinity (or is one) takes no part in the cross term:
-              // its sign is already decided by hi.hi
-              else hc[e] = ((hu & 0x7FFFFFFFu) >= 0x7F7F8000u) ? 0.f : hf;
-            }
-            if (kSplit != 0) {
-              lo[c * 2 + 0] = swp ? pack_bf16(lf[1], lf[0]) : pack_bf16(lf[0], lf[1]);
-              lo[c * 2 + 1] = swp ? pack_bf16(lf[3], lf[2]) : pack_bf16(lf[2], lf[3]);
-              lo[8 + c * 2 + 0] = swp ? pack_bf16(hc[1], hc[0]) : pack_bf16(hc[0], hc[1]);
-              lo[8 + c * 2 + 1] = swp ? pack_bf16(hc[3], hc[2]) : pack_bf16(hc[2], hc[3]);
-            }
-          }
+          convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
           if (h == 0 && pend >= 0) {
             // the previous chunk's stores have had this half's loads and arithmetic to complete
             tc_wait_st();
@@ -511,120 +832,13 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       mbar_wait(d_full(dr.idx), dr.phase);
       tc_fence_after();
       uint32_t words[8];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {   // 64 columns per step: two 32-column loads in flight per wait
-        uint32_t w0 = 0, w1 = 0;
-        if ((uint32_t)(g * 64) < N) {
-          uint32_t v0[32], v1[32];
-          const uint32_t src = tmem_base + lane_field + dr.idx * TN + g * 64;
-          tc_ld32(src, v0);
-          tc_ld32(src + 32, v1);
-          tc_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            w0 |= (__uint_as_float(v0[i]) > 0.f ? 1u : 0u) << i;
-            w1 |= (__uint_as_float(v1[i]) > 0.f ? 1u : 0u) << i;
-          }
-          // columns at or past N were never written by this pass's MMAs
-          const uint32_t left = N - (uint32_t)(g * 64);
-          if (left < 32u) w0 &= (1u << left) - 1u;
-          if (left <= 32u) w1 = 0u;
-          else if (left < 64u) w1 &= (1u << (left - 32u)) - 1u;
-        }
-        words[2 * g] = w0;
-        words[2 * g + 1] = w1;
-      }
+      read_sign_words(tmem_base + lane_field + dr.idx * TN, N, words);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d_empty(dr.idx));
       dr.advance(dstages);
 
-      const int64_t m = mt * TM + t;
-      if (p.repack && p.r == 4) {
-        // 4-row bands (BASELINE config 5): every nibble of the compact bits becomes one byte; pure
-        // register bit-spreading, 16 bits -> 4 bytes per step
-        if (m < p.n) {
-          const int band0 = pass * p.bpp;
-          const int nb = (p.num_bands - band0 < p.bpp) ? (p.num_bands - band0) : p.bpp;  // = output bytes
-          uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + band0;
-          const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {          // 64 compact bits -> 16 output bytes per step
-            if (g * 16 < nb) {
-              uint32_t o[4];
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                uint32_t x = (words[2 * g + (h >> 1)] >> (16 * (h & 1))) & 0xFFFFu;
-                x = (x | (x << 8)) & 0x00FF00FFu;
-                x = (x | (x << 4)) & 0x0F0F0F0Fu;
-                o[h] = x;
-              }
-              if (vec_ok && g * 16 + 16 <= nb) {
-                *reinterpret_cast<uint4*>(dst + g * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 16; ++e)
-                  if (g * 16 + e < nb) dst[g * 16 + e] = (uint8_t)(o[e >> 2] >> (8 * (e & 3)));
-              }
-            }
-          }
-        }
-      } else if (p.repack) {
-        // compact column bits -> every band padded to whole bytes (np.packbits zero high bits)
-        uint32_t* mine = repack_sm + t * 9;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) mine[i] = words[i];
-        mine[8] = 0u;
-        if (m < p.n) {
-          const int band0 = pass * p.bpp;
-          const int nb = (p.num_bands - band0 < p.bpp) ? (p.num_bands - band0) : p.bpp;
-          const int out_bytes = nb * p.bpb;                       // bytes this pass contributes to the row
-          uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + (int64_t)band0 * p.bpb;
-          const bool vec_ok = (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
-          int j = 0, q = 0;                                       // band within the pass, byte within the band
-          for (int ob = 0; ob < out_bytes; ob += 16) {            // 16 output bytes per step, in registers
-            uint32_t o[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (ob + e < out_bytes) {
-                const int src = j * p.r + 8 * q;
-                const int nbits = (p.r - 8 * q < 8) ? (p.r - 8 * q) : 8;
-                const uint32_t v = __funnelshift_r(mine[src >> 5], mine[(src >> 5) + 1], src & 31) &
-                                   ((1u << nbits) - 1u);
-                o[e >> 2] |= v << (8 * (e & 3));
-                if (++q == p.bpb) {
-                  q = 0;
-                  ++j;
-                }
-              }
-            }
-            if (vec_ok && ob + 16 <= out_bytes) {
-              *reinterpret_cast<uint4*>(dst + ob) = make_uint4(o[0], o[1], o[2], o[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (ob + e < out_bytes) dst[ob + e] = (uint8_t)(o[e >> 2] >> (8 * (e & 3)));
-            }
-          }
-        }
-      } else if (m < p.n) {
-        const int byte0 = pass * (int)(N / 8);  // 16 signature bytes per 128 columns
-        uint8_t* dst = p.out + m * (int64_t)p.sig_bytes + byte0;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if ((uint32_t)(j * TN) < N) {
-            const int b = byte0 + j * 16;
-            if (p.out_vec_ok && b + 16 <= p.sig_bytes) {
-              *reinterpret_cast<uint4*>(dst + j * 16) =
-                  make_uint4(words[j * 4], words[j * 4 + 1], words[j * 4 + 2], words[j * 4 + 3]);
-            } else {
-#pragma unroll
-              for (int q = 0; q < 16; ++q)
-                if (b + q < p.sig_bytes) dst[j * 16 + q] = (uint8_t)(words[j * 4 + (q >> 2)] >> (8 * (q & 3)));
-            }
-          }
-        }
-      }
+      store_signature(p, N, pass, mt * TM + t, t, words, repack_sm);
     }
   }
 
@@ -633,6 +847,225 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
+                 : "memory");
+  }
+}
+
+// =================================================================================================
+// 2-CTA variant (cta_group::2): two SMs of one TPC work on a 256-row tile.  Each CTA converts its own
+// 128 rows into its own TMEM and keeps its own 128 x N accumulator rows, but stages only HALF of the
+// projection columns of a pass in its shared memory; the pair's tensor cores read both halves.  That
+// halves the projection bytes every SM pulls from L2 per tile -- the limit of the 1-CTA kernel once
+// the split needs only two tensor-time units (measured: 80 KB per K chunk per SM = 10.9 TB/s of
+// L2->SM traffic at 724 M vectors/s, against a ~12 TB/s fabric cap) -- and the shared-memory reads
+// of the MMAs.  Only the leader CTA (cluster rank 0) issues MMAs; barriers that gate them (a_full,
+// b_full, d_empty) live in the leader and are arrived on across the cluster, barriers that the MMAs
+// release (a_empty, b_empty, d_full) are signalled in both CTAs by a multicast tcgen05.commit.
+// =================================================================================================
+template <int kSplit>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_rhi,
+                const __grid_constant__ CUtensorMap tm_rlo, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[XS_MAX * 2 + BS2 * 2 + AS * 2 + 4];
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // same offset in both CTAs
+  const uint32_t x_smem = smem_base;
+  const uint32_t XS = (uint32_t)p.xs;
+  const uint32_t N = (uint32_t)p.ncols_pass;
+  const uint32_t NH = N / 2;                                // projection columns staged by this CTA
+  const uint32_t B_HALF_BYTES = NH * TKB * 4u;              // one plane of one stage: N/2 rows x 64 B
+  const uint32_t B_STAGE_BYTES = 2u * B_HALF_BYTES;
+  const uint32_t b_smem = smem_base + XS * X_STAGE_BYTES;
+  const uint32_t bar0 = smem_u32(bars);
+  auto x_full = [&](uint32_t i) { return bar0 + 8u * i; };
+  auto x_empty = [&](uint32_t i) { return bar0 + 8u * (XS_MAX + i); };
+  auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + i); };
+  auto b_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + BS2 + i); };
+  auto a_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + 2 * BS2 + i); };
+  auto a_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + 2 * BS2 + AS + i); };
+  auto d_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + 2 * BS2 + 2 * AS + i); };
+  auto d_empty = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + 2 * BS2 + 2 * AS + 2 + i); };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const uint32_t dstages = (N <= (uint32_t)TN) ? 2u : 1u;
+  const int64_t work_items = p.mtiles * p.npass;            // mtiles = 256-row tiles here
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_rhi);
+    tma_prefetch_desc(&tm_rlo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t i = 0; i < XS_MAX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 4); }
+    for (uint32_t i = 0; i < BS2; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
+    for (uint32_t i = 0; i < AS; ++i) { mbar_init(a_full(i), 8); mbar_init(a_empty(i), 1); }   // 4 warps x 2 CTAs
+    for (uint32_t i = 0; i < 2; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // both CTAs take part in the pair-wide allocation
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(&tmem_base_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barriers of both CTAs initialised, TMEM allocated, before anything crosses
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== X producer (this CTA's 128 rows of the pair's tile) ==================
+    Ring xr;
+    for (int64_t w = pair; w < work_items; w += npairs) {
+      const int64_t mt = (p.npass == 1) ? w : w / p.npass;
+      const int row0 = (int)(mt * (2 * TM) + rank * TM);
+      for (int kc = 0; kc < p.kc; ++kc) {
+        mbar_wait(x_empty(xr.idx), xr.phase ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(x_full(xr.idx), X_STAGE_BYTES);
+          tma_load_2d(&tm_x, x_full(xr.idx), x_smem + xr.idx * X_STAGE_BYTES, kc * TK, row0);
+        }
+        __syncwarp();
+        xr.advance(XS);
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== projection producer: this CTA's half of the pass's columns ===========
+    Ring br;
+    const uint32_t half = (p.flags & TC_FLAG_SWAP_BHALF) ? (rank ^ 1u) : rank;
+    for (int64_t w = pair; w < work_items; w += npairs) {
+      const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
+      const int col0 = pass * (int)N + (int)(half * NH);
+      for (int kc = 0; kc < p.kc; ++kc) {
+        for (int hk = 0; hk < TK / TKB; ++hk) {
+          mbar_wait(b_empty(br.idx), br.phase ^ 1);
+          if (elect_one()) {
+            // the leader's barrier counts the bytes of both CTAs' loads
+            if (rank == 0) mbar_arrive_expect_tx(b_full(br.idx), 2u * B_STAGE_BYTES);
+            const uint32_t full0 = mapa_rank(b_full(br.idx), 0);
+            const uint32_t dst = b_smem + br.idx * B_STAGE_BYTES;
+            tma_load_2d_cg2(&tm_rhi, full0, dst, kc * TK + hk * TKB, col0);
+            tma_load_2d_cg2(&tm_rlo, full0, dst + B_HALF_BYTES, kc * TK + hk * TKB, col0);
+          }
+          __syncwarp();
+          br.advance(BS2);
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only): M = 256 over the pair ===================
+    Ring ar, br, dr;
+    const uint32_t idesc = (make_idesc(N) & ~(31u << 24)) | ((uint32_t)((2 * TM) >> 4) << 24);
+    const uint32_t idesc_x = (make_idesc_bf16(N) & ~(31u << 24)) | ((uint32_t)((2 * TM) >> 4) << 24);
+    for (int64_t w = pair; w < work_items; w += npairs) {
+      mbar_wait(d_empty(dr.idx), dr.phase ^ 1);   // both epilogues have drained this stage
+      tc_fence_after();
+      const uint32_t d_base = tmem_base + dr.idx * TN;
+      for (int kc = 0; kc < p.kc; ++kc) {
+        mbar_wait(a_full(ar.idx), ar.phase);      // both CTAs' converters
+        const uint32_t a_hi = tmem_base + A_COL0 + ar.idx * A_STAGE_COLS;
+        const uint32_t a_lo = a_hi + 32;
+        for (int hk = 0; hk < TK / TKB; ++hk) {
+          mbar_wait(b_full(br.idx), br.phase);
+          tc_fence_after();
+          const uint32_t bs = b_smem + br.idx * B_STAGE_BYTES;
+          const uint64_t desc_hi = make_b_desc(bs);
+          const uint64_t desc_lo = make_b_desc(bs + B_HALF_BYTES);
+          if (elect_one()) {
+#pragma unroll
+            for (int s = 0; s < TKB / 8; ++s) {
+              const uint32_t ka = (uint32_t)(hk * TKB + 8 * s);
+              const uint32_t acc = (kc > 0 || hk > 0 || s > 0) ? 1u : 0u;
+              if (kSplit == 0) {
+                tc_mma2_ts(d_base, a_lo + ka, desc_hi + (uint64_t)(2 * s), idesc, acc);
+                tc_mma2_ts(d_base, a_hi + ka, desc_lo + (uint64_t)(2 * s), idesc, 1u);
+              } else {
+                tc_mma2_ts_f16(d_base, a_lo + ka, desc_lo + (uint64_t)(2 * s), idesc_x, acc);
+              }
+            }
+#pragma unroll
+            for (int s = 0; s < TKB / 8; ++s)
+              tc_mma2_ts(d_base, a_hi + (uint32_t)(hk * TKB + 8 * s), desc_hi + (uint64_t)(2 * s), idesc, 1u);
+            tc_commit_pair(b_empty(br.idx));
+            if (hk == TK / TKB - 1) tc_commit_pair(a_empty(ar.idx));
+            if (hk == TK / TKB - 1 && kc == p.kc - 1) tc_commit_pair(d_full(dr.idx));
+          }
+          __syncwarp();
+          br.advance(BS2);
+        }
+        ar.advance(AS);
+      }
+      dr.advance(dstages);
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converters (as in the 1-CTA kernel; a_full lives in the leader) =======
+    const int t = (warp - 4) * 32 + lane;
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    const bool swp = (p.flags & TC_FLAG_SWAP_A) != 0;
+    Ring xr, ar;
+    for (int64_t w = pair; w < work_items; w += npairs) {
+      const int64_t mt = (p.npass == 1) ? w : w / p.npass;
+      const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
+      bool viol = false;
+      for (int kc = 0; kc < p.kc; ++kc) {
+        mbar_wait(x_full(xr.idx), xr.phase);
+        const uint32_t row = x_smem + xr.idx * X_STAGE_BYTES + (uint32_t)t * 128u;
+        mbar_wait(a_empty(ar.idx), ar.phase ^ 1);
+        tc_fence_after();
+        const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t hi[16], lo[16];
+          convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
+          tc_st16(a_dst + h * 16, hi);
+          tc_st16(a_dst + 32 + h * 16, lo);
+        }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(mapa_rank(a_full(ar.idx), 0));
+          mbar_arrive(x_empty(xr.idx));
+        }
+        xr.advance(XS);
+        ar.advance(AS);
+      }
+      if (p.zero_flag != nullptr && pass == 0) {
+        const int64_t m = mt * (2 * TM) + rank * TM + t;
+        if (m < p.n) p.zero_flag[m] = viol ? 0 : 1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: this CTA's 128 accumulator rows =============================
+    const int t = (warp - 8) * 32 + lane;
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    Ring dr;
+    for (int64_t w = pair; w < work_items; w += npairs) {
+      const int64_t mt = (p.npass == 1) ? w : w / p.npass;
+      const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
+      mbar_wait(d_full(dr.idx), dr.phase);
+      tc_fence_after();
+      uint32_t words[8];
+      read_sign_words(tmem_base + lane_field + dr.idx * TN, N, words);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(d_empty(dr.idx), 0));
+      dr.advance(dstages);
+      store_signature(p, N, pass, mt * (2 * TM) + rank * TM + t, t, words, nullptr);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // nothing may still target the peer's barriers / shared memory / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
 }
@@ -735,7 +1168,10 @@ struct TcPlan {
   float* d_lo = nullptr;     // TF32 residual plane (3xTF32 arm)
   uint32_t* d_x = nullptr;   // BF16 cross plane (TF32+BF16 arm)
   CUtensorMap tm_rhi, tm_rlo, tm_rx;
+  CUtensorMap tm2_rhi, tm2_rlo, tm2_rx;   // the same planes with boxes of ncols_pass / 2 rows (2-CTA kernel)
+  bool cg2_ok = false;
   int flags = 0;
+  int auto_split = 1;   // what split < 0 resolves to for this shape
   int num_sms = 0;
   // column layout of the split projections (see tc_plan_create)
   int ncols_pass = 0, npass = 0, repack = 0, bpp = 0;
@@ -810,14 +1246,33 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   rc = make_map(&pl->tm_rx, pl->d_x, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, brows,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc != LSHX_OK) return fail(rc);
-  pl->flags = TC_FLAG_B_WARP;
+  pl->cg2_ok = !pl->repack && pl->ncols_pass % 32 == 0;
+  if (pl->cg2_ok) {
+    const uint32_t hrows = brows / 2;
+    if ((rc = make_map(&pl->tm2_rhi, pl->d_hi, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, hrows,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != LSHX_OK ||
+        (rc = make_map(&pl->tm2_rlo, pl->d_lo, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, hrows,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != LSHX_OK ||
+        (rc = make_map(&pl->tm2_rx, pl->d_x, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, hrows,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != LSHX_OK)
+      return fail(rc);
+  }
+  pl->flags = TC_FLAG_B_WARP | TC_FLAG_CG2;
   if (const char* e = getenv("LSHX_TC_FLAGS")) pl->flags = atoi(e);
+  // Narrow passes (N < 128: 32-clock MMAs, HBM-bound shapes such as 128 -> 64 bits) are not limited by
+  // tensor time, and alternating kind::f16 / kind::tf32 MMAs that short measured slower (6.7 vs 8.0 G
+  // vectors/s at 128/64): they keep the all-TF32 split.
+  pl->auto_split = (pl->ncols_pass >= 128) ? 1 : 0;
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (cudaFuncSetAttribute(hash_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(SMEM_BYTES + 1024)) != cudaSuccess ||
       cudaFuncSetAttribute(hash_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(SMEM_BYTES + 1024)) != cudaSuccess ||
+      cudaFuncSetAttribute(hash_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(SMEM_BYTES + 1024)) != cudaSuccess ||
+      cudaFuncSetAttribute(hash_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(SMEM_BYTES + 1024)) != cudaSuccess) {
     set_error("cannot reserve %u bytes of shared memory for the tcgen05 kernel", SMEM_BYTES + 1024);
     (void)cudaGetLastError();
@@ -838,6 +1293,7 @@ void tc_plan_destroy(TcPlan* p) {
 int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X, int64_t n, uint8_t* d_out,
                    uint8_t* d_zero_flag, cudaStream_t stream) {
   if (n <= 0) return LSHX_OK;
+  if (split < 0) split = plan->auto_split;
   LSHX_REQUIRE((reinterpret_cast<uintptr_t>(d_X) & 15) == 0, "tcgen05 kernel needs 16-byte aligned vectors");
   LSHX_REQUIRE(n < (1ll << 31), "hash batch of %lld rows exceeds one launch", (long long)n);
   CUtensorMap tm_x;
@@ -868,6 +1324,24 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X
   p.out = d_out;
   p.zero_flag = d_zero_flag;
   p.flags = plan->flags;
+  // 2-CTA kernel: streamed projections, byte-aligned bands, enough 256-row tiles to fill every SM pair
+  const int npairs = plan->num_sms / 2;
+  if ((p.flags & TC_FLAG_CG2) && plan->cg2_ok && !p.b_resident && npairs > 0 &&
+      (((n + 2 * TM - 1) / (2 * TM)) * p.npass >= npairs || (p.flags & TC_FLAG_CG2_ALWAYS))) {
+    p.mtiles = (n + 2 * TM - 1) / (2 * TM);
+    const uint32_t b_bytes = BS2 * (uint32_t)plan->ncols_pass * TKB * 4u;   // per CTA: half the columns, two planes
+    const uint32_t fit = (SMEM_BYTES - b_bytes) / X_STAGE_BYTES;
+    p.xs = (int)(fit < (uint32_t)XS_MAX ? fit : (uint32_t)XS_MAX);
+    const int64_t work2 = p.mtiles * p.npass;
+    const unsigned grid2 = 2u * (unsigned)(work2 < npairs ? work2 : npairs);
+    if (split == 0)
+      hash_tc2_kernel<0><<<grid2, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm2_rhi, plan->tm2_rlo, p);
+    else
+      hash_tc2_kernel<1><<<grid2, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm2_rhi, plan->tm2_rx, p);
+    count_launch();
+    LSHX_CUDA(cudaGetLastError());
+    return LSHX_OK;
+  }
   const int64_t work = p.mtiles * p.npass;
   const unsigned grid = (unsigned)(work < plan->num_sms ? work : plan->num_sms);
   if (split == 0)

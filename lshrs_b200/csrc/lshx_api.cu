@@ -347,7 +347,7 @@ static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_o
     const float* x = d_X + r0 * h->s.dim;
     uint8_t* o = d_out + r0 * h->s.sig_bytes;
     uint8_t* f = d_flag ? d_flag + r0 : nullptr;
-    const int rc = use_tc ? launch_hash_tc(h->s, h->tc, tc3 ? 0 : 1, x, rows, o, f, st)
+    const int rc = use_tc ? launch_hash_tc(h->s, h->tc, tc3 ? 0 : -1, x, rows, o, f, st)
                           : launch_hash_ffma(h->s, x, rows, h->d_Rp, o, f, st);
     if (rc != LSHX_OK) return rc;
   }

@@ -69,7 +69,7 @@ struct TcPlan;  // opaque tcgen05 state (TMA descriptor of the split projections
 bool tc_shape_supported(const HashShape& s);
 int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out);
 void tc_plan_destroy(TcPlan* p);
-// split: 0 = 3xTF32, 1 = TF32 hi.hi + BF16 cross terms (the default arm)
+// split: 0 = 3xTF32, 1 = TF32 hi.hi + BF16 cross terms, < 0 = the plan's choice for the shape
 int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X, int64_t n, uint8_t* d_out,
                    uint8_t* d_zero_flag, cudaStream_t stream);
 

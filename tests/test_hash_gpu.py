@@ -17,7 +17,7 @@ from oracle import lshrs_oracle as oracle
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = ("ffma", "tcgen05")
+KERNELS = ("ffma", "tcgen05", "tcgen05_3xtf32")
 REL_MARGIN = 1e-5  # north_star exempt margin
 
 
@@ -29,7 +29,7 @@ def _hasher(nb, r, dim, seed=42, kernel="ffma"):
         h._ensure_handle()
         h.set_kernel(kernel)
     except LshxError as exc:
-        if kernel == "tcgen05" and "does not support" in str(exc):
+        if kernel.startswith("tcgen05") and "does not support" in str(exc):
             pytest.skip(f"tcgen05 kernel does not take this shape: {exc}")
         raise
     return h
@@ -112,6 +112,31 @@ def test_ragged_batch_sizes(n, kernel):
     h = _hasher(16, 16, 768, 42, kernel)
     X = np.random.default_rng(n).standard_normal((n, 768)).astype(np.float32)
     _assert_parity(h.hash_batch_packed(X), X, h.projections, f"n={n}")
+
+
+@pytest.mark.parametrize("kernel", ("tcgen05", "tcgen05_3xtf32"))
+@pytest.mark.parametrize(
+    "nb, r, dim, n",
+    [
+        (16, 16, 768, 1), (16, 16, 768, 129), (16, 16, 768, 255), (16, 16, 768, 257), (16, 16, 768, 1000),
+        (16, 16, 768, 40_000),      # more 256-row tiles than SM pairs: several tiles per pair, ragged tail
+        (16, 32, 1536, 3_000),      # two passes per tile
+        (16, 8, 32, 700),           # one K chunk, 128 columns (two accumulator stages)
+        (48, 8, 96, 5_000),         # 384 columns: three passes of 128
+    ],
+)
+def test_two_cta_kernel(nb, r, dim, n, kernel, monkeypatch):
+    """The cta_group::2 kernel on batches smaller than the AUTO threshold (which needs one 256-row tile
+    per SM pair): LSHX_TC_FLAGS = B_WARP | CG2 | CG2_ALWAYS, read when the plan is created."""
+    monkeypatch.setenv("LSHX_TC_FLAGS", str(1 | 8 | 32))
+    h = _hasher(nb, r, dim, 42, kernel)
+    X = np.random.default_rng(n).standard_normal((n, dim)).astype(np.float32)
+    X[n // 2] = 0.0
+    got, flag = h.hash_batch_packed(X, return_zero_flag=True)
+    _assert_parity(got, X, h.projections, f"2cta {nb}x{r}x{dim} n={n}")
+    want_flag = np.zeros(n, dtype=bool)
+    want_flag[n // 2] = True
+    np.testing.assert_array_equal(flag.astype(bool), want_flag)
 
 
 @pytest.mark.parametrize("kernel", KERNELS)

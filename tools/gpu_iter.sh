@@ -4,9 +4,13 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-it}
-timeout 600 python tools/tc_check.py > gpurun_out/${TAG}_tc_check.log 2>&1
-echo "tc_check exit $?"; tail -3 gpurun_out/${TAG}_tc_check.log
-grep -E "FAIL|TIMED" gpurun_out/${TAG}_tc_check.log | head -5
+for f in ${TCFLAGS_LIST:-default}; do
+  if [ "$f" = default ]; then unset LSHX_TC_FLAGS; else export LSHX_TC_FLAGS=$f; fi
+  timeout 900 python tools/tc_check.py > gpurun_out/${TAG}_tc_check_$f.log 2>&1
+  echo "tc_check flags=$f exit $?"; tail -2 gpurun_out/${TAG}_tc_check_$f.log
+  grep -E "FAIL|TIMED" gpurun_out/${TAG}_tc_check_$f.log | head -8
+done
+unset LSHX_TC_FLAGS
 run() {  # name workload kernel flags
   LSHX_TC_FLAGS=$4 timeout 300 python bench.py --workload $2 --kernel $3 --steps 10 --warmup 3 --no-cpu --no-e2e --no-rerank \
       > gpurun_out/${TAG}_$1.json 2>> gpurun_out/${TAG}_bench.err
