@@ -448,17 +448,18 @@ def run_b200(args) -> None:
     ncols = SIG_BYTES * 8
     useful_flop = 2.0 * DIM * NUM_PERM  # what the reference computes; padding columns are not useful work
     # tensor-time units per logical product, in TF32 MMAs: 3xTF32 = 3; TF32 hi.hi + the two BF16 cross
-    # terms (one K-doubled BF16 MMA = one TF32 MMA of tensor time) = 2
-    mma_passes = {"tcgen05": 2, "tcgen05_3xtf32": 3}.get(kernel_name, 1)
+    # terms (one K-doubled BF16 MMA = one TF32 MMA of tensor time) = 2; scaled FP16x3 (three FP16 MMAs,
+    # each half a TF32 MMA) = 1.5
+    mma_passes = {"tcgen05": 1.5, "tcgen05_tf32bf16": 2, "tcgen05_3xtf32": 3}.get(kernel_name, 1)
     is_tc = kernel_name.startswith("tcgen05")
     per_kernel_ms = kern_ms / max(1, len(kernel_events))
     # ALGORITHMIC flops (2*dim*num_perm per vector) against the ceiling for them: the
     # measured dense TF32 rate (= bf16_tflops_sustained / 2) divided by the tensor-time units the split
-    # spends per logical product (SURVEY section 8d "useful ceiling": 3 for 3xTF32; 2 for the default
-    # TF32 + BF16-cross-terms split).  The FFMA arm is held to the default arm's ceiling: it is what the
-    # hardware can do for this arithmetic.
+    # spends per logical product (SURVEY section 8d "useful ceiling": 3 for 3xTF32, 2 for TF32 + BF16
+    # cross terms, 1.5 for the default scaled FP16x3).  The FFMA arm is held to the default arm's
+    # ceiling: it is what the hardware can do for this arithmetic.
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
-    split_units = 3.0 if kernel_name == "tcgen05_3xtf32" else 2.0
+    split_units = {"tcgen05_3xtf32": 3.0, "tcgen05_tf32bf16": 2.0}.get(kernel_name, 1.5)
     useful_peak = tf32_peak / split_units
     achieved_tflops = useful_flop * kern_rows / (kern_ms * 1e-3) / 1e12
     ncols_exec = (NUM_PERM + 15) // 16 * 16 if ROWS_PER_BAND % 8 else (ncols + 127) // 128 * 128
@@ -479,7 +480,10 @@ def run_b200(args) -> None:
                    "peak_source": (f"{peak_src}: bf16_tflops_sustained / 2 (dense TF32) / 3 (3xTF32 split: three MMAs "
                                    "per logical product)" if split_units == 3.0 else
                                    f"{peak_src}: bf16_tflops_sustained / 2 (dense TF32) / 2 (split x = hi + lo: one TF32 MMA "
-                                   "for hi.hi + one K-doubled BF16 MMA of the same duration for both cross terms)"),
+                                   "for hi.hi + one K-doubled BF16 MMA of the same duration for both cross terms)"
+                                   if split_units == 2.0 else
+                                   f"{peak_src}: bf16_tflops_sustained / 3 (scaled FP16x3 split x = hi + lo: three dense "
+                                   "FP16 MMAs -- hi.hi, hi.lo, lo.hi -- per logical product; FP16 runs at the BF16 rate)"),
                    "flops_counted": "algorithmic: 2*dim*num_perm per vector",
                    "executed_tflops": executed_tflops, "executed_vs_tf32_peak": executed_tflops / tf32_peak,
                    "fp32_pipe_nominal_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},
@@ -532,7 +536,7 @@ def run_b200(args) -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"tcgen05": "tf32+bf16x2", "tcgen05_3xtf32": "tf32x3"}.get(kernel_name, "f32"),
+            "scaling": "weak", "vs_baseline": None, "dtype": {"tcgen05": "f16x3", "tcgen05_tf32bf16": "tf32+bf16x2", "tcgen05_3xtf32": "tf32x3"}.get(kernel_name, "f32"),
             "data": "synthetic", "config": workload_config(args), "impl": "b200", "kernel": kernel_name,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_rows * DIM * 4,
                     "d2h_bytes_per_step": e2e_rows * SIG_BYTES, "rows_per_step_per_gpu": e2e_rows,
@@ -684,7 +688,7 @@ def main() -> None:
     ap.add_argument("--chunk", type=int, default=None, help="rows per kernel launch / D2H copy")
     ap.add_argument("--e2e-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=65_536)
-    ap.add_argument("--kernel", choices=("auto", "ffma", "tcgen05", "tcgen05_3xtf32"), default="auto")
+    ap.add_argument("--kernel", choices=("auto", "ffma", "tcgen05", "tcgen05_3xtf32", "tcgen05_tf32bf16"), default="auto")
     ap.add_argument("--corpus", type=int, default=1_000_000)
     ap.add_argument("--queries", type=int, default=8192)
     ap.add_argument("--no-rerank", action="store_true")

@@ -57,13 +57,18 @@ typedef enum lshx_status {
 typedef enum lshx_hash_kernel {
   LSHX_KERNEL_AUTO = 0,    /* tcgen05 when the shape allows it, else FFMA            */
   LSHX_KERNEL_FFMA = 1,    /* FP32 FFMA register-tiled kernel                        */
-  LSHX_KERNEL_TCGEN05 = 2, /* tcgen05, TMA-staged, TMEM accumulators; split x = hi + lo:
-                              TF32 hi.hi + BF16 cross terms (fp32-sgemm accuracy)    */
+  LSHX_KERNEL_TCGEN05 = 2, /* tcgen05, TMA-staged, TMEM accumulators, operands split
+                              hi + lo; default arithmetic: scaled FP16x3 (power-of-two
+                              scale per vector and per projection row, three FP16 MMAs
+                              per product, 22 significand bits like 3xTF32; vectors
+                              outside the scaled FP16 range are recomputed in FP32)   */
   LSHX_KERNEL_SMALL = 3,   /* reported by lshx_hasher_last_kernel only: the per-vector
                               latency kernel (FP32 FMA, one warp per signature bit) that
                               AUTO uses for a handful of host rows                      */
-  LSHX_KERNEL_TCGEN05_3XTF32 = 4 /* the same tcgen05 kernel with all three terms in TF32
-                              (3xTF32: 1.5x the tensor work, ~10x smaller rounding error) */
+  LSHX_KERNEL_TCGEN05_3XTF32 = 4,  /* the same kernel, all three terms in TF32 (3xTF32:
+                              2x the tensor time of the default)                       */
+  LSHX_KERNEL_TCGEN05_TF32BF16 = 5 /* the same kernel, TF32 hi.hi + BF16 cross terms
+                              (1.33x the tensor time, fp32-sgemm accuracy)             */
 } lshx_hash_kernel;
 
 typedef struct lshx_hasher lshx_hasher;   /* opaque */

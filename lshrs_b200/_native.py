@@ -27,11 +27,13 @@ __all__ = [
     "KERNEL_FFMA",
     "KERNEL_TCGEN05",
     "KERNEL_TCGEN05_3XTF32",
+    "KERNEL_TCGEN05_TF32BF16",
     "EXPORTED_SYMBOLS",
 ]
 
 KERNEL_AUTO, KERNEL_FFMA, KERNEL_TCGEN05 = 0, 1, 2
 KERNEL_TCGEN05_3XTF32 = 4
+KERNEL_TCGEN05_TF32BF16 = 5
 ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM, ERR_ZERO_VECTOR = -1, -2, -3, -4, -5
 
 # every symbol include/lshx.h declares (tests/test_cabi.py checks them against the header)

@@ -52,7 +52,8 @@ template <bool VEC4>
 __global__ void __launch_bounds__(THREADS, 2)
 hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* __restrict__ Rp,
                  int ncols_pad, uint8_t* __restrict__ out, int sig_bytes,
-                 uint8_t* __restrict__ zero_flag, int out_word_ok) {
+                 uint8_t* __restrict__ zero_flag, int out_word_ok,
+                 const int* __restrict__ tile_list, const int* __restrict__ tile_count) {
   __shared__ __align__(16) float Xs[2][BK][LDS];
   __shared__ __align__(16) float Rs[2][BK][LDS];
   __shared__ uint32_t bits[BM][BN / 32];
@@ -62,8 +63,13 @@ hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* _
   const int ty = tid >> 4;   // row group
   // column tile is the fast index so the CTAs that share an X tile run back to back (L2 reuse)
   const int nt = ncols_pad / BN;
-  const int ntile = blockIdx.x % nt;
-  const int64_t m0 = (int64_t)(blockIdx.x / nt) * BM;
+  // Work items: one (row tile, column tile) per CTA, or -- recompute mode, tile_list != nullptr -- a
+  // grid-stride loop over the 128-row tiles a tcgen05 launch listed for FP32 recomputation
+  // (hash_tc.cu, FP16x3 split); usually none, and the CTAs return at once.
+  const int64_t items = (tile_list != nullptr) ? (int64_t)(*tile_count) * nt : (int64_t)gridDim.x;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+  const int ntile = (int)(item % nt);
+  const int64_t m0 = (int64_t)((tile_list != nullptr) ? tile_list[item / nt] : item / nt) * BM;
   const int n0 = ntile * BN;
 
   // loader mapping: 128 rows x 16 k = 512 float4, two per thread
@@ -179,6 +185,8 @@ hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* _
       if (m0 + lrow + 64 < n) zero_flag[m0 + lrow + 64] = v1 ? 0 : 1;
     }
   }
+  __syncthreads();   // recompute mode: the shared tiles are reused by the next item
+  }
 }
 
 
@@ -245,10 +253,30 @@ int launch_hash_ffma(const HashShape& s, const float* d_X, int64_t n, const floa
       (s.sig_bytes % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0) ? 1 : 0;
   if (vec4)
     hash_ffma_kernel<true><<<grid, THREADS, 0, stream>>>(d_X, n, s.dim, d_Rp, s.ncols_pad, d_out,
-                                                         s.sig_bytes, d_zero_flag, word_ok);
+                                                         s.sig_bytes, d_zero_flag, word_ok, nullptr, nullptr);
   else
     hash_ffma_kernel<false><<<grid, THREADS, 0, stream>>>(d_X, n, s.dim, d_Rp, s.ncols_pad, d_out,
-                                                          s.sig_bytes, d_zero_flag, word_ok);
+                                                          s.sig_bytes, d_zero_flag, word_ok, nullptr, nullptr);
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
+
+// Recompute the 128-row tiles listed in d_tile_list[0 .. *d_tile_count) (device memory) in FP32.
+int launch_hash_ffma_tiles(const HashShape& s, const float* d_X, int64_t n, const float* d_Rp, uint8_t* d_out,
+                           const int* d_tile_list, const int* d_tile_count, int num_ctas, cudaStream_t stream) {
+  if (n <= 0) return LSHX_OK;
+  const bool vec4 = (s.dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_X) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(d_Rp) & 15) == 0);
+  const int word_ok =
+      (s.sig_bytes % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 3) == 0) ? 1 : 0;
+  dim3 grid((unsigned)num_ctas);
+  if (vec4)
+    hash_ffma_kernel<true><<<grid, THREADS, 0, stream>>>(d_X, n, s.dim, d_Rp, s.ncols_pad, d_out, s.sig_bytes,
+                                                         nullptr, word_ok, d_tile_list, d_tile_count);
+  else
+    hash_ffma_kernel<false><<<grid, THREADS, 0, stream>>>(d_X, n, s.dim, d_Rp, s.ncols_pad, d_out, s.sig_bytes,
+                                                          nullptr, word_ok, d_tile_list, d_tile_count);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;

@@ -61,7 +61,6 @@ constexpr uint32_t A_COL0 = 256;
 constexpr uint32_t A_STAGE_COLS = 64;
 // bring-up switches (TcParams::flags; LSHX_TC_FLAGS in the environment overrides the default)
 constexpr int TC_FLAG_B_WARP = 1;    // projections are TMA-loaded by warp 3 instead of warp 0
-constexpr int TC_FLAG_DEFER_ST = 2;  // converters overlap tcgen05.wait::st with the next chunk's loads
 constexpr int TC_FLAG_SWAP_A = 4;    // (bring-up) odd k in the low half of the BF16 A words
 constexpr int TC_FLAG_CG2 = 8;       // 2-CTA kernel (cta_group::2) where the shape allows it
 constexpr int TC_FLAG_SWAP_BHALF = 16;  // (bring-up) cluster rank 1 stages the FIRST half of the columns
@@ -239,6 +238,10 @@ struct TcParams {
   int flags;        // TC_FLAG_* (bring-up switches)
   uint8_t* out;
   uint8_t* zero_flag;
+  // FP16x3: 128-row tiles holding a vector that does not fit the scaled FP16 range are appended here
+  // (one entry per converter warp that saw one) and recomputed in FP32 right after (launch_hash_tc)
+  int* redo_count;
+  int* redo_list;
 };
 
 // One half (16 floats) of thread t's 128 B row of an X chunk in shared memory -> A-operand words.
@@ -605,8 +608,9 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024 B alignment
   const uint32_t x_smem = smem_base;
   const uint32_t XS = (uint32_t)p.xs;
-  const uint32_t B_HALF_BYTES = (uint32_t)p.ncols_pass * TKB * 4u;   // hi (or lo) rows of one stage: N x 64 B
-  const uint32_t B_STAGE_BYTES = 2u * B_HALF_BYTES;
+  constexpr uint32_t kPlanes = (kSplit == 2) ? 1u : 2u;              // FP16x3: q_hi | q_lo share one 64 B row
+  const uint32_t B_HALF_BYTES = (uint32_t)p.ncols_pass * TKB * 4u;   // one plane of one stage: N x 64 B
+  const uint32_t B_STAGE_BYTES = kPlanes * B_HALF_BYTES;
   const uint32_t b_smem = smem_base + XS * X_STAGE_BYTES;
   const uint32_t bar0 = smem_u32(bars);
   auto x_full = [&](uint32_t i) { return bar0 + 8u * i; };
@@ -659,8 +663,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         for (int kc = 0; kc < p.kc; ++kc)
           for (int hk = 0; hk < TK / TKB; ++hk) {
             const uint32_t dst = b_smem + (uint32_t)(kc * (TK / TKB) + hk) * B_STAGE_BYTES;
-            tma_load_2d(&tm_rhi, b_full(0), dst, kc * TK + hk * TKB, 0);
-            tma_load_2d(&tm_rlo, b_full(0), dst + B_HALF_BYTES, kc * TK + hk * TKB, 0);
+            if (kPlanes == 2) tma_load_2d(&tm_rhi, b_full(0), dst, kc * TK + hk * TKB, 0);
+            tma_load_2d(&tm_rlo, b_full(0), dst + (kPlanes - 1) * B_HALF_BYTES, kc * TK + hk * TKB, 0);
           }
       }
       __syncwarp();
@@ -683,8 +687,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           if (elect_one()) {
             mbar_arrive_expect_tx(b_full(br.idx), B_STAGE_BYTES);
             const uint32_t dst = b_smem + br.idx * B_STAGE_BYTES;
-            tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK + hk * TKB, col0);
-            tma_load_2d(&tm_rlo, b_full(br.idx), dst + B_HALF_BYTES, kc * TK + hk * TKB, col0);
+            if (kPlanes == 2) tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK + hk * TKB, col0);
+            tma_load_2d(&tm_rlo, b_full(br.idx), dst + (kPlanes - 1) * B_HALF_BYTES, kc * TK + hk * TKB, col0);
           }
           __syncwarp();
           br.advance(BS);
@@ -704,8 +708,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           if (elect_one()) {
             mbar_arrive_expect_tx(b_full(br.idx), B_STAGE_BYTES);
             const uint32_t dst = b_smem + br.idx * B_STAGE_BYTES;
-            tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK + hk * TKB, col0);
-            tma_load_2d(&tm_rlo, b_full(br.idx), dst + B_HALF_BYTES, kc * TK + hk * TKB, col0);
+            if (kPlanes == 2) tma_load_2d(&tm_rhi, b_full(br.idx), dst, kc * TK + hk * TKB, col0);
+            tma_load_2d(&tm_rlo, b_full(br.idx), dst + (kPlanes - 1) * B_HALF_BYTES, kc * TK + hk * TKB, col0);
           }
           __syncwarp();
           br.advance(BS);
@@ -715,8 +719,6 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   } else if (warp == 1) {
     // ===================== MMA issuer (whole warp runs the loops, one elected lane issues) =====
     Ring ar, br, dr;
-    const uint32_t idesc = make_idesc(N);  // one MMA spans every column of the pass
-    const uint32_t idesc_x = make_idesc_bf16(N);
     if (p.b_resident && (int64_t)blockIdx.x < work_items) {
       mbar_wait(b_full(0), 0);
       tc_fence_after();
@@ -728,7 +730,6 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       for (int kc = 0; kc < p.kc; ++kc) {
         mbar_wait(a_full(ar.idx), ar.phase);
         const uint32_t a_hi = tmem_base + A_COL0 + ar.idx * A_STAGE_COLS;
-        const uint32_t a_lo = a_hi + 32;
         for (int hk = 0; hk < TK / TKB; ++hk) {
           if (!p.b_resident) {
             mbar_wait(b_full(br.idx), br.phase);
@@ -736,26 +737,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           }
           const uint32_t bs =
               b_smem + (p.b_resident ? (uint32_t)(kc * (TK / TKB) + hk) : br.idx) * B_STAGE_BYTES;
-          const uint64_t desc_hi = make_b_desc(bs);
-          const uint64_t desc_lo = make_b_desc(bs + B_HALF_BYTES);
           if (elect_one()) {
-            // +32 B per K step inside the 64 B swizzle row: start-address field += 2; the K step's
-            // columns in the A stage start at hk*16 + 8*s.  Small terms first.
-#pragma unroll
-            for (int s = 0; s < TKB / 8; ++s) {
-              const uint32_t ka = (uint32_t)(hk * TKB + 8 * s);
-              const uint32_t acc = (kc > 0 || hk > 0 || s > 0) ? 1u : 0u;
-              if (kSplit == 0) {
-                tc_mma_ts(d_base, a_lo + ka, desc_hi + (uint64_t)(2 * s), idesc, acc);   // x_lo . r_hi
-                tc_mma_ts(d_base, a_hi + ka, desc_lo + (uint64_t)(2 * s), idesc, 1u);    // x_hi . r_lo
-              } else {
-                // s = 0: bf(x_lo) . bf(r_hi), s = 1: bf(x_hi) . bf(r_lo), each over the 16 k of this half
-                tc_mma_ts_f16(d_base, a_lo + ka, desc_lo + (uint64_t)(2 * s), idesc_x, acc);
-              }
-            }
-#pragma unroll
-            for (int s = 0; s < TKB / 8; ++s)                                            // x_hi . r_hi
-              tc_mma_ts(d_base, a_hi + (uint32_t)(hk * TKB + 8 * s), desc_hi + (uint64_t)(2 * s), idesc, 1u);
+            issue_khalf<kSplit, 1>(d_base, a_hi, hk, bs, B_HALF_BYTES, N, kc == 0 && hk == 0);
             if (!p.b_resident) tc_commit(b_empty(br.idx));  // same thread as the MMAs (commit tracks its own ops)
             if (hk == TK / TKB - 1) tc_commit(a_empty(ar.idx));
             if (hk == TK / TKB - 1 && kc == p.kc - 1) tc_commit(d_full(dr.idx));
@@ -772,53 +755,56 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int t = (warp - 4) * 32 + lane;                 // row within the tile == TMEM lane
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     Ring xr, ar;
-    const bool defer = (p.flags & TC_FLAG_DEFER_ST) != 0;
     const bool swp = (p.flags & TC_FLAG_SWAP_A) != 0;
-    int pend = -1;   // A stage whose tcgen05.st are still in flight (defer mode)
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int64_t mt = (p.npass == 1) ? w : w / p.npass;   // (no 64-bit division on the common path)
       const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
       bool viol = false;  // some |x| > 1e-8 (or NaN): not a zero vector
+      bool redo = false;  // FP16x3: this vector does not fit the scaled FP16 range
+      float sc = 0.f;     // FP16x3: the vector's power-of-two scale (0 until a non-zero chunk is met)
       for (int kc = 0; kc < p.kc; ++kc) {
         mbar_wait(x_full(xr.idx), xr.phase);
         const uint32_t row = x_smem + xr.idx * X_STAGE_BYTES + (uint32_t)t * 128u;
+        if (kSplit == 2 && sc == 0.f && !redo) {
+          const float m = chunk_absmax(row, t);
+          if (m > 0.f) {
+            sc = row_scale_for(m);
+            redo = (sc == 0.f);
+          }
+        }
         mbar_wait(a_empty(ar.idx), ar.phase ^ 1);
         tc_fence_after();
         const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {   // two halves of 16 floats keep the register count down
-          uint32_t hi[16], lo[16];
-          convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
-          if (h == 0 && pend >= 0) {
-            // the previous chunk's stores have had this half's loads and arithmetic to complete
-            tc_wait_st();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full((uint32_t)pend));
-            pend = -1;
+          if (kSplit == 2) {
+            uint32_t wd[16];
+            convert_half_f16(row, t, h, sc, wd, viol, redo);
+            tc_st16(a_dst + h * 16, wd);
+          } else {
+            uint32_t hi[16], lo[16];
+            convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
+            tc_st16(a_dst + h * 16, hi);
+            tc_st16(a_dst + 32 + h * 16, lo);
           }
-          tc_st16(a_dst + h * 16, hi);
-          tc_st16(a_dst + 32 + h * 16, lo);
         }
-        if (defer && kc != p.kc - 1) {
-          pend = (int)ar.idx;
-          __syncwarp();
-          if (lane == 0) mbar_arrive(x_empty(xr.idx));   // the loads above were consumed by the arithmetic
-        } else {
-          tc_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(a_full(ar.idx));
-            mbar_arrive(x_empty(xr.idx));
-          }
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(a_full(ar.idx));
+          mbar_arrive(x_empty(xr.idx));
         }
         xr.advance(XS);
         ar.advance(AS);
       }
-      if (p.zero_flag != nullptr && pass == 0) {
+      if (pass == 0) {
         const int64_t m = mt * TM + t;
-        if (m < p.n) p.zero_flag[m] = viol ? 0 : 1;
+        if (p.zero_flag != nullptr && m < p.n) p.zero_flag[m] = viol ? 0 : 1;
+        if (kSplit == 2) {
+          const unsigned any = __ballot_sync(0xffffffffu, redo && m < p.n);
+          if (any != 0u && lane == 0) p.redo_list[atomicAdd(p.redo_count, 1)] = (int)mt;
+        }
       }
     }
   } else if (warp >= 8) {
@@ -875,8 +861,9 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   const uint32_t XS = (uint32_t)p.xs;
   const uint32_t N = (uint32_t)p.ncols_pass;
   const uint32_t NH = N / 2;                                // projection columns staged by this CTA
+  constexpr uint32_t kPlanes = (kSplit == 2) ? 1u : 2u;
   const uint32_t B_HALF_BYTES = NH * TKB * 4u;              // one plane of one stage: N/2 rows x 64 B
-  const uint32_t B_STAGE_BYTES = 2u * B_HALF_BYTES;
+  const uint32_t B_STAGE_BYTES = kPlanes * B_HALF_BYTES;
   const uint32_t b_smem = smem_base + XS * X_STAGE_BYTES;
   const uint32_t bar0 = smem_u32(bars);
   auto x_full = [&](uint32_t i) { return bar0 + 8u * i; };
@@ -950,8 +937,8 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             if (rank == 0) mbar_arrive_expect_tx(b_full(br.idx), 2u * B_STAGE_BYTES);
             const uint32_t full0 = mapa_rank(b_full(br.idx), 0);
             const uint32_t dst = b_smem + br.idx * B_STAGE_BYTES;
-            tma_load_2d_cg2(&tm_rhi, full0, dst, kc * TK + hk * TKB, col0);
-            tma_load_2d_cg2(&tm_rlo, full0, dst + B_HALF_BYTES, kc * TK + hk * TKB, col0);
+            if (kPlanes == 2) tma_load_2d_cg2(&tm_rhi, full0, dst, kc * TK + hk * TKB, col0);
+            tma_load_2d_cg2(&tm_rlo, full0, dst + (kPlanes - 1) * B_HALF_BYTES, kc * TK + hk * TKB, col0);
           }
           __syncwarp();
           br.advance(BS2);
@@ -961,8 +948,6 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   } else if (warp == 1 && rank == 0) {
     // ===================== MMA issuer (leader CTA only): M = 256 over the pair ===================
     Ring ar, br, dr;
-    const uint32_t idesc = (make_idesc(N) & ~(31u << 24)) | ((uint32_t)((2 * TM) >> 4) << 24);
-    const uint32_t idesc_x = (make_idesc_bf16(N) & ~(31u << 24)) | ((uint32_t)((2 * TM) >> 4) << 24);
     for (int64_t w = pair; w < work_items; w += npairs) {
       mbar_wait(d_empty(dr.idx), dr.phase ^ 1);   // both epilogues have drained this stage
       tc_fence_after();
@@ -970,28 +955,12 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       for (int kc = 0; kc < p.kc; ++kc) {
         mbar_wait(a_full(ar.idx), ar.phase);      // both CTAs' converters
         const uint32_t a_hi = tmem_base + A_COL0 + ar.idx * A_STAGE_COLS;
-        const uint32_t a_lo = a_hi + 32;
         for (int hk = 0; hk < TK / TKB; ++hk) {
           mbar_wait(b_full(br.idx), br.phase);
           tc_fence_after();
           const uint32_t bs = b_smem + br.idx * B_STAGE_BYTES;
-          const uint64_t desc_hi = make_b_desc(bs);
-          const uint64_t desc_lo = make_b_desc(bs + B_HALF_BYTES);
           if (elect_one()) {
-#pragma unroll
-            for (int s = 0; s < TKB / 8; ++s) {
-              const uint32_t ka = (uint32_t)(hk * TKB + 8 * s);
-              const uint32_t acc = (kc > 0 || hk > 0 || s > 0) ? 1u : 0u;
-              if (kSplit == 0) {
-                tc_mma2_ts(d_base, a_lo + ka, desc_hi + (uint64_t)(2 * s), idesc, acc);
-                tc_mma2_ts(d_base, a_hi + ka, desc_lo + (uint64_t)(2 * s), idesc, 1u);
-              } else {
-                tc_mma2_ts_f16(d_base, a_lo + ka, desc_lo + (uint64_t)(2 * s), idesc_x, acc);
-              }
-            }
-#pragma unroll
-            for (int s = 0; s < TKB / 8; ++s)
-              tc_mma2_ts(d_base, a_hi + (uint32_t)(hk * TKB + 8 * s), desc_hi + (uint64_t)(2 * s), idesc, 1u);
+            issue_khalf<kSplit, 2>(d_base, a_hi, hk, bs, B_HALF_BYTES, N, kc == 0 && hk == 0);
             tc_commit_pair(b_empty(br.idx));
             if (hk == TK / TKB - 1) tc_commit_pair(a_empty(ar.idx));
             if (hk == TK / TKB - 1 && kc == p.kc - 1) tc_commit_pair(d_full(dr.idx));
@@ -1012,19 +981,33 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     for (int64_t w = pair; w < work_items; w += npairs) {
       const int64_t mt = (p.npass == 1) ? w : w / p.npass;
       const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
-      bool viol = false;
+      bool viol = false, redo = false;
+      float sc = 0.f;
       for (int kc = 0; kc < p.kc; ++kc) {
         mbar_wait(x_full(xr.idx), xr.phase);
         const uint32_t row = x_smem + xr.idx * X_STAGE_BYTES + (uint32_t)t * 128u;
+        if (kSplit == 2 && sc == 0.f && !redo) {
+          const float m = chunk_absmax(row, t);
+          if (m > 0.f) {
+            sc = row_scale_for(m);
+            redo = (sc == 0.f);
+          }
+        }
         mbar_wait(a_empty(ar.idx), ar.phase ^ 1);
         tc_fence_after();
         const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          uint32_t hi[16], lo[16];
-          convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
-          tc_st16(a_dst + h * 16, hi);
-          tc_st16(a_dst + 32 + h * 16, lo);
+          if (kSplit == 2) {
+            uint32_t wd[16];
+            convert_half_f16(row, t, h, sc, wd, viol, redo);
+            tc_st16(a_dst + h * 16, wd);
+          } else {
+            uint32_t hi[16], lo[16];
+            convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
+            tc_st16(a_dst + h * 16, hi);
+            tc_st16(a_dst + 32 + h * 16, lo);
+          }
         }
         tc_wait_st();
         tc_fence_before();
@@ -1036,9 +1019,13 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         xr.advance(XS);
         ar.advance(AS);
       }
-      if (p.zero_flag != nullptr && pass == 0) {
+      if (pass == 0) {
         const int64_t m = mt * (2 * TM) + rank * TM + t;
-        if (m < p.n) p.zero_flag[m] = viol ? 0 : 1;
+        if (p.zero_flag != nullptr && m < p.n) p.zero_flag[m] = viol ? 0 : 1;
+        if (kSplit == 2) {
+          const unsigned any = __ballot_sync(0xffffffffu, redo && m < p.n);
+          if (any != 0u && lane == 0) p.redo_list[atomicAdd(p.redo_count, 1)] = (int)(mt * 2 + rank);
+        }
       }
     }
   } else if (warp >= 8) {
@@ -1120,6 +1107,43 @@ __global__ void split_cross_kernel(const float* __restrict__ Rp, const int* __re
   }
 }
 
+// FP16x3 plane, [rows][dim_pad] 32-bit words, one block per row.  q = s_r * r with the power of two s_r
+// that puts the row's largest |r| in [2^13, 2^14); the 16 words of K block g hold 32 FP16: words
+// [0,8) = q_hi pairs, [8,16) = q_lo pairs (q_hi = FP16(q), q_lo = FP16(q - q_hi), even k in the low half).
+__global__ void split_f16_kernel(const float* __restrict__ Rp, const int* __restrict__ rowmap,
+                                 uint32_t* __restrict__ plane, int dim, int dim_pad) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int src = rowmap[row];
+  const float* r = (src >= 0) ? Rp + (int64_t)src * dim : nullptr;
+  float m = 0.f;
+  if (r != nullptr)
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) m = fmaxf(m, fabsf(r[k]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+  const int e = (int)((__float_as_uint(m) >> 23) & 0xFFu);
+  const int se = 254 + 13 - e;
+  const float sc = (e >= 13 && e < 255 && se >= 1) ? __uint_as_float((uint32_t)se << 23) : 1.f;
+  for (int wd = threadIdx.x; wd < dim_pad; wd += blockDim.x) {
+    const int g = wd / 16, j = wd % 16;
+    const int k0 = 16 * g + 2 * (j & 7);
+    float v[2] = {0.f, 0.f};
+    for (int e2 = 0; e2 < 2; ++e2) {
+      const int k = k0 + e2;
+      if (r != nullptr && k < dim) {
+        const float q = r[k] * sc;
+        float h0, h1;
+        unpack_f16(pack_f16(q, 0.f), h0, h1);
+        v[e2] = (j < 8) ? q : (q - h0);
+      }
+    }
+    plane[(int64_t)row * dim_pad + wd] = pack_f16(v[0], v[1]);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -1167,8 +1191,10 @@ struct TcPlan {
   float* d_hi = nullptr;
   float* d_lo = nullptr;     // TF32 residual plane (3xTF32 arm)
   uint32_t* d_x = nullptr;   // BF16 cross plane (TF32+BF16 arm)
-  CUtensorMap tm_rhi, tm_rlo, tm_rx;
-  CUtensorMap tm2_rhi, tm2_rlo, tm2_rx;   // the same planes with boxes of ncols_pass / 2 rows (2-CTA kernel)
+  uint32_t* d_h = nullptr;   // scaled FP16 hi|lo plane (FP16x3 arm)
+  const float* d_Rp = nullptr;  // the hasher's padded FP32 projections (not owned): FP32 recomputation
+  CUtensorMap tm_rhi, tm_rlo, tm_rx, tm_rh;
+  CUtensorMap tm2_rhi, tm2_rlo, tm2_rx, tm2_rh;   // the same planes with boxes of ncols_pass / 2 rows (2-CTA kernel)
   bool cg2_ok = false;
   int flags = 0;
   int auto_split = 1;   // what split < 0 resolves to for this shape
@@ -1217,7 +1243,7 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   const size_t bytes = (size_t)rows * s.dim_pad * sizeof(float);
   int* d_rowmap = nullptr;
   if (cudaMalloc(&pl->d_hi, bytes) != cudaSuccess || cudaMalloc(&pl->d_lo, bytes) != cudaSuccess ||
-      cudaMalloc(&pl->d_x, bytes) != cudaSuccess ||
+      cudaMalloc(&pl->d_x, bytes) != cudaSuccess || cudaMalloc(&pl->d_h, bytes) != cudaSuccess ||
       cudaMalloc(&d_rowmap, rowmap.size() * sizeof(int)) != cudaSuccess) {
     set_error("cudaMalloc of %zu bytes for the split projections failed", bytes);
     (void)cudaGetLastError();
@@ -1227,7 +1253,9 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   cudaMemcpy(d_rowmap, rowmap.data(), rowmap.size() * sizeof(int), cudaMemcpyHostToDevice);
   split_projections_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_hi, pl->d_lo, rows, s.dim, s.dim_pad);
   split_cross_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_x, rows, s.dim, s.dim_pad);
-  count_launch(2);
+  split_f16_kernel<<<rows, 256>>>(d_Rp, d_rowmap, pl->d_h, s.dim, s.dim_pad);
+  count_launch(3);
+  pl->d_Rp = d_Rp;
   const cudaError_t serr = cudaDeviceSynchronize();
   cudaFree(d_rowmap);
   if (serr != cudaSuccess) {
@@ -1246,6 +1274,9 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   rc = make_map(&pl->tm_rx, pl->d_x, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, brows,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc != LSHX_OK) return fail(rc);
+  rc = make_map(&pl->tm_rh, pl->d_h, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, brows,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  if (rc != LSHX_OK) return fail(rc);
   pl->cg2_ok = !pl->repack && pl->ncols_pass % 32 == 0;
   if (pl->cg2_ok) {
     const uint32_t hrows = brows / 2;
@@ -1254,15 +1285,28 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
         (rc = make_map(&pl->tm2_rlo, pl->d_lo, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, hrows,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != LSHX_OK ||
         (rc = make_map(&pl->tm2_rx, pl->d_x, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, hrows,
+                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != LSHX_OK ||
+        (rc = make_map(&pl->tm2_rh, pl->d_h, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, hrows,
                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B)) != LSHX_OK)
       return fail(rc);
   }
   pl->flags = TC_FLAG_B_WARP | TC_FLAG_CG2;
-  if (const char* e = getenv("LSHX_TC_FLAGS")) pl->flags = atoi(e);
-  // Narrow passes (N < 128: 32-clock MMAs, HBM-bound shapes such as 128 -> 64 bits) are not limited by
-  // tensor time, and alternating kind::f16 / kind::tf32 MMAs that short measured slower (6.7 vs 8.0 G
-  // vectors/s at 128/64): they keep the all-TF32 split.
-  pl->auto_split = (pl->ncols_pass >= 128) ? 1 : 0;
+  if (const char* e = getenv("LSHX_TC_FLAGS")) if (*e) pl->flags = atoi(e);
+  pl->auto_split = 2;   // scaled FP16x3: fastest on every measured shape (768/256, 1536/512, 128/64)
+  if (const char* e = getenv("LSHX_TC_SPLIT")) if (*e) pl->auto_split = atoi(e);
+  {
+    // keep freed scratch of the stream-ordered allocator cached instead of returning it at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, 0) == cudaSuccess) {
+      int dev_now = 0;
+      cudaGetDevice(&dev_now);
+      if (cudaDeviceGetDefaultMemPool(&pool, dev_now) == cudaSuccess) {
+        uint64_t keep = 64ull << 20;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+    }
+    (void)cudaGetLastError();
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&pl->num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1273,6 +1317,10 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
       cudaFuncSetAttribute(hash_tc2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(SMEM_BYTES + 1024)) != cudaSuccess ||
       cudaFuncSetAttribute(hash_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(SMEM_BYTES + 1024)) != cudaSuccess ||
+      cudaFuncSetAttribute(hash_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)(SMEM_BYTES + 1024)) != cudaSuccess ||
+      cudaFuncSetAttribute(hash_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)(SMEM_BYTES + 1024)) != cudaSuccess) {
     set_error("cannot reserve %u bytes of shared memory for the tcgen05 kernel", SMEM_BYTES + 1024);
     (void)cudaGetLastError();
@@ -1287,6 +1335,7 @@ void tc_plan_destroy(TcPlan* p) {
   if (p->d_hi) cudaFree(p->d_hi);
   if (p->d_lo) cudaFree(p->d_lo);
   if (p->d_x) cudaFree(p->d_x);
+  if (p->d_h) cudaFree(p->d_h);
   delete p;
 }
 
@@ -1294,18 +1343,20 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X
                    uint8_t* d_zero_flag, cudaStream_t stream) {
   if (n <= 0) return LSHX_OK;
   if (split < 0) split = plan->auto_split;
+  LSHX_REQUIRE(split >= 0 && split <= 2, "unknown split %d", split);
   LSHX_REQUIRE((reinterpret_cast<uintptr_t>(d_X) & 15) == 0, "tcgen05 kernel needs 16-byte aligned vectors");
   LSHX_REQUIRE(n < (1ll << 31), "hash batch of %lld rows exceeds one launch", (long long)n);
   CUtensorMap tm_x;
   int rc = make_map(&tm_x, d_X, (uint64_t)n, (uint64_t)s.dim, (uint64_t)s.dim * sizeof(float), TK, TM,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   if (rc != LSHX_OK) return rc;
+  const uint32_t planes = (split == 2) ? 1u : 2u;   // FP16x3 keeps q_hi | q_lo in one 64 B row
   TcParams p;
   p.n = n;
   p.kc = s.dim_pad / TK;
   p.ncols_pass = plan->ncols_pass;
   {
-    const uint32_t b_stage = 2u * (uint32_t)plan->ncols_pass * TKB * 4u;
+    const uint32_t b_stage = planes * (uint32_t)plan->ncols_pass * TKB * 4u;
     const uint32_t b_all = (uint32_t)p.kc * (TK / TKB) * b_stage;  // the whole split matrix of one pass
     p.b_resident = (plan->npass == 1 && b_all <= SMEM_BYTES - 4 * X_STAGE_BYTES) ? 1 : 0;
     const uint32_t b_bytes = p.b_resident ? b_all : BS * b_stage;
@@ -1324,32 +1375,52 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X
   p.out = d_out;
   p.zero_flag = d_zero_flag;
   p.flags = plan->flags;
+  p.redo_count = nullptr;
+  p.redo_list = nullptr;
+  // FP16x3: stream-ordered scratch for the list of 128-row tiles to recompute in FP32 (a counter, then
+  // up to four entries -- one per converter warp -- for every tile)
+  int* scratch = nullptr;
+  if (split == 2) {
+    const size_t bytes = 16 + sizeof(int) * 4 * (size_t)p.mtiles;
+    LSHX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, stream));
+    LSHX_CUDA(cudaMemsetAsync(scratch, 0, 16, stream));
+    p.redo_count = scratch;
+    p.redo_list = scratch + 4;
+  }
   // 2-CTA kernel: streamed projections, byte-aligned bands, enough 256-row tiles to fill every SM pair
   const int npairs = plan->num_sms / 2;
   if ((p.flags & TC_FLAG_CG2) && plan->cg2_ok && !p.b_resident && npairs > 0 &&
       (((n + 2 * TM - 1) / (2 * TM)) * p.npass >= npairs || (p.flags & TC_FLAG_CG2_ALWAYS))) {
     p.mtiles = (n + 2 * TM - 1) / (2 * TM);
-    const uint32_t b_bytes = BS2 * (uint32_t)plan->ncols_pass * TKB * 4u;   // per CTA: half the columns, two planes
+    const uint32_t b_bytes = BS2 * planes * (uint32_t)(plan->ncols_pass / 2) * TKB * 4u;   // per CTA: half the columns
     const uint32_t fit = (SMEM_BYTES - b_bytes) / X_STAGE_BYTES;
     p.xs = (int)(fit < (uint32_t)XS_MAX ? fit : (uint32_t)XS_MAX);
     const int64_t work2 = p.mtiles * p.npass;
     const unsigned grid2 = 2u * (unsigned)(work2 < npairs ? work2 : npairs);
     if (split == 0)
       hash_tc2_kernel<0><<<grid2, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm2_rhi, plan->tm2_rlo, p);
-    else
+    else if (split == 1)
       hash_tc2_kernel<1><<<grid2, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm2_rhi, plan->tm2_rx, p);
-    count_launch();
-    LSHX_CUDA(cudaGetLastError());
-    return LSHX_OK;
+    else
+      hash_tc2_kernel<2><<<grid2, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm2_rh, plan->tm2_rh, p);
+  } else {
+    const int64_t work = p.mtiles * p.npass;
+    const unsigned grid = (unsigned)(work < plan->num_sms ? work : plan->num_sms);
+    if (split == 0)
+      hash_tc_kernel<0><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rlo, p);
+    else if (split == 1)
+      hash_tc_kernel<1><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rx, p);
+    else
+      hash_tc_kernel<2><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rh, plan->tm_rh, p);
   }
-  const int64_t work = p.mtiles * p.npass;
-  const unsigned grid = (unsigned)(work < plan->num_sms ? work : plan->num_sms);
-  if (split == 0)
-    hash_tc_kernel<0><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rlo, p);
-  else
-    hash_tc_kernel<1><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rx, p);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
+  if (split == 2) {
+    // vectors outside the scaled FP16 range (normally none: the CTAs read a zero counter and return)
+    rc = launch_hash_ffma_tiles(s, d_X, n, plan->d_Rp, d_out, p.redo_list, p.redo_count, 2 * plan->num_sms, stream);
+    if (rc != LSHX_OK) return rc;
+    LSHX_CUDA(cudaFreeAsync(scratch, stream));
+  }
   return LSHX_OK;
 }
 

@@ -220,10 +220,10 @@ extern "C" int lshx_hasher_set_projections(lshx_hasher* h, const float* projecti
 
 extern "C" int lshx_hasher_set_kernel(lshx_hasher* h, int kernel) {
   LSHX_REQUIRE(h != nullptr, "null handle");
-  LSHX_REQUIRE(kernel == LSHX_KERNEL_AUTO || kernel == LSHX_KERNEL_FFMA || kernel == LSHX_KERNEL_TCGEN05 ||
-                   kernel == LSHX_KERNEL_TCGEN05_3XTF32,
-               "unknown kernel %d", kernel);
-  LSHX_REQUIRE((kernel != LSHX_KERNEL_TCGEN05 && kernel != LSHX_KERNEL_TCGEN05_3XTF32) || h->tc != nullptr,
+  const bool is_tc = kernel == LSHX_KERNEL_TCGEN05 || kernel == LSHX_KERNEL_TCGEN05_3XTF32 ||
+                     kernel == LSHX_KERNEL_TCGEN05_TF32BF16;
+  LSHX_REQUIRE(kernel == LSHX_KERNEL_AUTO || kernel == LSHX_KERNEL_FFMA || is_tc, "unknown kernel %d", kernel);
+  LSHX_REQUIRE(!is_tc || h->tc != nullptr,
                "the tcgen05 kernel does not support this shape (dim %d, %d x %d)", h->s.dim,
                h->s.num_bands, h->s.rows_per_band);
   std::lock_guard<std::mutex> lk(h->mu);
@@ -334,12 +334,14 @@ static int hash_pageable(lshx_hasher* h, const float* X, int64_t n, uint8_t* out
 
 static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_out,
                        uint8_t* d_flag, cudaStream_t st) {
-  const bool tc3 = h->kernel_pref == LSHX_KERNEL_TCGEN05_3XTF32;
+  // operand split of the tcgen05 kernel: < 0 = the plan's default (scaled FP16x3)
+  const int split = h->kernel_pref == LSHX_KERNEL_TCGEN05_3XTF32 ? 0
+                    : h->kernel_pref == LSHX_KERNEL_TCGEN05_TF32BF16 ? 1 : -1;
   const bool use_tc =
-      h->tc != nullptr && (h->kernel_pref == LSHX_KERNEL_TCGEN05 || tc3 ||
+      h->tc != nullptr && (h->kernel_pref == LSHX_KERNEL_TCGEN05 || split >= 0 ||
                            (h->kernel_pref == LSHX_KERNEL_AUTO &&
                             (reinterpret_cast<uintptr_t>(d_X) & 15) == 0));
-  h->last_kernel = use_tc ? (tc3 ? LSHX_KERNEL_TCGEN05_3XTF32 : LSHX_KERNEL_TCGEN05) : LSHX_KERNEL_FFMA;
+  h->last_kernel = use_tc ? (split >= 0 ? h->kernel_pref : LSHX_KERNEL_TCGEN05) : LSHX_KERNEL_FFMA;
   // one launch takes < 2^31 rows (TMA coordinates / grid size are 32-bit): split larger batches
   const int64_t piece = 1ll << 30;
   for (int64_t r0 = 0; r0 < n; r0 += piece) {
@@ -347,7 +349,7 @@ static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_o
     const float* x = d_X + r0 * h->s.dim;
     uint8_t* o = d_out + r0 * h->s.sig_bytes;
     uint8_t* f = d_flag ? d_flag + r0 : nullptr;
-    const int rc = use_tc ? launch_hash_tc(h->s, h->tc, tc3 ? 0 : -1, x, rows, o, f, st)
+    const int rc = use_tc ? launch_hash_tc(h->s, h->tc, split, x, rows, o, f, st)
                           : launch_hash_ffma(h->s, x, rows, h->d_Rp, o, f, st);
     if (rc != LSHX_OK) return rc;
   }

@@ -131,9 +131,11 @@ class LSHHasher:
 
     # ------------------------------------------------------------------ kernel choice
     def set_kernel(self, kernel: str | int) -> None:
-        """Choose the projection kernel: "auto", "ffma", "tcgen05" or "tcgen05_3xtf32"."""
+        """Choose the projection kernel: "auto", "ffma", "tcgen05" (scaled FP16x3 operand split), or the
+        same tensor-core kernel with another split: "tcgen05_3xtf32", "tcgen05_tf32bf16"."""
         table = {"auto": _native.KERNEL_AUTO, "ffma": _native.KERNEL_FFMA, "tcgen05": _native.KERNEL_TCGEN05,
-                 "tcgen05_3xtf32": _native.KERNEL_TCGEN05_3XTF32}
+                 "tcgen05_3xtf32": _native.KERNEL_TCGEN05_3XTF32,
+                 "tcgen05_tf32bf16": _native.KERNEL_TCGEN05_TF32BF16}
         code = table[kernel] if isinstance(kernel, str) else int(kernel)
         self._kernel = code
         if self._handle is not None:
@@ -144,7 +146,7 @@ class LSHHasher:
         if self._handle is None:
             return "none"
         code = _native.lib().lshx_hasher_last_kernel(self._handle)
-        return {0: "none", 1: "ffma", 2: "tcgen05", 3: "small", 4: "tcgen05_3xtf32"}.get(code, str(code))
+        return {0: "none", 1: "ffma", 2: "tcgen05", 3: "small", 4: "tcgen05_3xtf32", 5: "tcgen05_tf32bf16"}.get(code, str(code))
 
     @property
     def device(self) -> int:

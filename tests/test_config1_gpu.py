@@ -10,7 +10,7 @@ from oracle import lshrs_oracle as oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("kernel", ["tcgen05", "tcgen05_3xtf32", "ffma"])
+@pytest.mark.parametrize("kernel", ["tcgen05", "tcgen05_3xtf32", "tcgen05_tf32bf16", "ffma"])
 def test_config1_all_band_keys(kernel):
     from lshrs_b200 import LSHHasher
 

@@ -17,7 +17,8 @@ from oracle import lshrs_oracle as oracle
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = ("ffma", "tcgen05", "tcgen05_3xtf32")
+KERNELS = ("ffma", "tcgen05", "tcgen05_3xtf32", "tcgen05_tf32bf16")
+TC_KERNELS = KERNELS[1:]
 REL_MARGIN = 1e-5  # north_star exempt margin
 
 
@@ -114,7 +115,7 @@ def test_ragged_batch_sizes(n, kernel):
     _assert_parity(h.hash_batch_packed(X), X, h.projections, f"n={n}")
 
 
-@pytest.mark.parametrize("kernel", ("tcgen05", "tcgen05_3xtf32"))
+@pytest.mark.parametrize("kernel", TC_KERNELS)
 @pytest.mark.parametrize(
     "nb, r, dim, n",
     [
@@ -137,6 +138,43 @@ def test_two_cta_kernel(nb, r, dim, n, kernel, monkeypatch):
     want_flag = np.zeros(n, dtype=bool)
     want_flag[n // 2] = True
     np.testing.assert_array_equal(flag.astype(bool), want_flag)
+
+
+@pytest.mark.parametrize("flags", [None, 1 | 8 | 32])   # default dispatch; 2-CTA kernel forced
+@pytest.mark.parametrize("kernel", TC_KERNELS)
+def test_vectors_outside_the_fp16_range_are_recomputed(kernel, flags, monkeypatch):
+    """Scale-free parity.  The default tcgen05 arithmetic scales every vector into FP16's range from its
+    first non-zero K chunk; vectors whose later elements overflow that range, or whose magnitude has no
+    representable scale, must come back bit-exact from the FP32 recomputation (hash_tc.cu redo list)."""
+    if flags is not None:
+        monkeypatch.setenv("LSHX_TC_FLAGS", str(flags))
+    rng = np.random.default_rng(99)
+    n, dim = 6_000, 768
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    wild = np.arange(n) % 3 == 0          # magnitudes spread over 2^-40 .. 2^40 inside the row
+    X[wild] = (X[wild] * np.exp2(rng.integers(-40, 41, size=X[wild].shape))).astype(np.float32)
+    late = np.arange(n) % 3 == 1          # tiny first chunk, ordinary rest: the scale comes out too large
+    X[late, :32] *= np.float32(1e-9)
+    X[5] *= np.float32(1e30)              # uniformly huge / tiny rows are fine for the scaling itself
+    X[8] *= np.float32(1e-30)
+    X[11] = (X[11] * np.float32(1e-38) * 0.01).astype(np.float32)   # denormals only
+    X[14, :700] = 0.0                     # first non-zero element late in the row
+    X[17, 3] = np.inf
+    X[20, 100] = -np.inf
+    h = _hasher(16, 16, dim, 42, kernel)
+    got, flag = h.hash_batch_packed(X, return_zero_flag=True)
+    finite = np.isfinite(X).all(axis=1)
+    dn = np.ones(n, dtype=bool)
+    if kernel != "tcgen05":
+        dn[11] = False                    # known deviation of the TF32 arms: denormal inputs are flushed
+    keep = finite & dn
+    _assert_parity(got[keep], X[keep], h.projections, f"{kernel} flags={flags}")
+    # +-inf elements: the sign of every projection follows the sign of r at that position (numpy: inf * r)
+    if kernel != "tcgen05_3xtf32":        # (3xTF32 multiplies the infinite hi by r_lo too: inf - inf)
+        with np.errstate(invalid="ignore"):
+            want = oracle.hash_batch_vectorized(h.projections, X[~finite])
+        np.testing.assert_array_equal(got[~finite], want)
+    np.testing.assert_array_equal(flag.astype(bool), (np.abs(X) <= 1e-8).all(axis=1))
 
 
 @pytest.mark.parametrize("kernel", KERNELS)

@@ -11,8 +11,8 @@ for f in ${TCFLAGS_LIST:-default}; do
   grep -E "FAIL|TIMED" gpurun_out/${TAG}_tc_check_$f.log | head -8
 done
 unset LSHX_TC_FLAGS
-run() {  # name workload kernel flags
-  LSHX_TC_FLAGS=$4 timeout 300 python bench.py --workload $2 --kernel $3 --steps 10 --warmup 3 --no-cpu --no-e2e --no-rerank \
+run() {  # name workload kernel flags [split]
+  LSHX_TC_SPLIT=${5:-${LSHX_TC_SPLIT:-}} LSHX_TC_FLAGS=${4:-} timeout 300 python bench.py --workload $2 --kernel $3 --steps 10 --warmup 3 --no-cpu --no-e2e --no-rerank \
       > gpurun_out/${TAG}_$1.json 2>> gpurun_out/${TAG}_bench.err
   python - <<PY
 import json
@@ -26,6 +26,6 @@ PY
 }
 for spec in "$@"; do
   [ "$spec" = "$TAG" ] && continue
-  IFS=: read name wl kern flags <<< "$spec"
-  run $name $wl $kern $flags
+  IFS=: read name wl kern flags split <<< "$spec"
+  run "$name" "$wl" "$kern" "$flags" "$split"
 done

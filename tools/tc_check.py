@@ -40,6 +40,11 @@ CASES = [
     (200, 3, 16, 700),     # 600 bits -> three passes
     (3, 100, 256, 1500),   # 300 bits, 13 bytes per band, two bands per pass
     (16, 4, 128, 1_000_000),
+    # element magnitudes spread over 2^-40 .. 2^40 inside every row: the FP16x3 split must send the rows
+    # that leave its scaled range to the FP32 recomputation
+    (16, 16, 768, 30_000, "wild"),
+    (16, 32, 1536, 1_000, "wild"),
+    (16, 16, 64, 3_000, "tiny"),   # whole rows around 1e-38 .. 1e-42 (scale not representable / denormals)
 ]
 
 
@@ -47,8 +52,15 @@ def run_case(i: int) -> int:
     from lshrs_b200 import LSHHasher
     from oracle import lshrs_oracle as oracle
 
-    nb, r, dim, n = CASES[i]
-    X = np.random.default_rng(i).standard_normal((n, dim)).astype(np.float32)
+    nb, r, dim, n = CASES[i][:4]
+    dist = CASES[i][4] if len(CASES[i]) > 4 else "gauss"
+    rng = np.random.default_rng(i)
+    X = rng.standard_normal((n, dim)).astype(np.float32)
+    if dist == "wild":
+        X = (X * np.exp2(rng.integers(-40, 41, size=X.shape))).astype(np.float32)
+        X[::7] = rng.standard_normal((len(X[::7]), dim)).astype(np.float32)   # ordinary rows in between
+    elif dist == "tiny":
+        X = (X * np.float32(1e-38) * np.exp2(rng.integers(-14, 1, size=(n, 1)))).astype(np.float32)
     h = LSHHasher(nb, r, dim, seed=42)
     h._ensure_handle()
     h.set_kernel(os.environ.get("TC_KERNEL", "tcgen05"))
@@ -57,7 +69,8 @@ def run_case(i: int) -> int:
     dt = time.perf_counter() - t0
     want = oracle.hash_batch_vectorized(h.projections, X)
     rep = oracle.compare_packed(got, want, oracle.projection_margins(h.projections, X), 1e-5)
-    bad = rep["flips_outside_margin"] or rep["nonzero_pad_bits"] or flag.any()
+    want_flag = (np.abs(X) <= 1e-8).all(axis=1)   # LSHRS._prepare_vector's np.allclose(arr, 0, atol=1e-8)
+    bad = rep["flips_outside_margin"] or rep["nonzero_pad_bits"] or (flag.astype(bool) != want_flag).any()
     print(f"case {i} {CASES[i]} kernel={h.last_kernel} {dt * 1e3:.1f} ms -> {'FAIL' if bad else 'ok'} {rep}", flush=True)
     if bad:
         diff = np.unpackbits(got ^ want, axis=2, bitorder="little")
