@@ -70,9 +70,9 @@ def select_workload(args) -> None:
     args.dist = w["dist"]
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel PER ROW, from the ncu --set full
-# captures committed under profiles/ (r1_hash_tc_ncu.csv: 4.803 GB + 0.053 GB over 1 562 500 rows;
+# captures committed under profiles/ (r1_hash_tc_ncu.csv: 2.401 GB + 0.027 GB over 781 250 rows;
 # r1_hash_tc_dim128_ncu.csv: 6.401 GB + 0.201 GB over 12 500 000 rows); scaled to the rows of one launch
-ROOFLINE_TRAFFIC_PER_ROW = {("hash768", "tcgen05"): 4.856e9 / 1_562_500, ("hash128", "tcgen05"): 6.602e9 / 12_500_000}
+ROOFLINE_TRAFFIC_PER_ROW = {("hash768", "tcgen05"): 2.428e9 / 781_250, ("hash128", "tcgen05"): 6.602e9 / 12_500_000}
 
 
 def log(*a):

@@ -9,7 +9,7 @@ $CMD > gpurun_out/${TAG}_prof_plain.json 2> gpurun_out/${TAG}_prof_plain.err || 
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list exit $?"
-ncu --set full --clock-control none --import-source on -k regex:hash_tc_kernel -s 4 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:hash_tc -s 4 -c 2 \
     -f -o gpurun_out/${TAG}_hash_tc $CMD > gpurun_out/${TAG}_ncu_hash.log 2>&1
 echo "hash capture exit $?"
 ncu --set full --clock-control none --import-source on -k regex:rerank_kernel -s 2 -c 2 \
