@@ -1,40 +1,40 @@
-// tcgen05 projection-and-sign kernel (sm_100a): 3xTF32 split, TMA-staged, accumulators in TMEM.
+// tcgen05 projection-and-sign kernel (sm_100a): split-operand MMAs, TMA-staged, accumulators in TMEM.
 //
 // Replaces LSHHasher._project_and_pack (reference lshrs/hash/lsh.py:200-211) for a whole
-// batch, like hash_ffma.cu, but on the 5th-generation tensor cores:
+// batch, like hash_ffma.cu, but on the 5th-generation tensor cores.  Both operands are split
 //
-//     x = x_hi + x_lo, r = r_hi + r_lo   (hi = round-to-nearest TF32, lo = TF32 of the residual)
-//     x.r ~= x_lo.r_hi + x_hi.r_lo + x_hi.r_hi      (three kind::tf32 MMAs, fp32 accumulate)
+//     x = x_hi + x_lo, r = r_hi + r_lo,      x.r ~= x_lo.r_hi + x_hi.r_lo + x_hi.r_hi   (fp32 accumulate)
 //
-// which keeps ~22 significand bits per operand (the dropped x_lo.r_lo term and the rounding of
-// the lo parts are each <= 2^-22 relative), i.e. the accuracy of an fp32 sgemm with a different
-// summation order -- far inside the 1e-5 relative margin the parity contract allows, where
-// single-pass TF32 is not.
+// which keeps ~22 significand bits per operand (the dropped x_lo.r_lo term is <= 2^-22 relative), i.e.
+// at least the accuracy of an fp32 sgemm with a different summation order -- far inside the 1e-5
+// relative margin the parity contract allows, where single-pass TF32 is not.
+// Three arithmetic arms (template parameter kSplit):
+//     2  scaled FP16x3 (default): power-of-two scales per vector / projection row, three kind::f16 MMAs
+//     1  TF32 hi.hi + BF16 cross terms in one K-doubled kind::f16 MMA
+//     0  3xTF32
 //
-// Data flow per CTA (persistent, one CTA per SM, 384 threads):
+// Data flow per CTA (persistent, one CTA per SM, 384 threads; hash_tc2_kernel pairs two CTAs with
+// cta_group::2 so that each stages only half of the projection columns):
 //
-//   warp 0      TMA producer: X tile chunks (128 rows x 32 floats, SWIZZLE_128B) and, per chunk, two
-//               16-float halves of the pre-split projections R_hi / R_lo for every column of the pass
-//               (up to 256 rows x 64 B each, SWIZZLE_64B)
+//   warp 0      X TMA producer: tile chunks of 128 rows x 32 floats (SWIZZLE_128B)
+//   warp 3      projection TMA producer: per chunk, two 16-k halves of the pre-split projection planes for
+//               every column of the pass (rows of 64 B, SWIZZLE_64B)
 //   warps 4-7   converters: thread t owns row t of the tile; reads its 128 B of the X chunk from
 //               shared memory, splits hi/lo, writes them to TMEM with tcgen05.st (A operand lives
 //               in TMEM, so the MMA never re-reads X from shared memory); fuses the zero-vector
 //               test of LSHRS._prepare_vector (reference lshrs/core/main.py:1083)
-//   warp 1      MMA issuer: one elected thread issues tcgen05.mma.cta_group::1.kind::tf32, M=128,
-//               N=256 (or 128), K=8, A from TMEM, B (projection chunk) from shared memory
+//   warp 1      MMA issuer: one elected thread issues tcgen05.mma, M=128 (256 over a CTA pair),
+//               N=256 (or 128 / the compact column count), A from TMEM, B (projection chunk) from shared memory
 //   warps 8-11  epilogue: tcgen05.ld the fp32 accumulators, strict `> 0`, one bit per column into
 //               per-row words, 16 B of signature per 128 columns, coalesced store
 //   warp 2      TMEM allocation
 //
 // TMEM (512 columns): accumulators in columns [0,256) (one 256-column tile, or two stages of a
-// 128-column tile), A-operand stages in [256,512): 4 stages x (32 hi + 32 lo) columns.
-// Shared memory: 4 X stages x 16 KB + 4 projection stages x 32 KB = 192 KB.
+// 128-column tile), A-operand stages in [256,512): 4 stages x 64 columns.
+// Shared memory: 192 KB of X stages (16 KB each) and projection stages.
 //
-// Measured on B200 (profiles/): 571 M vectors/s at dim 768 / 256 bits = 1.0 x the cuBLAS-derived
-// sustained TF32 rate under the power cap; DRAM traffic equals the algorithmic bytes.  Bring-up
-// experiments (deliberately wrong arithmetic, not in the tree): never re-streaming R from L2 would
-// save 8 % and dropping one of the three MMAs 18 %, so neither a 2-CTA/multicast variant nor a
-// cheaper split is where the remaining time is.
+// Measured on B200 (profiles/): 917-991 M vectors/s at dim 768 / 256 bits with the default arm, tensor
+// pipe 87 % active under the board's power cap, DRAM traffic equal to the algorithmic bytes.
 
 #include <cstdio>
 #include <cstdlib>
