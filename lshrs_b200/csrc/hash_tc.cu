@@ -47,6 +47,7 @@ namespace lshx {
 namespace {
 
 constexpr int TC_THREADS = 384;
+constexpr int TC_THREADS_2CONV = 512;   // + a second converter warpgroup (warps 12-15), 1-CTA kernel only
 constexpr int TM = 128;          // rows per tile
 constexpr int TK = 32;           // floats per K chunk (128 B: one SWIZZLE_128B row)
 constexpr int TN = 128;          // accumulator columns per column tile (16 signature bytes)
@@ -64,6 +65,8 @@ constexpr int TC_FLAG_B_WARP = 1;    // projections are TMA-loaded by warp 3 ins
 constexpr int TC_FLAG_SWAP_A = 4;    // (bring-up) odd k in the low half of the BF16 A words
 constexpr int TC_FLAG_CG2 = 8;       // 2-CTA kernel (cta_group::2) where the shape allows it
 constexpr int TC_FLAG_SWAP_BHALF = 16;  // (bring-up) cluster rank 1 stages the FIRST half of the columns
+constexpr int TC_FLAG_CONV2 = 64;       // 1-CTA kernel: two converter warpgroups even when the heuristic says one
+constexpr int TC_FLAG_CONV1 = 128;      // 1-CTA kernel: never two
 constexpr int TC_FLAG_CG2_ALWAYS = 32;  // (bring-up) 2-CTA kernel even for batches smaller than one wave
 
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor)
@@ -305,11 +308,12 @@ __device__ __forceinline__ void unpack_f16(uint32_t w, float& even, float& odd) 
 // tensor time per term: 1.5 tensor-time units per product, and half the projection bytes.
 //   s_r: per projection row, from its largest |r| (static, split_f16_kernel).
 //   s_x: per vector, fixed by the first K chunk that holds a non-zero element so that its largest |x|
-//        lands in [2^5, 2^6): later elements may be up to 2^10 times larger before FP16 overflows, and
-//        elements more than 2^19 below it lose precision that is negligible against |x|.  A vector that
-//        does overflow (or whose scale is not representable: |x| < 2^-121) is flagged in TcParams::redo
-//        and recomputed by the FP32 FFMA kernel right after this one (launch_hash_tc) -- never silently
-//        wrong.
+//        lands in [2, 4): later elements may be up to 2^14 times larger before FP16 overflows, and
+//        elements far below it only meet FP16's absolute floor (2^-25 per element, i.e. at most
+//        sqrt(dim) * 2^-26 of |x||r| in total by Cauchy-Schwarz: 4e-7 at dim 768).  A vector that does
+//        overflow (or whose scale is not representable: fp32 denormals, inf) has its 128-row tile
+//        appended to TcParams::redo_list and recomputed by the FP32 FFMA kernel right after this one
+//        (launch_hash_tc) -- never silently wrong.
 
 // largest |x| of thread t's 32 floats of an X chunk
 __device__ __forceinline__ float chunk_absmax(uint32_t row, int t) {
@@ -325,11 +329,11 @@ __device__ __forceinline__ float chunk_absmax(uint32_t row, int t) {
   }
   return m;
 }
-// power of two s with m * s in [2^5, 2^6); 0 when it is not representable (m tiny, inf)
+// power of two s with m * s in [2, 4); 0 when it is not representable (m denormal or inf)
 __device__ __forceinline__ float row_scale_for(float m) {
   const int e = (int)((__float_as_uint(m) >> 23) & 0xFFu);
-  const int se = 254 + 5 - e;                       // biased exponent of the scale
-  return (e >= 5 && e < 255 && se >= 1) ? __uint_as_float((uint32_t)se << 23) : 0.f;
+  const int se = 254 + 1 - e;                       // biased exponent of the scale
+  return (e >= 1 && e < 255) ? __uint_as_float((uint32_t)se << 23) : 0.f;
 }
 // One half (16 floats) of a row -> 16 A-operand words: [0,8) = FP16 pairs of y_hi, [8,16) = pairs of y_lo.
 __device__ __forceinline__ void convert_half_f16(uint32_t row, int t, int h, float sc, uint32_t (&w)[16],
@@ -598,7 +602,7 @@ __device__ __forceinline__ void issue_khalf(uint32_t d_base, uint32_t a_stage, i
 //   already 2^-11 down: worst case 4 * 2^-8 * 2^-11 = 2^-17 relative to sum|x_i r_i|, measured max
 //   1.3e-7 * |x||r| on Gaussian data -- the same as an fp32 sgemm, two orders inside the 1e-5 margin.
 template <int kSplit>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS_2CONV, 1)
 hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_rhi,
                const __grid_constant__ CUtensorMap tm_rlo, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -625,6 +629,11 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   __shared__ uint32_t repack_sm[TM * 9];  // per-thread 8 words (+1 zero) of compact column bits
+  __shared__ uint8_t conv_flags[2][TM];   // second converter group -> first: its share of viol / redo
+  // One or two converter warpgroups (launch with TC_THREADS or TC_THREADS_2CONV).  With two, BOTH take
+  // every chunk and each converts one 16-float half of it: half the per-chunk latency chain for shapes
+  // with few K chunks per tile, where the converters rather than the tensor pipe set the pace.
+  const uint32_t ngroups = (blockDim.x > (unsigned)TC_THREADS) ? 2u : 1u;
   const uint32_t N = (uint32_t)p.ncols_pass;
   const uint32_t dstages = (N <= (uint32_t)TN) ? 2u : 1u;
   const int64_t work_items = p.mtiles * p.npass;
@@ -635,9 +644,9 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     tma_prefetch_desc(&tm_rlo);
   }
   if (warp == 1 && lane == 0) {
-    for (uint32_t i = 0; i < XS_MAX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 4); }
+    for (uint32_t i = 0; i < XS_MAX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 4 * ngroups); }
     for (uint32_t i = 0; i < BS; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-    for (uint32_t i = 0; i < AS; ++i) { mbar_init(a_full(i), 4); mbar_init(a_empty(i), 1); }
+    for (uint32_t i = 0; i < AS; ++i) { mbar_init(a_full(i), 4 * ngroups); mbar_init(a_empty(i), 1); }
     for (uint32_t i = 0; i < 2; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -750,12 +759,14 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       }
       dr.advance(dstages);
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== converters: X fp32 (smem) -> hi/lo TF32 (TMEM) =====================
-    const int t = (warp - 4) * 32 + lane;                 // row within the tile == TMEM lane
+  } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+    // ===================== converters: X fp32 (smem) -> split A operand (TMEM) =================
+    const uint32_t grp = (warp >= 12) ? 1u : 0u;
+    const int t = (warp & 3) * 32 + lane;                 // row within the tile == TMEM lane
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     Ring xr, ar;
     const bool swp = (p.flags & TC_FLAG_SWAP_A) != 0;
+    uint32_t tile_par = 0;
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
       const int64_t mt = (p.npass == 1) ? w : w / p.npass;   // (no 64-bit division on the common path)
       const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
@@ -766,7 +777,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         mbar_wait(x_full(xr.idx), xr.phase);
         const uint32_t row = x_smem + xr.idx * X_STAGE_BYTES + (uint32_t)t * 128u;
         if (kSplit == 2 && sc == 0.f && !redo) {
-          const float m = chunk_absmax(row, t);
+          const float m = chunk_absmax(row, t);   // over the whole chunk: both groups get the same scale
           if (m > 0.f) {
             sc = row_scale_for(m);
             redo = (sc == 0.f);
@@ -777,6 +788,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {   // two halves of 16 floats keep the register count down
+          if (ngroups == 2u && (uint32_t)h != grp) continue;
           if (kSplit == 2) {
             uint32_t wd[16];
             convert_half_f16(row, t, h, sc, wd, viol, redo);
@@ -798,7 +810,17 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         xr.advance(XS);
         ar.advance(AS);
       }
-      if (pass == 0) {
+      if (ngroups == 2u) {   // fold the second group's share of the per-row flags into the first's
+        if (grp == 1u) conv_flags[tile_par][t] = (uint8_t)((viol ? 1 : 0) | (redo ? 2 : 0));
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (grp == 0u) {
+          const uint8_t f = conv_flags[tile_par][t];
+          viol |= (f & 1) != 0;
+          redo |= (f & 2) != 0;
+        }
+        tile_par ^= 1u;
+      }
+      if (pass == 0 && grp == 0u) {
         const int64_t m = mt * TM + t;
         if (p.zero_flag != nullptr && m < p.n) p.zero_flag[m] = viol ? 0 : 1;
         if (kSplit == 2) {
@@ -807,7 +829,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ===================== epilogue: accumulators -> sign bits -> signature bytes ==============
     const int t = (warp - 8) * 32 + lane;
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
@@ -1406,12 +1428,15 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X
   } else {
     const int64_t work = p.mtiles * p.npass;
     const unsigned grid = (unsigned)(work < plan->num_sms ? work : plan->num_sms);
+    // two converter warpgroups where a tile is a few short MMAs (resident projections: narrow, HBM-bound shapes)
+    const bool conv2 = !(p.flags & TC_FLAG_CONV1) && (p.b_resident || (p.flags & TC_FLAG_CONV2));
+    const unsigned threads = conv2 ? TC_THREADS_2CONV : TC_THREADS;
     if (split == 0)
-      hash_tc_kernel<0><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rlo, p);
+      hash_tc_kernel<0><<<grid, threads, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rlo, p);
     else if (split == 1)
-      hash_tc_kernel<1><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rx, p);
+      hash_tc_kernel<1><<<grid, threads, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rhi, plan->tm_rx, p);
     else
-      hash_tc_kernel<2><<<grid, TC_THREADS, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rh, plan->tm_rh, p);
+      hash_tc_kernel<2><<<grid, threads, SMEM_BYTES + 1024, stream>>>(tm_x, plan->tm_rh, plan->tm_rh, p);
   }
   count_launch();
   LSHX_CUDA(cudaGetLastError());
