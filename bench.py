@@ -527,6 +527,12 @@ def run_b200(args) -> None:
 
     # ---- rerank (config 4) ------------------------------------------------------------------
     rerank = None
+    api = None
+    if rank == 0 and world == 1 and not args.no_e2e and args.workload == "hash768":
+        try:
+            api = run_api(args, dev)
+        except Exception as exc:  # noqa: BLE001 -- a side measurement must not take the headline down
+            api = {"error": repr(exc)}
     if not args.no_rerank:
         del X, out_dev
         torch.cuda.empty_cache()
@@ -548,11 +554,69 @@ def run_b200(args) -> None:
                             "note": "signatures left in HBM (no D2H gather); value above includes the overlapped D2H "
                                     "of every signature into pinned host memory"},
             "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
-            "cpu_baseline": cpu_baseline, "parity": parity, "rerank": rerank,
+            "cpu_baseline": cpu_baseline, "parity": parity, "rerank": rerank, "api": api,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_api(args, dev) -> dict:
+    """Throughput of the reference-facing LSHRS calls on one GPU.
+
+    Host data in, Python results out, in-memory bucket storage (the reference's Redis stays a host
+    component).  These are dominated by host-side key / bucket handling, not by the kernels; they are here
+    so that the drop-in API has numbers next to the kernel figures.  SURVEY section 8a gives the reference's own
+    figures with the same kind of storage double, measured in the build container: index 2.2 k vectors/s,
+    get_top_k 3.9 k queries/s, get_above_p 2.7 k queries/s.
+    """
+    import torch
+
+    from lshrs_b200 import LSHRS, InMemoryStorage
+
+    n_index, n_single, n_batch = 50_000, 300, 2_048
+    rng = np.random.default_rng(11)
+    centers = rng.standard_normal((n_index // 8, DIM)).astype(np.float32)
+    Xh = (np.repeat(centers, 8, axis=0) + 0.15 * rng.standard_normal((n_index, DIM))).astype(np.float32)
+    corpus_dev = torch.from_numpy(Xh).to(dev)
+    lsh = LSHRS(dim=DIM, num_perm=NUM_PERM, storage=InMemoryStorage(), vector_fetch_fn=lambda ids: Xh[ids])
+    ids = list(range(n_index))
+    t0 = time.perf_counter()
+    lsh.index(ids, Xh)
+    index_vps = n_index / (time.perf_counter() - t0)
+    extra = (Xh[:n_single] + 0.05 * rng.standard_normal((n_single, DIM))).astype(np.float32)
+    t0 = time.perf_counter()
+    for i in range(n_single):
+        lsh.ingest(n_index + i, extra[i])
+    lsh.flush()
+    ingest_cps = n_single / (time.perf_counter() - t0)
+    Q = (Xh[rng.integers(0, n_index, n_batch)] + 0.05 * rng.standard_normal((n_batch, DIM))).astype(np.float32)
+    t0 = time.perf_counter()
+    got_k = [lsh.get_top_k(Q[i], topk=10) for i in range(n_single)]
+    topk_qps = n_single / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    got_p = [lsh.get_above_p(Q[i], p=0.2) for i in range(n_single)]
+    above_qps = n_single / (time.perf_counter() - t0)
+    lsh.query_batch(Q[:64], top_k=10, top_p=0.2, corpus=corpus_dev)
+    t0 = time.perf_counter()
+    batch = lsh.query_batch(Q, top_k=10, top_p=0.2, corpus=corpus_dev)
+    batch_qps = n_batch / (time.perf_counter() - t0)
+    # the batched call must return what the per-query call returns
+    same = all([i for i, _ in batch[j]] == [i for i, _ in lsh.query(Q[j], top_k=10, top_p=0.2)]
+               for j in range(0, 64))
+    return {
+        "storage": "InMemoryStorage (bucket sets in a Python dict; no Redis on the box)",
+        "index": {"value": index_vps, "unit": "vectors/s", "rows": n_index},
+        "ingest": {"value": ingest_cps, "unit": "calls/s", "calls": n_single},
+        "get_top_k": {"value": topk_qps, "unit": "queries/s", "calls": n_single,
+                      "mean_results": float(np.mean([len(r) for r in got_k]))},
+        "get_above_p": {"value": above_qps, "unit": "queries/s", "calls": n_single,
+                        "mean_results": float(np.mean([len(r) for r in got_p]))},
+        "query_batch": {"value": batch_qps, "unit": "queries/s", "queries": n_batch,
+                        "corpus": "device-resident", "equals_per_query_calls": bool(same)},
+        "reference_survey_values": {"index": 2.2e3, "get_top_k": 3.9e3, "get_above_p": 2.7e3,
+                                    "note": "SURVEY section 8a, reference with its MockStorage in the build container"},
+    }
 
 
 def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> dict:

@@ -629,10 +629,16 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   __shared__ uint32_t repack_sm[TM * 9];  // per-thread 8 words (+1 zero) of compact column bits
-  __shared__ uint8_t conv_flags[2][TM];   // second converter group -> first: its share of viol / redo
-  // One or two converter warpgroups (launch with TC_THREADS or TC_THREADS_2CONV).  With two, BOTH take
-  // every chunk and each converts one 16-float half of it: half the per-chunk latency chain for shapes
-  // with few K chunks per tile, where the converters rather than the tensor pipe set the pace.
+  // per-row flags of a tile (bit 0: some |x| > 1e-8, bit 1: recompute in FP32), converters -> epilogue:
+  // written by each converter group before the a_full arrive of its last chunk of the tile, read by the
+  // epilogue after d_full.  8 slots: the converters run at most 4 chunks + 2 accumulator stages ahead.
+  __shared__ uint8_t conv_flags[8][2][TM];
+  // One or two converter warpgroups (launch with TC_THREADS or TC_THREADS_2CONV).  With two, the groups
+  // take alternate K chunks, so two load -> split -> tcgen05.st -> wait chains are in flight per SM: for
+  // shapes with few K chunks per tile (128 -> 64 bits: HBM-bound) the converters, not the tensor pipe, set
+  // the pace (ncu: half of their time was per-chunk barrier / fence overhead).  Both groups still wait for
+  // every chunk (which keeps their x_empty arrivals in the right mbarrier phase) and derive the vector's
+  // FP16 scale from the same chunk, so they agree on it without talking to each other.
   const uint32_t ngroups = (blockDim.x > (unsigned)TC_THREADS) ? 2u : 1u;
   const uint32_t N = (uint32_t)p.ncols_pass;
   const uint32_t dstages = (N <= (uint32_t)TN) ? 2u : 1u;
@@ -646,7 +652,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (uint32_t i = 0; i < XS_MAX; ++i) { mbar_init(x_full(i), 1); mbar_init(x_empty(i), 4 * ngroups); }
     for (uint32_t i = 0; i < BS; ++i) { mbar_init(b_full(i), 1); mbar_init(b_empty(i), 1); }
-    for (uint32_t i = 0; i < AS; ++i) { mbar_init(a_full(i), 4 * ngroups); mbar_init(a_empty(i), 1); }
+    for (uint32_t i = 0; i < AS; ++i) { mbar_init(a_full(i), 4); mbar_init(a_empty(i), 1); }   // the chunk's owner group
     for (uint32_t i = 0; i < 2; ++i) { mbar_init(d_full(i), 1); mbar_init(d_empty(i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -766,79 +772,73 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     Ring xr, ar;
     const bool swp = (p.flags & TC_FLAG_SWAP_A) != 0;
-    uint32_t tile_par = 0;
+    uint32_t tcount = 0;   // tiles (work items) this CTA has converted
+    uint32_t seq = 0;      // running chunk number: chunk seq belongs to group (seq & 1)
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
-      const int64_t mt = (p.npass == 1) ? w : w / p.npass;   // (no 64-bit division on the common path)
-      const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
       bool viol = false;  // some |x| > 1e-8 (or NaN): not a zero vector
       bool redo = false;  // FP16x3: this vector does not fit the scaled FP16 range
       float sc = 0.f;     // FP16x3: the vector's power-of-two scale (0 until a non-zero chunk is met)
-      for (int kc = 0; kc < p.kc; ++kc) {
+      for (int kc = 0; kc < p.kc; ++kc, ++seq) {
+        const bool mine = (ngroups == 1u) || ((seq & 1u) == grp);
         mbar_wait(x_full(xr.idx), xr.phase);
         const uint32_t row = x_smem + xr.idx * X_STAGE_BYTES + (uint32_t)t * 128u;
         if (kSplit == 2 && sc == 0.f && !redo) {
-          const float m = chunk_absmax(row, t);   // over the whole chunk: both groups get the same scale
+          const float m = chunk_absmax(row, t);   // both groups look at the same chunk: same scale
           if (m > 0.f) {
             sc = row_scale_for(m);
             redo = (sc == 0.f);
           }
         }
-        mbar_wait(a_empty(ar.idx), ar.phase ^ 1);
-        tc_fence_after();
-        const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
+        if (mine) {
+          mbar_wait(a_empty(ar.idx), ar.phase ^ 1);
+          tc_fence_after();
+          const uint32_t a_dst = tmem_base + lane_field + A_COL0 + ar.idx * A_STAGE_COLS;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {   // two halves of 16 floats keep the register count down
-          if (ngroups == 2u && (uint32_t)h != grp) continue;
-          if (kSplit == 2) {
-            uint32_t wd[16];
-            convert_half_f16(row, t, h, sc, wd, viol, redo);
-            tc_st16(a_dst + h * 16, wd);
-          } else {
-            uint32_t hi[16], lo[16];
-            convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
-            tc_st16(a_dst + h * 16, hi);
-            tc_st16(a_dst + 32 + h * 16, lo);
+          for (int h = 0; h < 2; ++h) {   // two halves of 16 floats keep the register count down
+            if (kSplit == 2) {
+              uint32_t wd[16];
+              convert_half_f16(row, t, h, sc, wd, viol, redo);
+              tc_st16(a_dst + h * 16, wd);
+            } else {
+              uint32_t hi[16], lo[16];
+              convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
+              tc_st16(a_dst + h * 16, hi);
+              tc_st16(a_dst + 32 + h * 16, lo);
+            }
           }
+          tc_wait_st();
+          // this group's last chunk of the tile: hand its share of the row flags to the epilogue (the
+          // a_full arrive below releases the store; the epilogue reads after d_full)
+          if (kc + (int)ngroups >= p.kc)
+            conv_flags[tcount & 7u][grp][t] = (uint8_t)((viol ? 1 : 0) | (redo ? 2 : 0));
+          tc_fence_before();
         }
-        tc_wait_st();
-        tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(a_full(ar.idx));
+          if (mine) mbar_arrive(a_full(ar.idx));
           mbar_arrive(x_empty(xr.idx));
         }
         xr.advance(XS);
         ar.advance(AS);
       }
-      if (ngroups == 2u) {   // fold the second group's share of the per-row flags into the first's
-        if (grp == 1u) conv_flags[tile_par][t] = (uint8_t)((viol ? 1 : 0) | (redo ? 2 : 0));
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (grp == 0u) {
-          const uint8_t f = conv_flags[tile_par][t];
-          viol |= (f & 1) != 0;
-          redo |= (f & 2) != 0;
-        }
-        tile_par ^= 1u;
-      }
-      if (pass == 0 && grp == 0u) {
-        const int64_t m = mt * TM + t;
-        if (p.zero_flag != nullptr && m < p.n) p.zero_flag[m] = viol ? 0 : 1;
-        if (kSplit == 2) {
-          const unsigned any = __ballot_sync(0xffffffffu, redo && m < p.n);
-          if (any != 0u && lane == 0) p.redo_list[atomicAdd(p.redo_count, 1)] = (int)mt;
-        }
-      }
+      ++tcount;
     }
   } else if (warp >= 8 && warp < 12) {
     // ===================== epilogue: accumulators -> sign bits -> signature bytes ==============
     const int t = (warp - 8) * 32 + lane;
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     Ring dr;
-    for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
+    uint32_t tcount = 0;
+    for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x, ++tcount) {
       const int64_t mt = (p.npass == 1) ? w : w / p.npass;   // (no 64-bit division on the common path)
       const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
       mbar_wait(d_full(dr.idx), dr.phase);
       tc_fence_after();
+      // row flags from the converter group(s) that own chunks of this tile
+      const uint32_t first_owner = (tcount * (uint32_t)p.kc) & 1u;
+      uint32_t fl = 0;
+      if (ngroups == 1u || p.kc >= 2 || first_owner == 0u) fl |= conv_flags[tcount & 7u][0][t];
+      if (ngroups == 2u && (p.kc >= 2 || first_owner == 1u)) fl |= conv_flags[tcount & 7u][1][t];
       uint32_t words[8];
       read_sign_words(tmem_base + lane_field + dr.idx * TN, N, words);
       tc_fence_before();
@@ -846,7 +846,15 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       if (lane == 0) mbar_arrive(d_empty(dr.idx));
       dr.advance(dstages);
 
-      store_signature(p, N, pass, mt * TM + t, t, words, repack_sm);
+      const int64_t m = mt * TM + t;
+      store_signature(p, N, pass, m, t, words, repack_sm);
+      if (pass == 0) {
+        if (p.zero_flag != nullptr && m < p.n) p.zero_flag[m] = (fl & 1u) ? 0 : 1;
+        if (kSplit == 2) {
+          const unsigned any = __ballot_sync(0xffffffffu, (fl & 2u) != 0u && m < p.n);
+          if (any != 0u && lane == 0) p.redo_list[atomicAdd(p.redo_count, 1)] = (int)mt;
+        }
+      }
     }
   }
 
