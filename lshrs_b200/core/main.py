@@ -149,7 +149,12 @@ class LSHRS:
     def create_signatures(self, *, format: str = "postgres", **loader_kwargs: Any) -> None:
         """Stream ``(indices, vectors)`` batches from a loader into :meth:`index` (reference main.py:315-384)."""
         loader = self._resolve_loader(format)
-        for indices, vectors in loader(**loader_kwargs):
+        batches = loader(**loader_kwargs)
+        if format.lower() in {"parquet", "pq"}:
+            from lshrs_b200.io.parquet import prefetched
+
+            batches = prefetched(batches)   # decode the next row group while this batch is hashed
+        for indices, vectors in batches:
             self.index(indices, vectors)
 
     @staticmethod

@@ -28,7 +28,54 @@ except ImportError:  # pragma: no cover
 
 DEFAULT_PARQUET_BATCH_SIZE = 262_144  # rows per yielded batch; the GPU wants large batches
 
-__all__ = ["iter_parquet_vectors", "DEFAULT_PARQUET_BATCH_SIZE"]
+__all__ = ["iter_parquet_vectors", "prefetched", "DEFAULT_PARQUET_BATCH_SIZE"]
+
+
+def prefetched(batches: Iterator, depth: int = 2) -> Iterator:
+    """Run a batch iterator one step ahead in a worker thread.
+
+    ``LSHRS.create_signatures`` wraps the Parquet loader in this, so that decoding row group ``i + 1``
+    (pyarrow releases the GIL) overlaps hashing and bucket bookkeeping of batch ``i``.  Order is kept;
+    an exception in the loader is re-raised at the point of iteration; abandoning the iterator stops the
+    worker at its next hand-over.
+    """
+    import queue
+    import threading
+
+    q: queue.Queue = queue.Queue(maxsize=max(1, depth))
+    stop = threading.Event()
+    done = object()
+
+    def put(item) -> bool:
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def work() -> None:
+        try:
+            for item in batches:
+                if not put(("item", item)):
+                    return
+            put((done, None))
+        except BaseException as exc:  # noqa: BLE001 -- handed to the consumer
+            put(("error", exc))
+
+    worker = threading.Thread(target=work, name="lshrs-parquet-prefetch", daemon=True)
+    worker.start()
+    try:
+        while True:
+            kind, payload = q.get()
+            if kind is done:
+                return
+            if kind == "error":
+                raise payload
+            yield payload
+    finally:
+        stop.set()
 
 
 def _matrix_from_list_array(arr) -> np.ndarray:

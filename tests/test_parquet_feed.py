@@ -57,6 +57,37 @@ def test_errors_match_the_reference(tmp_path):
     assert np.isnan(out[0, 1]) and out[1, 1] == 4.0
 
 
+def test_prefetched_keeps_order_and_propagates_errors(tmp_path):
+    from lshrs_b200.io.parquet import prefetched
+
+    assert list(prefetched(iter(range(50)), depth=1)) == list(range(50))
+    assert list(prefetched(iter(()))) == []
+
+    def failing():
+        yield 1
+        yield 2
+        raise ValueError("boom")
+
+    it = prefetched(failing())
+    assert next(it) == 1 and next(it) == 2
+    with pytest.raises(ValueError, match="boom"):
+        next(it)
+    # abandoning the iterator early must not leave the worker blocked on a full queue
+    it = prefetched(iter(range(10_000)), depth=1)
+    assert next(it) == 0
+    it.close()
+    # the Parquet loader behind it: same batches as without
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((35, 4)).astype(np.float32)
+    path = tmp_path / "p.parquet"
+    _write(path, list(range(35)), X.tolist(), pa.list_(pa.float32()))
+    plain = list(iter_parquet_vectors(path, batch_size=8))
+    ahead = list(prefetched(iter_parquet_vectors(path, batch_size=8)))
+    assert [i for i, _ in plain] == [i for i, _ in ahead]
+    for (_, a), (_, b) in zip(plain, ahead):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_loader_resolution():
     from lshrs_b200 import LSHRS
 
