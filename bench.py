@@ -71,8 +71,8 @@ def select_workload(args) -> None:
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel PER ROW, from the ncu --set full
 # captures committed under profiles/ (r1_hash_tc_ncu.csv: 2.401 GB + 0.027 GB over 781 250 rows;
-# r1_hash_tc_dim128_ncu.csv: 6.401 GB + 0.201 GB over 12 500 000 rows); scaled to the rows of one launch
-ROOFLINE_TRAFFIC_PER_ROW = {("hash768", "tcgen05"): 2.428e9 / 781_250, ("hash128", "tcgen05"): 6.602e9 / 12_500_000}
+# r1_hash_tc_dim128_ncu.csv: 6.400 GB + 0.201 GB over 12 500 000 rows); scaled to the rows of one launch
+ROOFLINE_TRAFFIC_PER_ROW = {("hash768", "tcgen05"): 2.428e9 / 781_250, ("hash128", "tcgen05"): 6.601e9 / 12_500_000}
 
 
 def log(*a):
@@ -578,13 +578,14 @@ def run_api(args, dev) -> dict:
     rng = np.random.default_rng(11)
     centers = rng.standard_normal((n_index // 8, DIM)).astype(np.float32)
     Xh = (np.repeat(centers, 8, axis=0) + 0.15 * rng.standard_normal((n_index, DIM))).astype(np.float32)
-    corpus_dev = torch.from_numpy(Xh).to(dev)
-    lsh = LSHRS(dim=DIM, num_perm=NUM_PERM, storage=InMemoryStorage(), vector_fetch_fn=lambda ids: Xh[ids])
+    extra = (Xh[:n_single] + 0.05 * rng.standard_normal((n_single, DIM))).astype(np.float32)
+    allvec = np.concatenate([Xh, extra])          # id -> vector, what vector_fetch_fn serves
+    corpus_dev = torch.from_numpy(allvec).to(dev)
+    lsh = LSHRS(dim=DIM, num_perm=NUM_PERM, storage=InMemoryStorage(), vector_fetch_fn=lambda ids: allvec[ids])
     ids = list(range(n_index))
     t0 = time.perf_counter()
     lsh.index(ids, Xh)
     index_vps = n_index / (time.perf_counter() - t0)
-    extra = (Xh[:n_single] + 0.05 * rng.standard_normal((n_single, DIM))).astype(np.float32)
     t0 = time.perf_counter()
     for i in range(n_single):
         lsh.ingest(n_index + i, extra[i])
