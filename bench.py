@@ -592,6 +592,8 @@ def run_api(args, dev) -> dict:
     lsh.flush()
     ingest_cps = n_single / (time.perf_counter() - t0)
     Q = (Xh[rng.integers(0, n_index, n_batch)] + 0.05 * rng.standard_normal((n_batch, DIM))).astype(np.float32)
+    lsh.get_top_k(Q[-1], topk=10)        # first calls create the rerank handle / workspaces: off the clock
+    lsh.get_above_p(Q[-1], p=0.2)
     t0 = time.perf_counter()
     got_k = [lsh.get_top_k(Q[i], topk=10) for i in range(n_single)]
     topk_qps = n_single / (time.perf_counter() - t0)

@@ -62,9 +62,7 @@ constexpr uint32_t A_COL0 = 256;
 constexpr uint32_t A_STAGE_COLS = 64;
 // bring-up switches (TcParams::flags; LSHX_TC_FLAGS in the environment overrides the default)
 constexpr int TC_FLAG_B_WARP = 1;    // projections are TMA-loaded by warp 3 instead of warp 0
-constexpr int TC_FLAG_SWAP_A = 4;    // (bring-up) odd k in the low half of the BF16 A words
 constexpr int TC_FLAG_CG2 = 8;       // 2-CTA kernel (cta_group::2) where the shape allows it
-constexpr int TC_FLAG_SWAP_BHALF = 16;  // (bring-up) cluster rank 1 stages the FIRST half of the columns
 constexpr int TC_FLAG_CONV2 = 64;       // 1-CTA kernel: two converter warpgroups even when the heuristic says one
 constexpr int TC_FLAG_CONV1 = 128;      // 1-CTA kernel: never two
 constexpr int TC_FLAG_CG2_ALWAYS = 32;  // (bring-up) 2-CTA kernel even for batches smaller than one wave
@@ -252,7 +250,7 @@ struct TcParams {
 // words [8,16) = BF16 pairs of hi (the layout of the cross plane, split_cross_kernel).  `viol` collects
 // the zero-vector test of LSHRS._prepare_vector (some |x| > 1e-8, or NaN).
 template <int kSplit>
-__device__ __forceinline__ void convert_half(uint32_t row, int t, int h, bool swp, uint32_t (&hi)[16],
+__device__ __forceinline__ void convert_half(uint32_t row, int t, int h, uint32_t (&hi)[16],
                                              uint32_t (&lo)[16], bool& viol) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -279,10 +277,10 @@ __device__ __forceinline__ void convert_half(uint32_t row, int t, int h, bool sw
       else hc[e] = ((hu & 0x7FFFFFFFu) >= 0x7F7F8000u) ? 0.f : hf;
     }
     if (kSplit != 0) {
-      lo[c * 2 + 0] = swp ? pack_bf16(lf[1], lf[0]) : pack_bf16(lf[0], lf[1]);
-      lo[c * 2 + 1] = swp ? pack_bf16(lf[3], lf[2]) : pack_bf16(lf[2], lf[3]);
-      lo[8 + c * 2 + 0] = swp ? pack_bf16(hc[1], hc[0]) : pack_bf16(hc[0], hc[1]);
-      lo[8 + c * 2 + 1] = swp ? pack_bf16(hc[3], hc[2]) : pack_bf16(hc[2], hc[3]);
+      lo[c * 2 + 0] = pack_bf16(lf[0], lf[1]);
+      lo[c * 2 + 1] = pack_bf16(lf[2], lf[3]);
+      lo[8 + c * 2 + 0] = pack_bf16(hc[0], hc[1]);
+      lo[8 + c * 2 + 1] = pack_bf16(hc[2], hc[3]);
     }
   }
 }
@@ -771,7 +769,6 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
     const int t = (warp & 3) * 32 + lane;                 // row within the tile == TMEM lane
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     Ring xr, ar;
-    const bool swp = (p.flags & TC_FLAG_SWAP_A) != 0;
     uint32_t tcount = 0;   // tiles (work items) this CTA has converted
     uint32_t seq = 0;      // running chunk number: chunk seq belongs to group (seq & 1)
     for (int64_t w = blockIdx.x; w < work_items; w += gridDim.x) {
@@ -801,7 +798,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
               tc_st16(a_dst + h * 16, wd);
             } else {
               uint32_t hi[16], lo[16];
-              convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
+              convert_half<kSplit>(row, t, h, hi, lo, viol);
               tc_st16(a_dst + h * 16, hi);
               tc_st16(a_dst + 32 + h * 16, lo);
             }
@@ -955,7 +952,7 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   } else if (warp == 3) {
     // ===================== projection producer: this CTA's half of the pass's columns ===========
     Ring br;
-    const uint32_t half = (p.flags & TC_FLAG_SWAP_BHALF) ? (rank ^ 1u) : rank;
+    const uint32_t half = rank;   // the leader's shared memory feeds accumulator columns [0, N/2)
     for (int64_t w = pair; w < work_items; w += npairs) {
       const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
       const int col0 = pass * (int)N + (int)(half * NH);
@@ -1006,7 +1003,6 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
     // ===================== converters (as in the 1-CTA kernel; a_full lives in the leader) =======
     const int t = (warp - 4) * 32 + lane;
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
-    const bool swp = (p.flags & TC_FLAG_SWAP_A) != 0;
     Ring xr, ar;
     for (int64_t w = pair; w < work_items; w += npairs) {
       const int64_t mt = (p.npass == 1) ? w : w / p.npass;
@@ -1034,7 +1030,7 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
             tc_st16(a_dst + h * 16, wd);
           } else {
             uint32_t hi[16], lo[16];
-            convert_half<kSplit>(row, t, h, swp, hi, lo, viol);
+            convert_half<kSplit>(row, t, h, hi, lo, viol);
             tc_st16(a_dst + h * 16, hi);
             tc_st16(a_dst + 32 + h * 16, lo);
           }
