@@ -60,12 +60,13 @@ constexpr uint32_t SMEM_BYTES = 196608;                // 4 x 16 KB of X + 4 x 3
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t A_COL0 = 256;
 constexpr uint32_t A_STAGE_COLS = 64;
-// bring-up switches (TcParams::flags; LSHX_TC_FLAGS in the environment overrides the default)
-constexpr int TC_FLAG_B_WARP = 1;    // projections are TMA-loaded by warp 3 instead of warp 0
-constexpr int TC_FLAG_CG2 = 8;       // 2-CTA kernel (cta_group::2) where the shape allows it
+// dispatch switches (TcParams::flags).  The default is B_WARP | CG2; LSHX_TC_FLAGS in the environment
+// overrides it when a plan is created -- the tests use that to drive every variant on small batches.
+constexpr int TC_FLAG_B_WARP = 1;       // projections are TMA-loaded by warp 3 instead of warp 0
+constexpr int TC_FLAG_CG2 = 8;          // 2-CTA kernel (cta_group::2) where the shape allows it
+constexpr int TC_FLAG_CG2_ALWAYS = 32;  // ... even for batches smaller than one 256-row tile per SM pair
 constexpr int TC_FLAG_CONV2 = 64;       // 1-CTA kernel: two converter warpgroups even when the heuristic says one
 constexpr int TC_FLAG_CONV1 = 128;      // 1-CTA kernel: never two
-constexpr int TC_FLAG_CG2_ALWAYS = 32;  // (bring-up) 2-CTA kernel even for batches smaller than one wave
 
 // instruction descriptor: D=F32, A=B=TF32, both K-major, M=128, N=n (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t n) {
@@ -236,7 +237,7 @@ struct TcParams {
   int64_t mtiles;   // ceil(n / 128)
   int sig_bytes;
   int out_vec_ok;   // 16-byte stores allowed
-  int flags;        // TC_FLAG_* (bring-up switches)
+  int flags;        // TC_FLAG_*
   uint8_t* out;
   uint8_t* zero_flag;
   // FP16x3: 128-row tiles holding a vector that does not fit the scaled FP16 range are appended here

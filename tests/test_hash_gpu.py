@@ -140,6 +140,30 @@ def test_two_cta_kernel(nb, r, dim, n, kernel, monkeypatch):
     np.testing.assert_array_equal(flag.astype(bool), want_flag)
 
 
+@pytest.mark.parametrize("kernel", TC_KERNELS)
+@pytest.mark.parametrize(
+    "nb, r, dim, n",
+    [
+        (16, 16, 768, 3_000),    # 24 K chunks per tile, streamed projections
+        (16, 4, 128, 20_000),    # config 5: resident projections, 4 chunks, nibble bands
+        (16, 8, 32, 1_500),      # ONE chunk per tile: the groups own alternate tiles
+        (5, 20, 96, 2_000),      # three chunks per tile (odd): ownership flips from tile to tile; compact columns
+        (16, 32, 1536, 1_000),   # two passes per tile
+    ],
+)
+def test_two_converter_groups_in_the_one_cta_kernel(nb, r, dim, n, kernel, monkeypatch):
+    """LSHX_TC_FLAGS = B_WARP | CONV2: the 1-CTA kernel with two converter warpgroups on alternate K
+    chunks and the row flags handed to the epilogue through shared memory."""
+    monkeypatch.setenv("LSHX_TC_FLAGS", str(1 | 64))
+    h = _hasher(nb, r, dim, 42, kernel)
+    X = np.random.default_rng(n + dim).standard_normal((n, dim)).astype(np.float32)
+    X[::97] = 0.0
+    X[5::211, : dim // 2] = 0.0          # leading zeros: the FP16 scale comes from a later chunk
+    got, flag = h.hash_batch_packed(X, return_zero_flag=True)
+    _assert_parity(got, X, h.projections, f"2conv {nb}x{r}x{dim} n={n}")
+    np.testing.assert_array_equal(flag.astype(bool), (np.abs(X) <= 1e-8).all(axis=1))
+
+
 @pytest.mark.parametrize("flags", [None, 1 | 8 | 32])   # default dispatch; 2-CTA kernel forced
 @pytest.mark.parametrize("kernel", TC_KERNELS)
 def test_vectors_outside_the_fp16_range_are_recomputed(kernel, flags, monkeypatch):
