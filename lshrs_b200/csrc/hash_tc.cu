@@ -608,14 +608,17 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
   __shared__ __align__(8) uint64_t bars[XS_MAX * 2 + BS * 2 + AS * 2 + 4];
   __shared__ uint32_t tmem_base_slot;
 
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024 B alignment
+  uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: 1024 B alignment
+  uint32_t bar0 = smem_u32(bars);
+  // opaque to the compiler from here on: otherwise it re-derives the shared-window addresses (S2R
+  // SR_CgaCtaId + LEA) in front of every mbarrier operation of the role loops instead of keeping them
+  asm volatile("" : "+r"(smem_base), "+r"(bar0));
   const uint32_t x_smem = smem_base;
   const uint32_t XS = (uint32_t)p.xs;
   constexpr uint32_t kPlanes = (kSplit == 2) ? 1u : 2u;              // FP16x3: q_hi | q_lo share one 64 B row
   const uint32_t B_HALF_BYTES = (uint32_t)p.ncols_pass * TKB * 4u;   // one plane of one stage: N x 64 B
   const uint32_t B_STAGE_BYTES = kPlanes * B_HALF_BYTES;
   const uint32_t b_smem = smem_base + XS * X_STAGE_BYTES;
-  const uint32_t bar0 = smem_u32(bars);
   auto x_full = [&](uint32_t i) { return bar0 + 8u * i; };
   auto x_empty = [&](uint32_t i) { return bar0 + 8u * (XS_MAX + i); };
   auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + i); };
@@ -884,7 +887,9 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   __shared__ __align__(8) uint64_t bars[XS_MAX * 2 + BS2 * 2 + AS * 2 + 4];
   __shared__ uint32_t tmem_base_slot;
 
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // same offset in both CTAs
+  uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // same offset in both CTAs
+  uint32_t bar0 = smem_u32(bars);
+  asm volatile("" : "+r"(smem_base), "+r"(bar0));   // keep both in registers (see hash_tc_kernel)
   const uint32_t x_smem = smem_base;
   const uint32_t XS = (uint32_t)p.xs;
   const uint32_t N = (uint32_t)p.ncols_pass;
@@ -893,7 +898,6 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
   const uint32_t B_HALF_BYTES = NH * TKB * 4u;              // one plane of one stage: N/2 rows x 64 B
   const uint32_t B_STAGE_BYTES = kPlanes * B_HALF_BYTES;
   const uint32_t b_smem = smem_base + XS * X_STAGE_BYTES;
-  const uint32_t bar0 = smem_u32(bars);
   auto x_full = [&](uint32_t i) { return bar0 + 8u * i; };
   auto x_empty = [&](uint32_t i) { return bar0 + 8u * (XS_MAX + i); };
   auto b_full = [&](uint32_t i) { return bar0 + 8u * (2 * XS_MAX + i); };
