@@ -336,9 +336,13 @@ def run_b200(args) -> None:
     compute = torch.cuda.Stream(device=dev)
     copy = torch.cuda.Stream(device=dev)
 
+    copied = [None, None]   # per output slot: the event of its last D2H (persists across steps)
+
     def one_step(kernel_events=None):
-        """Hash every chunk on `compute`, D2H each chunk's signatures on `copy` (double-buffered)."""
-        copied = [None, None]
+        """Hash every chunk on `compute`, D2H each chunk's signatures on `copy` (double-buffered).
+
+        Steps stream into each other: the D2H of a step's last chunks overlaps the next step's first
+        kernels; the timed region ends only after every copy has landed (drain())."""
         for ci, (r0, r1) in enumerate(chunks):
             slot = ci & 1
             if copied[slot] is not None:
@@ -359,10 +363,13 @@ def run_b200(args) -> None:
             ev = torch.cuda.Event()
             ev.record(copy)
             copied[slot] = ev
+
+    def drain():
         compute.wait_stream(copy)
 
     for _ in range(args.warmup):
         one_step()
+    drain()
     barrier()
     def timed_region():
         sampler = ClockSampler(local)
@@ -375,6 +382,7 @@ def run_b200(args) -> None:
         t_start.record(compute)
         for _ in range(args.steps):
             one_step(events)
+        drain()                      # every signature of every step is in host memory before the clock stops
         t_stop.record(compute)
         barrier()
         return (t_start, t_stop, events, _native.launch_count() - launches0,
