@@ -1413,7 +1413,13 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X
   int* scratch = nullptr;
   if (split == 2) {
     const size_t bytes = 16 + sizeof(int) * 4 * (size_t)p.mtiles;
-    LSHX_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, stream));
+    if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, stream) != cudaSuccess) {
+      // no stream-ordered allocator here (e.g. memory pools disabled): take the scale-free TF32+BF16
+      // arm for this launch, which needs no scratch
+      (void)cudaGetLastError();
+      scratch = nullptr;
+      return launch_hash_tc(s, plan, 1, d_X, n, d_out, d_zero_flag, stream);
+    }
     LSHX_CUDA(cudaMemsetAsync(scratch, 0, 16, stream));
     p.redo_count = scratch;
     p.redo_list = scratch + 4;
