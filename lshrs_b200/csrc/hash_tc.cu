@@ -334,9 +334,17 @@ __device__ __forceinline__ float row_scale_for(float m) {
   const int se = 254 + 1 - e;                       // biased exponent of the scale
   return (e >= 1 && e < 255) ? __uint_as_float((uint32_t)se << 23) : 0.f;
 }
+// NaN-propagating max(m, |x|): one instruction per element carries both per-row tests of the FP16x3
+// converters -- "some |x| > 1e-8 or NaN" (the zero-vector test) and "some |s_x * x| > 65504" (FP16 overflow).
+__device__ __forceinline__ float absmax_nan(float m, float x) {
+  float d;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(m), "f"(fabsf(x)));
+  return d;
+}
 // One half (16 floats) of a row -> 16 A-operand words: [0,8) = FP16 pairs of y_hi, [8,16) = pairs of y_lo.
+// `mx` accumulates max |x| over the row (NaN sticks).
 __device__ __forceinline__ void convert_half_f16(uint32_t row, int t, int h, float sc, uint32_t (&w)[16],
-                                                 bool& viol, bool& redo) {
+                                                 float& mx) {
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int chunk = h * 4 + c;
@@ -349,9 +357,8 @@ __device__ __forceinline__ void convert_half_f16(uint32_t row, int t, int h, flo
     float y[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      viol |= !(fabsf(f[e]) <= 1e-8f);
+      mx = absmax_nan(mx, f[e]);
       y[e] = f[e] * sc;
-      redo |= fabsf(y[e]) > 65504.f;               // would round to an FP16 infinity (or is one)
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -364,6 +371,11 @@ __device__ __forceinline__ void convert_half_f16(uint32_t row, int t, int h, flo
     }
   }
 }
+// the two row tests from the running max: viol = some |x| > 1e-8 (or NaN); overflow = the scaled row
+// leaves FP16's range (s_x is fixed before the first non-zero element is converted, so max|x| * s_x is
+// the largest scaled magnitude; NaN compares false: a NaN row hashes to zeros like numpy)
+__device__ __forceinline__ bool row_viol(float mx) { return !(mx <= 1e-8f); }
+__device__ __forceinline__ bool row_overflow(float mx, float sc) { return mx * sc > 65504.f; }
 
 // Accumulator row of this thread (TMEM lane) -> one sign bit per column: words[c >> 5] bit (c & 31) = D[c] > 0.
 __device__ __forceinline__ void read_sign_words(uint32_t tmem_row, uint32_t N, uint32_t (&words)[8]) {
@@ -779,6 +791,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       bool viol = false;  // some |x| > 1e-8 (or NaN): not a zero vector
       bool redo = false;  // FP16x3: this vector does not fit the scaled FP16 range
       float sc = 0.f;     // FP16x3: the vector's power-of-two scale (0 until a non-zero chunk is met)
+      float mx = 0.f;     // FP16x3: max |x| over the chunks this group converted (NaN sticks)
       for (int kc = 0; kc < p.kc; ++kc, ++seq) {
         const bool mine = (ngroups == 1u) || ((seq & 1u) == grp);
         mbar_wait(x_full(xr.idx), xr.phase);
@@ -798,7 +811,7 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           for (int h = 0; h < 2; ++h) {   // two halves of 16 floats keep the register count down
             if (kSplit == 2) {
               uint32_t wd[16];
-              convert_half_f16(row, t, h, sc, wd, viol, redo);
+              convert_half_f16(row, t, h, sc, wd, mx);
               tc_st16(a_dst + h * 16, wd);
             } else {
               uint32_t hi[16], lo[16];
@@ -810,8 +823,13 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
           tc_wait_st();
           // this group's last chunk of the tile: hand its share of the row flags to the epilogue (the
           // a_full arrive below releases the store; the epilogue reads after d_full)
-          if (kc + (int)ngroups >= p.kc)
+          if (kc + (int)ngroups >= p.kc) {
+            if (kSplit == 2) {
+              viol = row_viol(mx);
+              redo |= row_overflow(mx, sc);
+            }
             conv_flags[tcount & 7u][grp][t] = (uint8_t)((viol ? 1 : 0) | (redo ? 2 : 0));
+          }
           tc_fence_before();
         }
         __syncwarp();
@@ -1013,7 +1031,7 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       const int64_t mt = (p.npass == 1) ? w : w / p.npass;
       const int pass = (p.npass == 1) ? 0 : (int)(w % p.npass);
       bool viol = false, redo = false;
-      float sc = 0.f;
+      float sc = 0.f, mx = 0.f;
       for (int kc = 0; kc < p.kc; ++kc) {
         mbar_wait(x_full(xr.idx), xr.phase);
         const uint32_t row = x_smem + xr.idx * X_STAGE_BYTES + (uint32_t)t * 128u;
@@ -1031,7 +1049,7 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         for (int h = 0; h < 2; ++h) {
           if (kSplit == 2) {
             uint32_t wd[16];
-            convert_half_f16(row, t, h, sc, wd, viol, redo);
+            convert_half_f16(row, t, h, sc, wd, mx);
             tc_st16(a_dst + h * 16, wd);
           } else {
             uint32_t hi[16], lo[16];
@@ -1049,6 +1067,10 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
         }
         xr.advance(XS);
         ar.advance(AS);
+      }
+      if (kSplit == 2) {
+        viol = row_viol(mx);
+        redo |= row_overflow(mx, sc);
       }
       if (pass == 0) {
         const int64_t m = mt * (2 * TM) + rank * TM + t;
