@@ -443,6 +443,19 @@ def run_b200(args) -> None:
         pageable_value = 3 * e2e_rows / (time.perf_counter() - t_pg)
         same = same and bool(np.array_equal(op, oh.numpy()))
         del xp, op
+    # a float16 numpy array (what embedding stores often hold): raw rows over PCIe, exact cast on the device
+    # (lshx_hash_batch_typed); the signatures must equal those of the same values given as float32
+    f16_value = None
+    if not args.no_e2e:
+        x16 = xh.numpy().astype(np.float16)
+        want16 = hasher.hash_batch_packed(x16.astype(np.float32)).reshape(e2e_rows, SIG_BYTES)
+        got16 = hasher.hash_batch_packed(x16).reshape(e2e_rows, SIG_BYTES)
+        t_16 = time.perf_counter()
+        for _ in range(3):
+            hasher.hash_batch_packed(x16)
+        f16_value = 3 * e2e_rows / (time.perf_counter() - t_16)
+        same = same and bool(np.array_equal(got16, want16))
+        del x16, want16, got16
     # latency of the per-vector call LSHRS.ingest / query make (reference: one hash_vector per call)
     one = xh[:1].numpy().copy()
     for _ in range(20):
@@ -557,7 +570,7 @@ def run_b200(args) -> None:
                     "ms_per_step": e2e_ms / e2e_steps,
                     "api": "lshx_hash_batch(host pinned X -> host pinned signatures)",
                     "single_vector_call_us": single_us,
-                    "pageable_numpy_input_value": pageable_value},
+                    "pageable_numpy_input_value": pageable_value, "float16_numpy_input_value": f16_value},
             "kernel_only": {"value": kernel_only_value, "unit": UNIT,
                             "note": "signatures left in HBM (no D2H gather); value above includes the overlapped D2H "
                                     "of every signature into pinned host memory"},

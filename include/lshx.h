@@ -131,6 +131,25 @@ int lshx_hasher_signature_bytes(const lshx_hasher* h);
 int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_is_device,
                     uint8_t* out, int out_is_device, uint8_t* zero_flag, void* stream);
 
+/* Element type of a host batch handed to lshx_hash_batch_typed. */
+typedef enum lshx_dtype {
+  LSHX_DTYPE_F32 = 0,
+  LSHX_DTYPE_F16 = 1, /* IEEE binary16 (numpy float16)                                  */
+  LSHX_DTYPE_U8 = 2,  /* e.g. SIFT descriptors                                           */
+  LSHX_DTYPE_I8 = 3
+} lshx_dtype;
+
+/*
+ * lshx_hash_batch for a HOST batch that is not float32.  The reference casts on
+ * the host first -- np.asarray(vectors, dtype=np.float32), lsh.py:162 / 243 --
+ * which for these types is exact; here the raw rows cross PCIe (half / a quarter
+ * of the float32 bytes) and are cast on the device, so the signatures are the
+ * same bytes.  X is n x dim elements of `dtype`, row-major, contiguous; out and
+ * zero_flag as in lshx_hash_batch with host pointers.  Synchronous.
+ */
+int lshx_hash_batch_typed(lshx_hasher* h, const void* X, int dtype /* lshx_dtype */, int64_t n,
+                          uint8_t* out, uint8_t* zero_flag);
+
 /*
  * Lower-case hex of the band bytes, the variable part of
  * RedisStorage.bucket_key (reference lshrs/storage/redis.py:225:

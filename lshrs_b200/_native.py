@@ -34,6 +34,7 @@ __all__ = [
 KERNEL_AUTO, KERNEL_FFMA, KERNEL_TCGEN05 = 0, 1, 2
 KERNEL_TCGEN05_3XTF32 = 4
 KERNEL_TCGEN05_TF32BF16 = 5
+DTYPE_F32, DTYPE_F16, DTYPE_U8, DTYPE_I8 = 0, 1, 2, 3
 ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM, ERR_ZERO_VECTOR = -1, -2, -3, -4, -5
 
 # every symbol include/lshx.h declares (tests/test_cabi.py checks them against the header)
@@ -48,6 +49,7 @@ EXPORTED_SYMBOLS = (
     "lshx_hasher_last_kernel",
     "lshx_hasher_signature_bytes",
     "lshx_hash_batch",
+    "lshx_hash_batch_typed",
     "lshx_signatures_to_hex",
     "lshx_hasher_destroy",
     "lshx_rerank_create",
@@ -105,6 +107,8 @@ def _declare(cdll: ctypes.CDLL) -> None:
     cdll.lshx_hasher_signature_bytes.argtypes = [vp]
     cdll.lshx_hash_batch.restype = c_int
     cdll.lshx_hash_batch.argtypes = [vp, vp, c_int64, c_int, vp, c_int, vp, vp]
+    cdll.lshx_hash_batch_typed.restype = c_int
+    cdll.lshx_hash_batch_typed.argtypes = [vp, vp, c_int, c_int64, vp, vp]
     cdll.lshx_signatures_to_hex.restype = c_int
     cdll.lshx_signatures_to_hex.argtypes = [vp, c_int64, c_int, vp]
     cdll.lshx_hasher_destroy.restype = c_int

@@ -208,7 +208,10 @@ class LSHRS:
             return
         if vectors is None:
             vectors = self._require_vector_fetch_fn()(indices)
-        arr = np.asarray(vectors, dtype=np.float32)
+        if isinstance(vectors, np.ndarray) and vectors.dtype in self._hasher._TYPED and vectors.ndim == 2:
+            arr = vectors   # float16 / int8 / uint8 batches are cast on the device (exact), not here
+        else:
+            arr = np.asarray(vectors, dtype=np.float32)
         if arr.ndim != 2 or arr.shape[1] != self._dim:
             raise ValueError(f"Vectors must have shape (n, {self._dim}); received {arr.shape}")
         if arr.shape[0] != len(indices):

@@ -10,6 +10,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "lshx_common.cuh"
 
 namespace lshx {
@@ -99,6 +101,7 @@ struct lshx_hasher {
   cudaStream_t streams[2] = {nullptr, nullptr};
   cudaEvent_t ev_in = nullptr;
   DevBuf x_stage[2], out_stage[2], flag_stage[2];
+  DevBuf raw_stage[2];         // typed host batches (fp16 / int8 / uint8) before the on-device cast
   // small-batch path (per-vector calls): pinned, device-mapped staging for up to small_rows rows
   int small_rows = 0;
   float* pin_x = nullptr;      // host, pinned
@@ -335,12 +338,70 @@ static bool is_pageable_host(const void* p) {
 static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_out,
                        uint8_t* d_flag, cudaStream_t st);
 
-// Large PAGEABLE host batch (an ordinary numpy array): cudaMemcpyAsync from pageable memory is staged by
+// ---- typed host batches: the cast to float32 that LSHHasher.hash_batch does with np.asarray(vectors,
+// float32) (reference lshrs/hash/lsh.py:162) happens on the device, so fp16 embeddings cross PCIe at half
+// and uint8 / int8 descriptors at a quarter of the float32 bytes.  Every one of these conversions is exact.
+static __device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
+static __device__ __forceinline__ float to_f32(uint8_t v) { return (float)v; }
+static __device__ __forceinline__ float to_f32(int8_t v) { return (float)v; }
+
+template <typename T>
+__global__ void expand_to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t count) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += stride) {
+    if (i + 4 <= count) {   // both staging buffers are 256-byte aligned and i % 4 == 0
+      T v[4];
+      if (sizeof(T) == 1) *reinterpret_cast<uint32_t*>(v) = *reinterpret_cast<const uint32_t*>(in + i);
+      else *reinterpret_cast<uint2*>(v) = *reinterpret_cast<const uint2*>(in + i);
+      *reinterpret_cast<float4*>(out + i) = make_float4(to_f32(v[0]), to_f32(v[1]), to_f32(v[2]), to_f32(v[3]));
+    } else {
+      for (int64_t j = i; j < count; ++j) out[j] = to_f32(in[j]);
+    }
+  }
+}
+
+static size_t dtype_size(int dtype) {
+  switch (dtype) {
+    case LSHX_DTYPE_F32: return 4;
+    case LSHX_DTYPE_F16: return 2;
+    case LSHX_DTYPE_U8:
+    case LSHX_DTYPE_I8: return 1;
+    default: return 0;
+  }
+}
+
+static int expand_chunk(int dtype, const void* d_raw, float* d_x, int64_t count, cudaStream_t st) {
+  const int threads = 256;
+  int64_t want = (count / 4 + threads - 1) / threads;
+  const int blocks = (int)(want < 1 ? 1 : (want > 148 * 16 ? 148 * 16 : want));
+  switch (dtype) {
+    case LSHX_DTYPE_F16:
+      expand_to_f32_kernel<<<blocks, threads, 0, st>>>(static_cast<const __half*>(d_raw), d_x, count);
+      break;
+    case LSHX_DTYPE_U8:
+      expand_to_f32_kernel<<<blocks, threads, 0, st>>>(static_cast<const uint8_t*>(d_raw), d_x, count);
+      break;
+    case LSHX_DTYPE_I8:
+      expand_to_f32_kernel<<<blocks, threads, 0, st>>>(static_cast<const int8_t*>(d_raw), d_x, count);
+      break;
+    default:
+      set_error("unsupported dtype %d", dtype);
+      return LSHX_ERR_INVALID_ARG;
+  }
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
+
+// Large host batch that is not pinned float32: an ordinary (pageable) numpy array, and / or a typed one.
+// cudaMemcpyAsync from pageable memory is staged by
 // the driver on one thread (~11 GB/s measured).  Instead the rows go through two pinned bounce buffers
 // filled by parallel_memcpy while the previous chunk is in flight; signatures and flags come back through
 // pinned bounce buffers too and are copied out when their slot is reused.
-static int hash_pageable(lshx_hasher* h, const float* X, int64_t n, uint8_t* out, uint8_t* zero_flag) {
+static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, uint8_t* out, uint8_t* zero_flag) {
   const HashShape& s = h->s;
+  const char* X = static_cast<const char*>(Xv);
+  const size_t in_row = (size_t)s.dim * dtype_size(dtype);      // bytes of one row as the caller holds it
   const size_t row_bytes = (size_t)s.dim * sizeof(float);
   const size_t out_row = (size_t)s.sig_bytes + 1;  // signature bytes + 1 flag byte per row
   if (h->bounce_rows == 0) {
@@ -369,6 +430,7 @@ static int hash_pageable(lshx_hasher* h, const float* X, int64_t n, uint8_t* out
     if ((rc = h->x_stage[i].reserve((size_t)chunk * row_bytes)) != LSHX_OK) return rc;
     if ((rc = h->out_stage[i].reserve((size_t)chunk * s.sig_bytes)) != LSHX_OK) return rc;
     if ((rc = h->flag_stage[i].reserve((size_t)chunk)) != LSHX_OK) return rc;
+    if (dtype != LSHX_DTYPE_F32 && (rc = h->raw_stage[i].reserve((size_t)chunk * in_row)) != LSHX_OK) return rc;
   }
   struct Pending { int64_t r0 = 0, rows = 0; } pending[2];
   auto drain = [&](int slot) -> int {  // copy a finished slot's results to the caller's memory
@@ -385,10 +447,17 @@ static int hash_pageable(lshx_hasher* h, const float* X, int64_t n, uint8_t* out
     const int64_t rows = (n - r0 < chunk) ? (n - r0) : chunk;
     int rc = drain(slot);  // also guarantees the slot's H2D source is no longer being read
     if (rc != LSHX_OK) return rc;
-    parallel_memcpy(h->bounce_x[slot], X + r0 * s.dim, (size_t)rows * row_bytes);
+    parallel_memcpy(h->bounce_x[slot], X + r0 * in_row, (size_t)rows * in_row);
     cudaStream_t st = h->streams[slot];
-    LSHX_CUDA(cudaMemcpyAsync(h->x_stage[slot].p, h->bounce_x[slot], (size_t)rows * row_bytes,
-                              cudaMemcpyHostToDevice, st));
+    if (dtype == LSHX_DTYPE_F32) {
+      LSHX_CUDA(cudaMemcpyAsync(h->x_stage[slot].p, h->bounce_x[slot], (size_t)rows * row_bytes,
+                                cudaMemcpyHostToDevice, st));
+    } else {
+      LSHX_CUDA(cudaMemcpyAsync(h->raw_stage[slot].p, h->bounce_x[slot], (size_t)rows * in_row,
+                                cudaMemcpyHostToDevice, st));
+      rc = expand_chunk(dtype, h->raw_stage[slot].p, static_cast<float*>(h->x_stage[slot].p), rows * s.dim, st);
+      if (rc != LSHX_OK) return rc;
+    }
     uint8_t* d_o = static_cast<uint8_t*>(h->out_stage[slot].p);
     uint8_t* d_f = zero_flag ? static_cast<uint8_t*>(h->flag_stage[slot].p) : nullptr;
     rc = launch_hash(h, static_cast<const float*>(h->x_stage[slot].p), rows, d_o, d_f, st);
@@ -468,7 +537,7 @@ extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_
   // ---- a large pageable host batch: pinned bounce buffers filled by several CPU threads -----------
   if (!x_is_device && !out_is_device && n >= 4096 && is_pageable_host(X)) {
     LSHX_CUDA(cudaStreamSynchronize(user));
-    return hash_pageable(h, X, n, out, zero_flag);
+    return hash_pageable(h, X, LSHX_DTYPE_F32, n, out, zero_flag);
   }
 
   // ---- at least one side on the host: chunked, two streams, synchronous -----------
@@ -522,6 +591,21 @@ extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_
   return LSHX_OK;
 }
 
+extern "C" int lshx_hash_batch_typed(lshx_hasher* h, const void* X, int dtype, int64_t n, uint8_t* out,
+                                     uint8_t* zero_flag) {
+  LSHX_REQUIRE(h != nullptr, "null handle");
+  LSHX_REQUIRE(n >= 0, "n must be >= 0");
+  LSHX_REQUIRE(dtype_size(dtype) != 0, "unsupported dtype %d", dtype);
+  if (n == 0) return LSHX_OK;
+  LSHX_REQUIRE(X != nullptr && out != nullptr, "null buffer");
+  if (dtype == LSHX_DTYPE_F32)
+    return lshx_hash_batch(h, static_cast<const float*>(X), n, 0, out, 0, zero_flag, nullptr);
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  LSHX_CUDA(cudaStreamSynchronize(nullptr));
+  return hash_pageable(h, X, dtype, n, out, zero_flag);
+}
+
 extern "C" int lshx_signatures_to_hex(const uint8_t* sig, int64_t n, int sig_bytes, char* hex_out) {
   LSHX_REQUIRE(sig != nullptr && hex_out != nullptr && n >= 0 && sig_bytes > 0, "bad argument");
   static const char digits[] = "0123456789abcdef";
@@ -542,6 +626,7 @@ extern "C" int lshx_hasher_destroy(lshx_hasher* h) {
     if (h->d_Rp) cudaFree(h->d_Rp);
     for (int i = 0; i < 2; ++i) {
       h->x_stage[i].release();
+      h->raw_stage[i].release();
       h->out_stage[i].release();
       h->flag_stage[i].release();
       if (h->streams[i]) cudaStreamDestroy(h->streams[i]);

@@ -113,7 +113,7 @@ class ShardedHasher:
 
     def hash_batch_packed(self, vectors: np.ndarray) -> np.ndarray:
         arr = self.hashers[0]._validate_batch(vectors)
-        arr = np.ascontiguousarray(arr)
+        arr = np.ascontiguousarray(arr, dtype=np.float32)   # (hash_into below takes float32 rows)
         n = arr.shape[0]
         out = np.empty((n, self.signature_bytes), dtype=np.uint8)
         bounds = shard_bounds(n, len(self.hashers))

@@ -201,6 +201,32 @@ def test_vectors_outside_the_fp16_range_are_recomputed(kernel, flags, monkeypatc
     np.testing.assert_array_equal(flag.astype(bool), (np.abs(X) <= 1e-8).all(axis=1))
 
 
+@pytest.mark.parametrize("dtype", [np.float16, np.uint8, np.int8])
+@pytest.mark.parametrize("n", [4096, 50_000])
+def test_typed_host_batches_are_cast_on_the_device(dtype, n):
+    """float16 / uint8 / int8 arrays go through lshx_hash_batch_typed (raw rows over PCIe, exact cast on the
+    device): the same bytes as casting on the host first, which is what the reference does (lsh.py:162)."""
+    rng = np.random.default_rng(7)
+    dim = 128
+    if dtype is np.float16:
+        X = rng.standard_normal((n, dim)).astype(np.float16)
+    elif dtype is np.uint8:
+        X = np.minimum(255, np.floor(np.abs(rng.standard_normal((n, dim))) * 40)).astype(np.uint8)  # SIFT-like
+    else:
+        X = rng.integers(-128, 128, size=(n, dim), dtype=np.int8)
+    X[17] = 0
+    h = _hasher(16, 4, dim, 42, "auto")
+    got, flag = h.hash_batch_packed(X, return_zero_flag=True)
+    want, want_flag = h.hash_batch_packed(X.astype(np.float32), return_zero_flag=True)
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(flag, want_flag)
+    assert flag[17] == 1 and flag.sum() == (X.astype(np.float32) == 0).all(axis=1).sum()
+    _assert_parity(got, X.astype(np.float32), h.projections, f"typed {np.dtype(dtype).name}")
+    # the object API and a non-contiguous view take the same route
+    assert h.hash_batch(X[:5000:1])[3].as_tuple() == tuple(bytes(b) for b in want[3])
+    np.testing.assert_array_equal(h.hash_batch_packed(X[::2]), want[::2])
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_zero_flag_is_prepare_vector_test(kernel):
     h = _hasher(4, 4, 32, 42, kernel)
