@@ -415,7 +415,8 @@ static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, u
     if (rows < 128) rows = 128;
     for (int i = 0; i < 2; ++i) {
       if (cudaHostAlloc(&h->bounce_x[i], rows * row_bytes, cudaHostAllocDefault) != cudaSuccess ||
-          cudaHostAlloc(reinterpret_cast<void**>(&h->bounce_out[i]), rows * out_row, cudaHostAllocDefault) != cudaSuccess ||
+          // (4x the rows: a chunk of 1-byte elements holds four times as many rows in the same bounce_x bytes)
+          cudaHostAlloc(reinterpret_cast<void**>(&h->bounce_out[i]), 4 * rows * out_row, cudaHostAllocDefault) != cudaSuccess ||
           cudaEventCreateWithFlags(&h->bounce_ev[i], cudaEventDisableTiming) != cudaSuccess) {
         (void)cudaGetLastError();
         set_error("cannot allocate pinned bounce buffers");
@@ -424,7 +425,9 @@ static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, u
     }
     h->bounce_rows = rows;
   }
-  const int64_t chunk = (int64_t)h->bounce_rows;
+  // rows per chunk: what fills a bounce buffer in the caller's element type (float32: bounce_rows;
+  // float16: twice, 1-byte types: four times as many -- the per-chunk fixed costs are per byte moved)
+  const int64_t chunk = (int64_t)(h->bounce_rows * row_bytes / in_row) / 128 * 128;
   for (int i = 0; i < 2; ++i) {
     int rc;
     if ((rc = h->x_stage[i].reserve((size_t)chunk * row_bytes)) != LSHX_OK) return rc;
