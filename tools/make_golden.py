@@ -102,6 +102,14 @@ def main() -> None:
          lambda: np.stack([np.zeros(32, np.float32), np.full(32, np.nan, np.float32),
                            np.full(32, 1e-30, np.float32), -np.ones(32, np.float32),
                            np.random.default_rng(15).standard_normal(32).astype(np.float32) * 1e20])),
+        # typed inputs: the reference casts them with np.asarray(vectors, float32) (lsh.py:162); 4096 rows so
+        # that lshrs_b200 takes lshx_hash_batch_typed (raw rows over PCIe, cast on the device)
+        ("typed_u8_4096x32_4x4", 4, 4, 32, 42,
+         lambda: sift_like(np.random.default_rng(21), 4096, 32).astype(np.uint8)),
+        ("typed_f16_4096x32_4x4", 4, 4, 32, 42,
+         lambda: np.random.default_rng(22).standard_normal((4096, 32)).astype(np.float16)),
+        ("typed_i8_4096x32_4x4", 4, 4, 32, 42,
+         lambda: np.random.default_rng(23).integers(-128, 128, size=(4096, 32), dtype=np.int8)),
     ]
     for name, nb, r, dim, seed, build in hash_cases:
         h = LSHHasher(num_bands=nb, rows_per_band=r, dim=dim, seed=seed)
