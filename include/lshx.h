@@ -207,8 +207,11 @@ int lshx_rerank_create(int device, int dim, lshx_reranker** out);
  *                    (queries against a corpus resident in HBM)
  * Scores: fp32 dot(c, q) / (||c|| ||q||), within 1e-5 of the reference's
  * normalise-then-dot order (BASELINE.json north_star tolerance).
- * Limits: a query may have any number of candidates when its result count is
- * <= 8192; above that the candidate count must be <= 16384 (one in-SM sort).
+ * Any number of candidates and results per query (< 2^32): up to 16384 candidates are
+ * sorted in shared memory, more are scored in chunks with a running top-8192, and a
+ * launch that needs more than 8192 results from more than 16384 candidates sorts the
+ * keys in a handle-owned global scratch (slower; the reference's argpartition + argsort
+ * has no size limit either, similarity.py:174-179).
  */
 int lshx_rerank_topk(lshx_reranker* r, const float* Q, int64_t nq,
                      const float* vectors, int64_t n_vectors,

@@ -31,6 +31,7 @@ __all__ = [
     "EXPORTED_SYMBOLS",
 ]
 
+ABI_VERSION = 1   # LSHX_ABI_VERSION of include/lshx.h this binding was written against
 KERNEL_AUTO, KERNEL_FFMA, KERNEL_TCGEN05 = 0, 1, 2
 KERNEL_TCGEN05_3XTF32 = 4
 KERNEL_TCGEN05_TF32BF16 = 5
@@ -151,8 +152,9 @@ def lib() -> ctypes.CDLL:
         except OSError as exc:
             raise LshxUnavailable(ERR_NO_DEVICE, f"cannot load {path}: {exc}; lshrs_b200 has no CPU fallback") from exc
         _declare(cdll)
-        if cdll.lshx_abi_version() != 1:
-            raise LshxUnavailable(ERR_INVALID_ARG, f"{path} has ABI version {cdll.lshx_abi_version()}, expected 1")
+        if cdll.lshx_abi_version() != ABI_VERSION:
+            raise LshxUnavailable(ERR_INVALID_ARG,
+                                  f"{path} has ABI version {cdll.lshx_abi_version()}, expected {ABI_VERSION}")
         _lib = cdll
         return cdll
 

@@ -29,7 +29,8 @@ import numpy as np
 
 from lshrs_b200._config.config import HashSignatures
 from lshrs_b200.hash.lsh import LSHHasher
-from lshrs_b200.storage.memory import BucketOperation, BucketStorage
+from lshrs_b200.storage.memory import BucketOperation, BucketStorage, InMemoryStorage
+from lshrs_b200.utils.br import get_optimal_config
 from lshrs_b200.utils.similarity import _get_reranker
 
 logger = logging.getLogger(__name__)
@@ -37,28 +38,20 @@ logger = logging.getLogger(__name__)
 VectorFetchFn = Callable[[Sequence[int]], np.ndarray]
 CandidateScores = list[tuple[int, float]]
 
-# (num_bands, rows_per_band) the reference's get_optimal_config(num_perm, 0.5) selects
-# (reference lshrs/utils/br.py:325-395, recorded by tools/make_golden.py in
-# tests/golden/manifest.json).  Other thresholds need the reference's br module.
-_AUTO_CONFIG_T05 = {64: (16, 4), 128: (8, 16), 256: (16, 16), 512: (16, 32), 1024: (128, 8)}
-
 _ZERO_VECTOR_MSG = "Cannot index zero vector - norm undefined. Check embeddings for corruption."
+
+try:  # Redis bucket storage is the reference's, unchanged (out of scope here).  The name
+    # lives at module level because the reference's tests patch it there
+    # (reference tests/test_redis_pooling.py:34: patch("lshrs.core.main.RedisStorage")).
+    from lshrs.storage.redis import RedisStorage  # type: ignore
+except ImportError:  # the reference package is not installed next to us: storage= must be given
+    RedisStorage = None
 
 
 def _auto_config(num_perm: int, threshold: float) -> tuple[int, int]:
-    try:  # the reference's own chooser when it is installed next to us
-        from lshrs.utils.br import get_optimal_config  # type: ignore
-
-        b, r = get_optimal_config(num_perm, threshold)
-        return int(b), int(r)
-    except ImportError:
-        pass
-    if abs(threshold - 0.5) < 1e-12 and num_perm in _AUTO_CONFIG_T05:
-        return _AUTO_CONFIG_T05[num_perm]
-    raise ValueError(
-        f"num_bands and rows_per_band must be given for num_perm={num_perm}, "
-        f"similarity_threshold={threshold} (band/row auto-configuration lives in the reference's lshrs.utils.br)"
-    )
+    """``(num_bands, rows_per_band)`` when the caller gives only ``num_perm`` (reference main.py:253-255)."""
+    b, r = get_optimal_config(num_perm, threshold)
+    return int(b), int(r)
 
 
 class LSHRS:
@@ -120,14 +113,16 @@ class LSHRS:
 
     @staticmethod
     def _make_redis_storage(**kwargs: Any) -> BucketStorage:
-        try:
-            from lshrs.storage.redis import RedisStorage  # type: ignore  # the reference's, unchanged
-        except ImportError as exc:
-            raise RuntimeError(
-                "no storage given: pass storage=<RedisStorage or compatible> (Redis bucket storage stays in the "
-                "reference package lshrs.storage.redis, which is not importable here)"
-            ) from exc
-        return RedisStorage(**kwargs)
+        cls = RedisStorage      # module global: patched by the reference's tests, None when not importable at load
+        if cls is None:
+            try:
+                from lshrs.storage.redis import RedisStorage as cls  # type: ignore
+            except ImportError as exc:
+                raise RuntimeError(
+                    "no storage given: pass storage=<RedisStorage or compatible> (Redis bucket storage stays in the "
+                    "reference package lshrs.storage.redis, which is not importable here)"
+                ) from exc
+        return cls(**kwargs)
 
     # ------------------------------------------------------------------ lifecycle
     def close(self) -> None:
@@ -397,7 +392,9 @@ class LSHRS:
         src = Path(path)
         if not src.exists():
             raise FileNotFoundError(f"Directory not found: {src}")
-        meta = json.loads((src / "metadata.json").read_text())
+        meta = json.loads((src / "metadata.json").read_text())   # FileNotFoundError when absent, like the reference
+        if not (src / "projections.npz").exists():   # before any storage / device handle is created
+            raise FileNotFoundError(f"No such file or directory: '{src / 'projections.npz'}'")
         cfg = meta["config"]
         red = dict(meta["redis_config"])
         if redis_config:
@@ -416,7 +413,8 @@ class LSHRS:
         return {
             "config": dict(self._config), "redis_config": dict(self._redis_config),
             "projections": [np.asarray(m, dtype=np.float32) for m in self._hasher.projections],
-            "storage": self._storage if not type(self._storage).__module__.startswith("lshrs.storage") else None,
+            # the reference does not persist its storage (a Redis connection); the in-memory double travels
+            "storage": self._storage if isinstance(self._storage, InMemoryStorage) else None,
         }
 
     def __setstate__(self, state: dict[str, Any]) -> None:

@@ -659,6 +659,7 @@ struct lshx_reranker {
   cudaStream_t stream = nullptr, stream2 = nullptr;  // host-buffer calls alternate query chunks on the two
   cudaEvent_t ev = nullptr;
   DevBuf q, vecs, offs, ids, pos, score, count, zero, all;
+  DevBuf big;   // global sort scratch of oversized selections (rerank_scratch_bytes)
   std::mutex mu;
 };
 
@@ -689,7 +690,7 @@ extern "C" int lshx_rerank_destroy(lshx_reranker* r) {
   {
     DeviceGuard g(r->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&r->q, &r->vecs, &r->offs, &r->ids, &r->pos, &r->score, &r->count, &r->zero, &r->all})
+    for (DevBuf* b : {&r->q, &r->vecs, &r->offs, &r->ids, &r->pos, &r->score, &r->count, &r->zero, &r->all, &r->big})
       b->release();
     if (r->stream) cudaStreamDestroy(r->stream);
     if (r->stream2) cudaStreamDestroy(r->stream2);
@@ -739,6 +740,14 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
     a.out_pos = out_pos; a.out_score = out_score; a.out_count = out_count; a.out_zero = out_zero;
     a.all_scores = out_all;
     a.max_cand = max_candidates;
+    if (const size_t need = rerank_scratch_bytes(a, nullptr)) {
+      // the scratch may still be in use by an earlier launch on another stream: drain before growing it
+      if (need > r->big.cap) LSHX_CUDA(cudaDeviceSynchronize());
+      int rc = r->big.reserve(need);
+      if (rc != LSHX_OK) return rc;
+      a.big_keys = static_cast<uint64_t*>(r->big.p);
+      a.big_bytes = r->big.cap;
+    }
     return launch_rerank(a, user);  // NULL = the default stream
   }
 
@@ -773,6 +782,12 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
     if ((rc = r->all.reserve((size_t)(end > 0 ? end : 1) * sizeof(float))) != LSHX_OK) return rc;
   }
   if ((rc = r->zero.reserve((size_t)nq * sizeof(int32_t))) != LSHX_OK) return rc;
+  const size_t big_need = rerank_scratch_bytes(a, nullptr);
+  if (big_need) {
+    if ((rc = r->big.reserve(big_need)) != LSHX_OK) return rc;
+    a.big_keys = static_cast<uint64_t*>(r->big.p);
+    a.big_bytes = r->big.cap;
+  }
 
   float* d_q = static_cast<float*>(r->q.p);
   int64_t* d_offs = static_cast<int64_t*>(r->offs.p);
@@ -793,7 +808,8 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
   LSHX_CUDA(cudaStreamWaitEvent(streams[1], r->ev, 0));
 
   // query chunks alternate between two streams so the H2D of one overlaps the kernel of the other
-  const int64_t qchunk = (nq >= 1024) ? (nq + 7) / 8 : nq;
+  // (an oversized selection shares one sort scratch: a single chunk on one stream)
+  const int64_t qchunk = (nq >= 1024 && !big_need) ? (nq + 7) / 8 : nq;
   int slot = 0;
   for (int64_t c0 = 0; c0 < nq; c0 += qchunk, slot ^= 1) {
     const int64_t c1 = (c0 + qchunk < nq) ? c0 + qchunk : nq;

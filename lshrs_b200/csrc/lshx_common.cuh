@@ -96,7 +96,14 @@ struct RerankArgs {
   float* all_scores;  // optional: every candidate's score (cosine_similarity)
   int64_t max_cand;   // largest per-query candidate count (sizes the sort buffer)
   bool select;        // false: scores only
+  // oversized selections (see rerank_scratch_bytes): global sort scratch owned by the caller
+  uint64_t* big_keys;   // null unless the launch needs the global-memory sort
+  size_t big_bytes;
+  int64_t big_stride;   // set by launch_rerank
 };
+// Bytes of device scratch launch_rerank needs for `a` (0 for all but oversized selections: a query with more
+// than 16384 candidates AND more than 8192 results); queries_per_pass = queries sorted per scratch fill.
+size_t rerank_scratch_bytes(const RerankArgs& a, int64_t* queries_per_pass);
 int launch_rerank(const RerankArgs& a, cudaStream_t stream);
 int launch_l2_normalize(const float* d_X, int64_t n, int dim, float* d_out, int32_t* d_zero,
                         cudaStream_t stream);

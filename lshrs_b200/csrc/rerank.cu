@@ -184,6 +184,9 @@ rerank_kernel(RerankArgs a, unsigned cap, int q_floats) {
           if (!oka) sa = __int_as_float(0x7fc00000);
           if (ca == 0.f || !oka) atomicAdd(&zero_cnt, 1);
           if (a.all_scores) a.all_scores[base + c0 + j] = sa;
+          if (a.big_keys)
+            a.big_keys[qi * a.big_stride + c0 + j] =
+                ((uint64_t)order_key(sa) << 32) | (uint64_t)(0xffffffffu - (uint32_t)(c0 + j));
           if (a.select)
             keys[dst0 + j] = ((uint64_t)order_key(sa) << 32) | (uint64_t)(0xffffffffu - (uint32_t)(c0 + j));
           if (has_b) {
@@ -191,6 +194,9 @@ rerank_kernel(RerankArgs a, unsigned cap, int q_floats) {
             if (!okb) sb = __int_as_float(0x7fc00000);
             if (cb == 0.f || !okb) atomicAdd(&zero_cnt, 1);
             if (a.all_scores) a.all_scores[base + c0 + jb] = sb;
+            if (a.big_keys)
+              a.big_keys[qi * a.big_stride + c0 + jb] =
+                  ((uint64_t)order_key(sb) << 32) | (uint64_t)(0xffffffffu - (uint32_t)(c0 + jb));
             if (a.select)
               keys[dst0 + jb] = ((uint64_t)order_key(sb) << 32) | (uint64_t)(0xffffffffu - (uint32_t)(c0 + jb));
           }
@@ -214,9 +220,92 @@ rerank_kernel(RerankArgs a, unsigned cap, int q_floats) {
       }
       if (tid == 0) a.out_count[qi] = (int32_t)limit;
     }
+    if (a.big_keys)   // pad the query's slot range up to the power-of-two stride the global sort works on
+      for (int64_t i = n + tid; i < a.big_stride; i += RR_THREADS) a.big_keys[qi * a.big_stride + i] = 0ull;
     if (tid == 0 && a.out_zero) a.out_zero[qi] = zero_cnt + ((qq == 0.f) ? 1 : 0);
     __syncthreads();
   }
+}
+
+// Oversized selections (more than RR_MAX_CAP candidates for one query AND more than RR_MAX_CAP / 2 results,
+// e.g. get_above_p(p = 0.95) on a 16 x 4 index where every bucket holds 1/16 of the corpus): the scoring
+// pass above leaves every candidate's 64-bit key in global memory (stride = next power of two) and one
+// 1024-thread CTA per query sorts them there -- bitonic network on L2-resident keys, strides below the
+// shared-memory tile finished in shared memory -- then writes the first `limit`.  Rare path: the reference
+// handles any candidate count (np.argpartition + argsort, similarity.py:174-179), so this must too.
+constexpr int BS_THREADS = 1024;
+constexpr unsigned BS_TILE = 4096;   // keys sorted / merged per shared-memory tile (32 KB)
+
+__global__ void __launch_bounds__(BS_THREADS)
+rerank_bigsort_kernel(RerankArgs a) {
+  __shared__ uint64_t tile[BS_TILE];
+  const int tid = threadIdx.x;
+  const int64_t qi = blockIdx.x;
+  uint64_t* keys = a.big_keys + qi * a.big_stride;
+  const uint64_t cap = (uint64_t)a.big_stride;
+  const int64_t n = a.offs[qi + 1] - a.offs[qi];
+
+  // phase 1: every BS_TILE-key tile fully sorted in shared memory, direction alternating like the network's
+  for (uint64_t t0 = 0; t0 < cap; t0 += BS_TILE) {
+    for (unsigned i = tid; i < BS_TILE; i += BS_THREADS) tile[i] = keys[t0 + i];
+    __syncthreads();
+    for (unsigned size = 2; size <= BS_TILE; size <<= 1) {
+      for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+        for (unsigned t = tid; t < (BS_TILE >> 1); t += BS_THREADS) {
+          const unsigned i = 2 * t - (t & (stride - 1)), j = i + stride;
+          const bool desc = (((t0 + i) & size) == 0);
+          const uint64_t x = tile[i], y = tile[j];
+          if ((x < y) == desc) { tile[i] = y; tile[j] = x; }
+        }
+        __syncthreads();
+      }
+    }
+    for (unsigned i = tid; i < BS_TILE; i += BS_THREADS) keys[t0 + i] = tile[i];
+    __syncthreads();
+  }
+  // phase 2: merge levels above the tile size; strides >= BS_TILE in global memory, the rest per tile
+  for (uint64_t size = 2ull * BS_TILE; size <= cap; size <<= 1) {
+    for (uint64_t stride = size >> 1; stride >= BS_TILE; stride >>= 1) {
+      for (uint64_t t = tid; t < (cap >> 1); t += BS_THREADS) {
+        const uint64_t i = 2 * t - (t & (stride - 1)), j = i + stride;
+        const bool desc = ((i & size) == 0);
+        const uint64_t x = keys[i], y = keys[j];
+        if ((x < y) == desc) { keys[i] = y; keys[j] = x; }
+      }
+      __syncthreads();
+    }
+    for (uint64_t t0 = 0; t0 < cap; t0 += BS_TILE) {
+      for (unsigned i = tid; i < BS_TILE; i += BS_THREADS) tile[i] = keys[t0 + i];
+      __syncthreads();
+      const bool desc = ((t0 & size) == 0);
+      for (unsigned stride = BS_TILE >> 1; stride > 0; stride >>= 1) {
+        for (unsigned t = tid; t < (BS_TILE >> 1); t += BS_THREADS) {
+          const unsigned i = 2 * t - (t & (stride - 1)), j = i + stride;
+          const uint64_t x = tile[i], y = tile[j];
+          if ((x < y) == desc) { tile[i] = y; tile[j] = x; }
+        }
+        __syncthreads();
+      }
+      for (unsigned i = tid; i < BS_TILE; i += BS_THREADS) keys[t0 + i] = tile[i];
+      __syncthreads();
+    }
+  }
+  int64_t limit;
+  if (a.p > 0.0) {
+    int64_t lp = (int64_t)ceil((double)n * a.p);
+    if (lp < 1) lp = 1;
+    limit = (a.k > 0 && a.k < lp) ? a.k : lp;
+  } else {
+    limit = a.k;
+  }
+  if (limit > n) limit = n;
+  if (limit > a.out_stride) limit = a.out_stride;
+  for (int64_t i = tid; i < limit; i += BS_THREADS) {
+    const uint64_t kv = keys[i];
+    a.out_pos[qi * (int64_t)a.out_stride + i] = (int32_t)(0xffffffffu - (uint32_t)(kv & 0xffffffffu));
+    a.out_score[qi * (int64_t)a.out_stride + i] = key_score((uint32_t)(kv >> 32));
+  }
+  if (tid == 0) a.out_count[qi] = (int32_t)limit;
 }
 
 // out[i] = x[i] / ||x[i]||_2 for every row; zero[i] = 1 where the norm is 0 (reference l2_norm raises).
@@ -259,33 +348,82 @@ int launch_l2_normalize(const float* d_X, int64_t n, int dim, float* d_out, int3
   return LSHX_OK;
 }
 
-int launch_rerank(const RerankArgs& a, cudaStream_t stream) {
+// Worst-case result count of a launch (the largest query decides).
+static int64_t worst_limit(const RerankArgs& a, int64_t mc) {
+  int64_t worst = a.k > 0 ? a.k : mc;
+  if (a.p > 0.0) {
+    int64_t lp = (int64_t)ceil((double)mc * a.p);
+    if (lp < 1) lp = 1;
+    worst = (a.k > 0 && a.k < lp) ? a.k : lp;
+  }
+  return worst < mc ? worst : mc;
+}
+
+static bool needs_bigsort(const RerankArgs& a) {
+  return a.select && a.max_cand > RR_MAX_CAP && worst_limit(a, a.max_cand) > RR_MAX_CAP / 2;
+}
+
+size_t rerank_scratch_bytes(const RerankArgs& a, int64_t* queries_per_pass) {
+  if (queries_per_pass) *queries_per_pass = a.nq;
+  if (!needs_bigsort(a)) return 0;
+  uint64_t stride = BS_TILE;
+  while (stride < (uint64_t)a.max_cand) stride <<= 1;
+  const size_t per_query = (size_t)stride * sizeof(uint64_t);
+  int64_t group = (int64_t)((1ull << 30) / per_query);   // at most 1 GiB of keys in flight
+  if (group < 1) group = 1;
+  if (group > a.nq) group = a.nq;
+  if (queries_per_pass) *queries_per_pass = group;
+  return per_query * (size_t)group;
+}
+
+int launch_rerank(const RerankArgs& a_in, cudaStream_t stream) {
+  RerankArgs a = a_in;
   if (a.nq <= 0) return LSHX_OK;
+  const int q_floats = (a.dim + 3) & ~3;
+  const bool vec4 = (a.dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.V) & 15) == 0);
+  auto kern = vec4 ? rerank_kernel<true> : rerank_kernel<false>;
+
+  if (needs_bigsort(a)) {
+    int64_t group = 0;
+    const size_t need = rerank_scratch_bytes(a, &group);
+    LSHX_REQUIRE(a.big_keys != nullptr && a.big_bytes >= need,
+                 "rerank: %lld candidates for one query need %zu bytes of sort scratch", (long long)a.max_cand, need);
+    const int64_t stride = (int64_t)(need / sizeof(uint64_t) / (size_t)group);
+    LSHX_REQUIRE(a.max_cand < (1ll << 32), "rerank: more than 2^32 candidates for one query");
+    const size_t smem = (size_t)q_floats * sizeof(float) + 2 * sizeof(uint64_t);
+    LSHX_REQUIRE(smem <= 227 * 1024, "rerank: dim %d too large for shared memory", a.dim);
+    LSHX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t q0 = 0; q0 < a_in.nq; q0 += group) {
+      RerankArgs c = a_in;
+      c.nq = (a_in.nq - q0 < group) ? (a_in.nq - q0) : group;
+      c.Q = a_in.Q + q0 * (int64_t)a_in.dim;
+      c.offs = a_in.offs + q0;
+      c.out_pos = a_in.out_pos + q0 * (int64_t)a_in.out_stride;
+      c.out_score = a_in.out_score + q0 * (int64_t)a_in.out_stride;
+      c.out_count = a_in.out_count + q0;
+      c.out_zero = a_in.out_zero ? a_in.out_zero + q0 : nullptr;
+      c.big_stride = stride;
+      RerankArgs score = c;       // pass 1: score every candidate, keys to global memory, no in-SM selection
+      score.select = false;
+      kern<<<(unsigned)c.nq, RR_THREADS, smem, stream>>>(score, 2u, q_floats);
+      count_launch();
+      LSHX_CUDA(cudaGetLastError());
+      rerank_bigsort_kernel<<<(unsigned)c.nq, BS_THREADS, 0, stream>>>(c);   // pass 2: sort + cut
+      count_launch();
+      LSHX_CUDA(cudaGetLastError());
+    }
+    return LSHX_OK;
+  }
+
+  a.big_keys = nullptr;
   unsigned cap = 2;
   if (a.select) {
     const int64_t mc = a.max_cand < 1 ? 1 : a.max_cand;
-    if (mc <= RR_MAX_CAP) {
-      cap = next_pow2((uint64_t)mc);
-    } else {
-      cap = RR_MAX_CAP;
-      // chunked running top-k keeps the best cap/2 keys between chunks
-      int64_t worst = a.k > 0 ? a.k : mc;
-      if (a.p > 0.0) {
-        int64_t lp = (int64_t)ceil((double)mc * a.p);
-        if (lp < 1) lp = 1;
-        worst = (a.k > 0 && a.k < lp) ? a.k : lp;
-      }
-      LSHX_REQUIRE(worst <= RR_MAX_CAP / 2,
-                   "rerank: %lld candidates for one query with up to %lld results; at most %d "
-                   "candidates per query, or at most %d results, are supported",
-                   (long long)mc, (long long)worst, RR_MAX_CAP, RR_MAX_CAP / 2);
-    }
+    // above RR_MAX_CAP candidates: chunked running top-k that keeps the best cap/2 keys between chunks
+    cap = mc <= RR_MAX_CAP ? next_pow2((uint64_t)mc) : (unsigned)RR_MAX_CAP;
   }
-  const int q_floats = (a.dim + 3) & ~3;
   const size_t smem = (size_t)q_floats * sizeof(float) + (size_t)cap * sizeof(uint64_t);
   LSHX_REQUIRE(smem <= 227 * 1024, "rerank: dim %d too large for shared memory", a.dim);
-  const bool vec4 = (a.dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.V) & 15) == 0);
-  auto kern = vec4 ? rerank_kernel<true> : rerank_kernel<false>;
   LSHX_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)(a.nq < (1 << 20) ? a.nq : (1 << 20));
   kern<<<grid, RR_THREADS, smem, stream>>>(a, cap, q_floats);

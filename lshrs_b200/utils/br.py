@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 __all__ = ["compute_lsh_threshold", "compute_collision_probability", "compute_false_rates",
-           "find_optimal_br", "get_optimal_config", "PRECOMPUTED_CONFIGS"]
+           "find_optimal_br", "get_optimal_config", "print_config_analysis", "PRECOMPUTED_CONFIGS"]
 
 # rows_per_band the reference tabulates per (signature bits, threshold); bands = bits // rows (br.py:38-79)
 _TABLE_ROWS = {
@@ -97,3 +97,20 @@ def get_optimal_config(num_perm: int, target_threshold: float = 0.5) -> tuple[in
     while num_perm % b:
         b -= 1
     return b, num_perm // b
+
+
+def print_config_analysis(num_perm: int, threshold: float = 0.5) -> None:
+    """Print the selected shape, its midpoint, both error areas and four points of the detection curve
+    (diagnostic helper the reference exports, br.py:398-460)."""
+    b, r = get_optimal_config(num_perm, threshold)
+    fp, fn = compute_false_rates(b, r, threshold)
+    print("LSH Configuration Analysis")
+    print("=" * 50)
+    print(f"Number of permutations: {num_perm}")
+    print(f"Target threshold: {threshold:.2f}")
+    print(f"\nOptimal configuration:\n  Bands (b): {b}\n  Rows per band (r): {r}")
+    print(f"\nPerformance metrics:\n  Actual threshold: {compute_lsh_threshold(b, r):.4f}")
+    print(f"  False positive rate: {fp:.2%}\n  False negative rate: {fn:.2%}")
+    print("\nDetection probabilities:")
+    for sim in (0.3, 0.5, 0.7, 0.9):
+        print(f"  Similarity {sim:.1f}: {compute_collision_probability(sim, b, r):.2%} chance of detection")

@@ -168,8 +168,10 @@ def projection_margins(projections: Sequence[np.ndarray], vectors) -> np.ndarray
 def compare_packed(got: np.ndarray, want: np.ndarray, margins: np.ndarray, rel_margin: float = 1e-5) -> dict:
     """Bit-level comparison of two packed signature arrays.
 
-    Returns counts of differing bits outside / inside the exempt margin and the
-    number of differing band keys whose every differing bit is exempt.
+    Returns counts of differing bits outside / inside the exempt margin, the
+    number of differing band keys, and ``max_flipped_margin``: the largest relative
+    margin |x.r| / (||x|| ||r||) at which a bit actually differs (0.0 when none
+    does) -- the empirical headroom of an arithmetic against the 1e-5 parity band.
     """
     assert got.shape == want.shape, (got.shape, want.shape)
     n, nb, bpb = want.shape
@@ -187,6 +189,7 @@ def compare_packed(got: np.ndarray, want: np.ndarray, margins: np.ndarray, rel_m
         "band_keys": int(n * nb),
         "band_keys_differing": int(np.count_nonzero(diff.any(axis=2))),
         "nonzero_pad_bits": int(np.count_nonzero(pad_g)),
+        "max_flipped_margin": float(margins[diff].max()) if diff.any() else 0.0,
     }
 
 

@@ -113,8 +113,17 @@ def test_top_p_limit_and_zero_test():
     assert not oracle.is_zero_vector(np.array([0, 0, 2e-8, 0])) and not oracle.is_zero_vector(np.array([np.nan, 0]))
 
 
-def test_auto_config_table_matches_reference(golden_manifest):
-    from lshrs_b200.core.main import _AUTO_CONFIG_T05
+def test_auto_config_matches_reference(golden_manifest):
+    """LSHRS(dim, num_perm=...) without num_bands / rows_per_band: lshrs_b200.utils.br must select what the
+    reference's get_optimal_config selects (reference lshrs/utils/br.py:325-395) on the whole recorded grid."""
+    from lshrs_b200.core.main import _auto_config
+    from lshrs_b200.utils.br import get_optimal_config
 
-    for n, (b, r) in _AUTO_CONFIG_T05.items():
-        assert golden_manifest["optimal_config"][str(n)] == [b, r]
+    for n, want in golden_manifest["optimal_config"].items():
+        assert list(_auto_config(int(n), 0.5)) == want
+    assert list(get_optimal_config(4096, 0.9)) == golden_manifest["optimal_config_4096_0.9"]
+    grid = golden_manifest["optimal_config_grid"]
+    assert len(grid) >= 200
+    for key, want in grid.items():
+        n, t = key.split("@")
+        assert list(map(int, get_optimal_config(int(n), float(t)))) == want, key

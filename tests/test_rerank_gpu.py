@@ -154,8 +154,10 @@ def test_ragged_candidate_lists_and_empty_queries():
 
 
 def test_more_candidates_than_one_sort_buffer():
-    """n > 16384 candidates for one query: chunked running top-k inside the kernel."""
-    from lshrs_b200 import LshxError, top_k_cosine
+    """n > 16384 candidates for one query: chunked running top-k inside the kernel, and -- when more than
+    8192 results are wanted as well -- the global-memory sort (the reference has no size limit,
+    similarity.py:174-179)."""
+    from lshrs_b200 import top_k_cosine
 
     rng = np.random.default_rng(4)
     n, dim = 40_000, 32
@@ -164,8 +166,58 @@ def test_more_candidates_than_one_sort_buffer():
     ref = oracle.cosine_similarity(q, C).astype(np.float64)
     _check_topk(top_k_cosine(q, C, k=100), ref, 100)
     _check_topk(top_k_cosine(q, C, k=8192), ref, 8192)
-    with pytest.raises(LshxError, match="at most"):
-        top_k_cosine(q, C, k=n)  # documented limit: fails loudly, no silent fallback
+    _check_topk(top_k_cosine(q, C, k=8193), ref, 8193)
+    _check_topk(top_k_cosine(q, C, k=n), ref, n)          # every candidate, fully sorted
+    _check_topk(top_k_cosine(q, C, k=10 * n), ref, n)
+
+
+def test_oversized_selection_batch_against_host_sort():
+    """Several queries of very different sizes in one oversized launch (one > 16384 candidates with p = 1.0):
+    positions must be exactly the stable descending sort of the kernel's own scores."""
+    from lshrs_b200.utils.similarity import _get_reranker
+
+    rng = np.random.default_rng(41)
+    dim = 24
+    sizes = [5, 70_000, 0, 16_385, 1, 20_000]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    V = rng.standard_normal((int(offsets[-1]), dim)).astype(np.float32)
+    V[offsets[1] + 7] = V[offsets[1] + 3]      # an exact tie: lower position first
+    Q = rng.standard_normal((len(sizes), dim)).astype(np.float32)
+    rer = _get_reranker(dim)
+    scores, zero = rer.scores(Q, V, offsets)
+    for p, k in ((1.0, 0), (0.6, 0), (1.0, 30_000)):
+        pos, score, count, zero2 = rer.topk(Q, V, offsets, k=k, p=p)
+        for i, n in enumerate(sizes):
+            want_n = 0 if n == 0 else min(max(1, math.ceil(n * p)), k or n, n)
+            assert count[i] == want_n, (i, p, k)
+            s = scores[offsets[i]:offsets[i + 1]]
+            order = np.lexsort((np.arange(n), -s.astype(np.float64)))[:want_n]
+            np.testing.assert_array_equal(pos[i, :want_n], order)
+            np.testing.assert_array_equal(score[i, :want_n], s[order])
+        np.testing.assert_array_equal(zero, zero2)
+
+
+def test_get_above_p_with_more_than_16384_candidates():
+    """ADVICE r1 (rerank.cu:278): LSHRS.get_above_p(p=0.95) on buckets that hold most of the corpus."""
+    from lshrs_b200 import LSHRS, InMemoryStorage
+
+    rng = np.random.default_rng(5)
+    n, dim = 20_000, 16
+    base = rng.standard_normal(dim).astype(np.float32)
+    X = (base[None, :] + 0.01 * rng.standard_normal((n, dim))).astype(np.float32)   # one tight cluster
+    lsh = LSHRS(dim=dim, num_perm=4, num_bands=2, rows_per_band=2, storage=InMemoryStorage(),
+                vector_fetch_fn=lambda ids: X[np.asarray(ids, dtype=np.int64)])
+    lsh.index(list(range(n)), X)
+    res = lsh.get_above_p(X[0], p=0.95)
+    cands = sorted(lsh.query(X[0], top_k=None))
+    assert len(cands) > 16_384
+    assert len(res) == max(1, math.ceil(len(cands) * 0.95))
+    ref = oracle.cosine_similarity(X[0], X[cands]).astype(np.float64)
+    by_id = dict(zip(cands, ref))
+    sc = np.array([s for _, s in res])
+    assert np.all(np.diff(sc) <= 0)
+    np.testing.assert_allclose(sc, [by_id[i] for i, _ in res], atol=SCORE_TOL, rtol=0)
+    assert res[0][0] == 0 or abs(res[0][1] - 1.0) < 1e-6
 
 
 def test_l2_norm_on_gpu():

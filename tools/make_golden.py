@@ -147,6 +147,12 @@ def main() -> None:
         str(n): list(map(int, get_optimal_config(n, 0.5))) for n in (64, 128, 256, 512, 1024)
     }
     manifest["optimal_config_4096_0.9"] = list(map(int, get_optimal_config(4096, 0.9)))
+    manifest["optimal_config_grid"] = {
+        f"{n}@{t}": list(map(int, get_optimal_config(n, t)))
+        for n in (1, 2, 3, 7, 16, 17, 32, 48, 64, 96, 100, 120, 128, 200, 256, 384, 512, 768, 1000, 1024, 2048,
+                  4096, 8192, 16384, 65536)
+        for t in (0.1, 0.3, 0.42, 0.5, 0.55, 0.6, 0.7, 0.8, 0.87, 0.9, 0.95, 0.99)
+    }
 
     # ------------------------------------------------------------------ rerank
     rer_cases = [
