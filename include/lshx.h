@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define LSHX_ABI_VERSION 1
+#define LSHX_ABI_VERSION 2
 
 typedef enum lshx_status {
   LSHX_OK = 0,
@@ -159,6 +159,29 @@ int lshx_hash_batch_typed(lshx_hasher* h, const void* X, int dtype /* lshx_dtype
 int lshx_signatures_to_hex(const uint8_t* sig, int64_t n, int sig_bytes, char* hex_out);
 
 int lshx_hasher_destroy(lshx_hasher* h);
+
+/*
+ * Bit mask of the tuning / bring-up environment overrides that are set in this
+ * process: 1 LSHX_TC_FLAGS, 2 LSHX_TC_SPLIT (kernel variant / operand split of
+ * the tcgen05 kernel), 4 LSHX_COPY_THREADS, 8 LSHX_BOUNCE_MB (pageable-input
+ * staging).  No reference counterpart; bench.py records it so that a published
+ * number states that the product dispatch was not overridden.
+ */
+int lshx_env_overrides(void);
+
+/*
+ * DIAGNOSTICS (tests only; no reference counterpart).  Runs the tcgen05 kernel
+ * over X (n rows, HOST float32) and returns the raw fp32 TMEM accumulators of
+ * the first tile of pass 0 -- before the sign test that LSHHasher._project_and_pack
+ * applies (lsh.py:204) -- row-major acc_out[out_rows][out_cols]:
+ * out_rows = min(n, 128) (min(n, 256) when the 2-CTA variant ran, n >= 256),
+ * out_cols = accumulator columns of a pass (column c = signature bit c when
+ * rows_per_band % 8 == 0).  With the default scaled FP16x3 arm entry (i, c)
+ * is s_x[i] * s_r[c] * (x_i . r_c) for exact powers of two s_x, s_r; the
+ * tests use it to measure the arithmetic's error on the hardware.
+ */
+int lshx_hasher_debug_accumulators(lshx_hasher* h, const float* X_host, int64_t n, float* acc_out,
+                                   int64_t acc_capacity, int* out_rows, int* out_cols);
 
 /* ---- reranker: replaces top_k_cosine (reference lshrs/utils/similarity.py) */
 

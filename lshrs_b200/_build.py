@@ -34,12 +34,26 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found; liblshx.so cannot be built")
 
 
+HASH_PATH = LIB_DIR / "liblshx.srchash"   # sha256 of the sources the shipped library was built from
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is compiled from (mtimes do not survive a snapshot copy)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    deps = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + [REPO / "include" / "lshx.h"]
+    for d in deps:
+        h.update(d.name.encode())
+        h.update(d.read_bytes())
+    h.update(" ".join(ARCH_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not LIB_PATH.exists():
+    if not LIB_PATH.exists() or not HASH_PATH.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [REPO / "include" / "lshx.h", Path(__file__)]
-    return any(d.stat().st_mtime > t for d in deps)
+    return HASH_PATH.read_text().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
@@ -48,6 +62,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB_PATH
     nvcc = _nvcc()
     LIB_DIR.mkdir(exist_ok=True)
+    import fcntl
+
+    with open(LIB_DIR / ".build.lock", "w") as lock:      # several ranks may find the library stale at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():
+            return LIB_PATH
+        return _build_locked(nvcc, verbose)
+
+
+def _build_locked(nvcc: str, verbose: bool) -> Path:
+    want_hash = source_hash()
     obj_dir = LIB_DIR / "obj"
     obj_dir.mkdir(exist_ok=True)
     common = [nvcc, "-O3", "-std=c++17", *ARCH_FLAGS, "-lineinfo", "-Xcompiler", "-fPIC",
@@ -71,6 +96,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
     os.replace(tmp, LIB_PATH)
+    HASH_PATH.write_text(want_hash + "\n")
     return LIB_PATH
 
 

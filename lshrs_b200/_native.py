@@ -31,7 +31,7 @@ __all__ = [
     "EXPORTED_SYMBOLS",
 ]
 
-ABI_VERSION = 1   # LSHX_ABI_VERSION of include/lshx.h this binding was written against
+ABI_VERSION = 2   # LSHX_ABI_VERSION of include/lshx.h this binding was written against
 KERNEL_AUTO, KERNEL_FFMA, KERNEL_TCGEN05 = 0, 1, 2
 KERNEL_TCGEN05_3XTF32 = 4
 KERNEL_TCGEN05_TF32BF16 = 5
@@ -53,6 +53,8 @@ EXPORTED_SYMBOLS = (
     "lshx_hash_batch_typed",
     "lshx_signatures_to_hex",
     "lshx_hasher_destroy",
+    "lshx_env_overrides",
+    "lshx_hasher_debug_accumulators",
     "lshx_rerank_create",
     "lshx_rerank_topk",
     "lshx_rerank_scores",
@@ -114,6 +116,10 @@ def _declare(cdll: ctypes.CDLL) -> None:
     cdll.lshx_signatures_to_hex.argtypes = [vp, c_int64, c_int, vp]
     cdll.lshx_hasher_destroy.restype = c_int
     cdll.lshx_hasher_destroy.argtypes = [vp]
+    cdll.lshx_env_overrides.restype = c_int
+    cdll.lshx_env_overrides.argtypes = []
+    cdll.lshx_hasher_debug_accumulators.restype = c_int
+    cdll.lshx_hasher_debug_accumulators.argtypes = [vp, vp, c_int64, vp, c_int64, POINTER(c_int), POINTER(c_int)]
 
     cdll.lshx_rerank_create.restype = c_int
     cdll.lshx_rerank_create.argtypes = [c_int, c_int, POINTER(vp)]
@@ -137,16 +143,21 @@ def lib() -> ctypes.CDLL:
         if _lib is not None:
             return _lib
         path = lib_path()
-        if not path.exists() and not os.environ.get("LSHX_LIBRARY"):
-            try:
-                from lshrs_b200 import _build
+        if not os.environ.get("LSHX_LIBRARY"):
+            # (re)build when the library is missing or was built from other sources than the ones in the tree
+            # (content hash, lshrs_b200/_lib/liblshx.srchash); a stale library without nvcc is an error, not
+            # something to run silently
+            from lshrs_b200 import _build
 
-                _build.build()
-            except Exception as exc:  # noqa: BLE001 - re-raised as the loud failure below
-                raise LshxUnavailable(
-                    ERR_NO_DEVICE,
-                    f"{path} is missing and could not be built ({exc}); lshrs_b200 has no CPU fallback",
-                ) from exc
+            if _build._stale():
+                try:
+                    _build.build()
+                except Exception as exc:  # noqa: BLE001 - re-raised as the loud failure below
+                    what = "is missing" if not path.exists() else "was built from different sources"
+                    raise LshxUnavailable(
+                        ERR_NO_DEVICE,
+                        f"{path} {what} and could not be (re)built ({exc}); lshrs_b200 has no CPU fallback",
+                    ) from exc
         try:
             cdll = ctypes.CDLL(str(path))
         except OSError as exc:
@@ -178,6 +189,13 @@ def default_device() -> int:
         if val is not None and val.strip() != "":
             return int(val)
     return 0
+
+
+def env_overrides() -> list[str]:
+    """Names of the LSHX_* tuning overrides set in this process (empty in a product run)."""
+    mask = int(lib().lshx_env_overrides())
+    names = ("LSHX_TC_FLAGS", "LSHX_TC_SPLIT", "LSHX_COPY_THREADS", "LSHX_BOUNCE_MB")
+    return [n for i, n in enumerate(names) if mask & (1 << i)]
 
 
 def launch_count() -> int:

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* __restrict__ Rp,
                  int ncols_pad, uint8_t* __restrict__ out, int sig_bytes,
                  uint8_t* __restrict__ zero_flag, int out_word_ok,
-                 const int* __restrict__ tile_list, const int* __restrict__ tile_count) {
+                 const int* __restrict__ tile_list, int* tile_count) {
   __shared__ __align__(16) float Xs[2][BK][LDS];
   __shared__ __align__(16) float Rs[2][BK][LDS];
   __shared__ uint32_t bits[BM][BN / 32];
@@ -187,6 +187,16 @@ hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* _
   }
   __syncthreads();   // recompute mode: the shared tiles are reused by the next item
   }
+  // recompute mode: the last CTA to leave resets the list's counter (tile_count[0]) and the exit ticket
+  // (tile_count[1]) for the slot's next launch -- every CTA read the counter before taking its ticket
+  __syncthreads();
+  if (tile_list != nullptr && tid == 0) {
+    __threadfence();
+    if (atomicAdd(tile_count + 1, 1) == (int)gridDim.x - 1) {
+      tile_count[0] = 0;
+      tile_count[1] = 0;
+    }
+  }
 }
 
 
@@ -264,7 +274,7 @@ int launch_hash_ffma(const HashShape& s, const float* d_X, int64_t n, const floa
 
 // Recompute the 128-row tiles listed in d_tile_list[0 .. *d_tile_count) (device memory) in FP32.
 int launch_hash_ffma_tiles(const HashShape& s, const float* d_X, int64_t n, const float* d_Rp, uint8_t* d_out,
-                           const int* d_tile_list, const int* d_tile_count, int num_ctas, cudaStream_t stream) {
+                           const int* d_tile_list, int* d_tile_count, int num_ctas, cudaStream_t stream) {
   if (n <= 0) return LSHX_OK;
   const bool vec4 = (s.dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_X) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(d_Rp) & 15) == 0);

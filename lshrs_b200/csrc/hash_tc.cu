@@ -244,6 +244,9 @@ struct TcParams {
   // (one entry per converter warp that saw one) and recomputed in FP32 right after (launch_hash_tc)
   int* redo_count;
   int* redo_list;
+  // diagnostics (lshx_hasher_debug_accumulators, tests only; nullptr in every product launch): the raw fp32
+  // TMEM accumulators of the first tile, pass 0, row-major [tile rows][ncols_pass]
+  float* dbg_acc;
 };
 
 // One half (16 floats) of thread t's 128 B row of an X chunk in shared memory -> A-operand words.
@@ -401,6 +404,18 @@ __device__ __forceinline__ void read_sign_words(uint32_t tmem_row, uint32_t N, u
     }
     words[2 * g] = w0;
     words[2 * g + 1] = w1;
+  }
+}
+
+// Diagnostics: this thread's accumulator row as it sits in TMEM (before the sign test) -> dst[0 .. N).
+__device__ __noinline__ void dump_accumulator_row(uint32_t tmem_row, uint32_t N, float* dst) {
+  for (uint32_t c = 0; c < N; c += 32) {
+    uint32_t v[32];
+    tc_ld32(tmem_row + c, v);
+    tc_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (c + (uint32_t)i < N) dst[c + i] = __uint_as_float(v[i]);
   }
 }
 
@@ -859,6 +874,8 @@ hash_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__
       if (ngroups == 1u || p.kc >= 2 || first_owner == 0u) fl |= conv_flags[tcount & 7u][0][t];
       if (ngroups == 2u && (p.kc >= 2 || first_owner == 1u)) fl |= conv_flags[tcount & 7u][1][t];
       uint32_t words[8];
+      if (p.dbg_acc != nullptr && w == 0)
+        dump_accumulator_row(tmem_base + lane_field + dr.idx * TN, N, p.dbg_acc + (size_t)t * N);
       read_sign_words(tmem_base + lane_field + dr.idx * TN, N, words);
       tc_fence_before();
       __syncwarp();
@@ -1092,6 +1109,8 @@ hash_tc2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant_
       mbar_wait(d_full(dr.idx), dr.phase);
       tc_fence_after();
       uint32_t words[8];
+      if (p.dbg_acc != nullptr && w == 0)
+        dump_accumulator_row(tmem_base + lane_field + dr.idx * TN, N, p.dbg_acc + (size_t)(rank * TM + t) * N);
       read_sign_words(tmem_base + lane_field + dr.idx * TN, N, words);
       tc_fence_before();
       __syncwarp();
@@ -1164,7 +1183,7 @@ __global__ void split_cross_kernel(const float* __restrict__ Rp, const int* __re
 // that puts the row's largest |r| in [2^13, 2^14); the 16 words of K block g hold 32 FP16: words
 // [0,8) = q_hi pairs, [8,16) = q_lo pairs (q_hi = FP16(q), q_lo = FP16(q - q_hi), even k in the low half).
 __global__ void split_f16_kernel(const float* __restrict__ Rp, const int* __restrict__ rowmap,
-                                 uint32_t* __restrict__ plane, int dim, int dim_pad) {
+                                 uint32_t* __restrict__ plane, int dim, int dim_pad, int* __restrict__ bad_rows) {
   __shared__ float red[32];
   const int row = blockIdx.x;
   const int src = rowmap[row];
@@ -1179,7 +1198,17 @@ __global__ void split_f16_kernel(const float* __restrict__ Rp, const int* __rest
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
   const int e = (int)((__float_as_uint(m) >> 23) & 0xFFu);
   const int se = 254 + 13 - e;
-  const float sc = (e >= 13 && e < 255 && se >= 1) ? __uint_as_float((uint32_t)se << 23) : 1.f;
+  const bool representable = (e >= 13 && e < 255 && se >= 1);
+  const float sc = representable ? __uint_as_float((uint32_t)se << 23) : 1.f;
+  // a NON-ZERO row without a representable scale (largest |r| below 2^-114, infinite, or NaN -- only
+  // reachable through hasher.projections = [...]) would be flushed by FP16: the plan then refuses the FP16x3
+  // arm and the hasher runs the FP32 kernel instead (tc_plan_create), never silently wrong bits
+  bool has_nan = false;
+  if (r != nullptr)
+    for (int k = threadIdx.x; k < dim; k += blockDim.x) has_nan |= (r[k] != r[k]);
+  if (__syncthreads_or((int)has_nan) || (!representable && m != 0.f)) {
+    if (threadIdx.x == 0) atomicAdd(bad_rows, 1);
+  }
   for (int wd = threadIdx.x; wd < dim_pad; wd += blockDim.x) {
     const int g = wd / 16, j = wd % 16;
     const int k0 = 16 * g + 2 * (j & 7);
@@ -1254,6 +1283,22 @@ struct TcPlan {
   int num_sms = 0;
   // column layout of the split projections (see tc_plan_create)
   int ncols_pass = 0, npass = 0, repack = 0, bpp = 0;
+  bool f16_ok = true;   // false: some projection row has no representable FP16 scale (split_f16_kernel)
+  // FP16x3: handle-owned scratch for the lists of 128-row tiles to recompute in FP32.  A small ring, one
+  // slot per launch in flight: [0] = counter (reset by the recompute kernel itself), [1] = its exit ticket,
+  // [4 ..] = up to four entries per tile.  `done` orders a slot's next user after its last one when the two
+  // launches are on different streams.
+  struct RedoSlot {
+    int* buf = nullptr;
+    size_t tiles = 0;
+    cudaEvent_t done = nullptr;
+    cudaStream_t last = nullptr;
+    bool used = false;
+  };
+  static constexpr int kRedoSlots = 4;
+  RedoSlot redo[kRedoSlots];
+  int next_redo = 0;
+  float* dbg_acc = nullptr;   // diagnostics only (lshx_hasher_debug_accumulators): 256 x 256 floats when set
 };
 
 bool tc_shape_supported(const HashShape& s) {
@@ -1303,19 +1348,27 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
     if (d_rowmap) cudaFree(d_rowmap);
     return fail(LSHX_ERR_OOM);
   }
-  cudaMemcpy(d_rowmap, rowmap.data(), rowmap.size() * sizeof(int), cudaMemcpyHostToDevice);
-  split_projections_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_hi, pl->d_lo, rows, s.dim, s.dim_pad);
-  split_cross_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_x, rows, s.dim, s.dim_pad);
-  split_f16_kernel<<<rows, 256>>>(d_Rp, d_rowmap, pl->d_h, s.dim, s.dim_pad);
-  count_launch(3);
+  int* d_bad = nullptr;
+  cudaError_t serr = cudaMemcpy(d_rowmap, rowmap.data(), rowmap.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (serr == cudaSuccess) serr = cudaMalloc(&d_bad, sizeof(int));
+  if (serr == cudaSuccess) serr = cudaMemset(d_bad, 0, sizeof(int));
+  int bad_rows = 0;
+  if (serr == cudaSuccess) {
+    split_projections_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_hi, pl->d_lo, rows, s.dim, s.dim_pad);
+    split_cross_kernel<<<256, 256>>>(d_Rp, d_rowmap, pl->d_x, rows, s.dim, s.dim_pad);
+    split_f16_kernel<<<rows, 256>>>(d_Rp, d_rowmap, pl->d_h, s.dim, s.dim_pad, d_bad);
+    count_launch(3);
+    serr = cudaMemcpy(&bad_rows, d_bad, sizeof(int), cudaMemcpyDeviceToHost);   // synchronises
+  }
   pl->d_Rp = d_Rp;
-  const cudaError_t serr = cudaDeviceSynchronize();
   cudaFree(d_rowmap);
+  if (d_bad) cudaFree(d_bad);
   if (serr != cudaSuccess) {
-    set_error("split_projections_kernel failed: %s", cudaGetErrorString(serr));
+    set_error("splitting the projections failed: %s", cudaGetErrorString(serr));
     (void)cudaGetLastError();
     return fail(LSHX_ERR_CUDA);
   }
+  pl->f16_ok = (bad_rows == 0);
   const uint64_t pitch = (uint64_t)s.dim_pad * sizeof(float);
   const uint32_t brows = (uint32_t)pl->ncols_pass;  // columns per pass = rows of one projection box
   int rc = make_map(&pl->tm_rhi, pl->d_hi, (uint64_t)rows, (uint64_t)s.dim_pad, pitch, TKB, brows,
@@ -1383,8 +1436,32 @@ int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out) {
   return LSHX_OK;
 }
 
+bool tc_plan_f16_ok(const TcPlan* p) { return p != nullptr && p->f16_ok; }
+int tc_plan_default_split(const TcPlan* p) { return p ? p->auto_split : -1; }
+int tc_plan_flags(const TcPlan* p) { return p ? p->flags : 0; }
+
+int tc_plan_set_debug(TcPlan* p, bool on) {
+  if (on && p->dbg_acc == nullptr) {
+    LSHX_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->dbg_acc), 2 * TM * 2 * TN * sizeof(float)));
+    LSHX_CUDA(cudaMemset(p->dbg_acc, 0, 2 * TM * 2 * TN * sizeof(float)));
+  } else if (!on && p->dbg_acc != nullptr) {
+    cudaFree(p->dbg_acc);
+    p->dbg_acc = nullptr;
+  }
+  return LSHX_OK;
+}
+const float* tc_plan_debug_buffer(const TcPlan* p, int* cols) {
+  if (cols) *cols = p->ncols_pass;
+  return p->dbg_acc;
+}
+
 void tc_plan_destroy(TcPlan* p) {
   if (!p) return;
+  for (auto& slot : p->redo) {
+    if (slot.buf) cudaFree(slot.buf);
+    if (slot.done) cudaEventDestroy(slot.done);
+  }
+  if (p->dbg_acc) cudaFree(p->dbg_acc);
   if (p->d_hi) cudaFree(p->d_hi);
   if (p->d_lo) cudaFree(p->d_lo);
   if (p->d_x) cudaFree(p->d_x);
@@ -1430,21 +1507,35 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X
   p.flags = plan->flags;
   p.redo_count = nullptr;
   p.redo_list = nullptr;
-  // FP16x3: stream-ordered scratch for the list of 128-row tiles to recompute in FP32 (a counter, then
-  // up to four entries -- one per converter warp -- for every tile)
-  int* scratch = nullptr;
+  p.dbg_acc = plan->dbg_acc;
+  // FP16x3: a handle-owned scratch slot for the list of 128-row tiles to recompute in FP32 (a counter, then
+  // up to four entries -- one per converter warp -- for every tile); no allocation on the launch path
+  TcPlan::RedoSlot* slot = nullptr;
   if (split == 2) {
-    const size_t bytes = 16 + sizeof(int) * 4 * (size_t)p.mtiles;
-    if (cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, stream) != cudaSuccess) {
-      // no stream-ordered allocator here (e.g. memory pools disabled): take the scale-free TF32+BF16
-      // arm for this launch, which needs no scratch
-      (void)cudaGetLastError();
-      scratch = nullptr;
-      return launch_hash_tc(s, plan, 1, d_X, n, d_out, d_zero_flag, stream);
+    LSHX_REQUIRE(plan->f16_ok, "a projection row has no representable FP16 scale: the FP16x3 arm cannot be "
+                               "used with these projections (LSHX_KERNEL_AUTO takes the FP32 kernel)");
+    slot = &plan->redo[plan->next_redo];
+    plan->next_redo = (plan->next_redo + 1) % TcPlan::kRedoSlots;
+    const size_t tiles = (size_t)p.mtiles;
+    if (slot->done == nullptr) LSHX_CUDA(cudaEventCreateWithFlags(&slot->done, cudaEventDisableTiming));
+    if (slot->tiles < tiles) {
+      if (slot->used) LSHX_CUDA(cudaEventSynchronize(slot->done));   // its last launch still reads the old buffer
+      if (slot->buf) cudaFree(slot->buf);
+      slot->buf = nullptr;
+      slot->tiles = 0;
+      const size_t want = tiles < 4096 ? 4096 : tiles + tiles / 4;
+      if (cudaMalloc(reinterpret_cast<void**>(&slot->buf), 16 + sizeof(int) * 4 * want) != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_error("cudaMalloc of %zu bytes for the FP32-recompute tile list failed", 16 + sizeof(int) * 4 * want);
+        return LSHX_ERR_OOM;
+      }
+      LSHX_CUDA(cudaMemset(slot->buf, 0, 16));
+      slot->tiles = want;
+      slot->used = false;
     }
-    LSHX_CUDA(cudaMemsetAsync(scratch, 0, 16, stream));
-    p.redo_count = scratch;
-    p.redo_list = scratch + 4;
+    if (slot->used && slot->last != stream) LSHX_CUDA(cudaStreamWaitEvent(stream, slot->done, 0));
+    p.redo_count = slot->buf;
+    p.redo_list = slot->buf + 4;
   }
   // 2-CTA kernel: streamed projections, byte-aligned bands, enough 256-row tiles to fill every SM pair
   const int npairs = plan->num_sms / 2;
@@ -1479,9 +1570,12 @@ int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X
   LSHX_CUDA(cudaGetLastError());
   if (split == 2) {
     // vectors outside the scaled FP16 range (normally none: the CTAs read a zero counter and return)
+    // (the recompute kernel resets the slot's counter when its last CTA leaves)
     rc = launch_hash_ffma_tiles(s, d_X, n, plan->d_Rp, d_out, p.redo_list, p.redo_count, 2 * plan->num_sms, stream);
     if (rc != LSHX_OK) return rc;
-    LSHX_CUDA(cudaFreeAsync(scratch, stream));
+    LSHX_CUDA(cudaEventRecord(slot->done, stream));
+    slot->last = stream;
+    slot->used = true;
   }
   return LSHX_OK;
 }

@@ -228,10 +228,13 @@ extern "C" int lshx_hasher_set_kernel(lshx_hasher* h, int kernel) {
   const bool is_tc = kernel == LSHX_KERNEL_TCGEN05 || kernel == LSHX_KERNEL_TCGEN05_3XTF32 ||
                      kernel == LSHX_KERNEL_TCGEN05_TF32BF16;
   LSHX_REQUIRE(kernel == LSHX_KERNEL_AUTO || kernel == LSHX_KERNEL_FFMA || is_tc, "unknown kernel %d", kernel);
+  std::lock_guard<std::mutex> lk(h->mu);   // h->tc is rebuilt by lshx_hasher_set_projections under the same lock
   LSHX_REQUIRE(!is_tc || h->tc != nullptr,
                "the tcgen05 kernel does not support this shape (dim %d, %d x %d)", h->s.dim,
                h->s.num_bands, h->s.rows_per_band);
-  std::lock_guard<std::mutex> lk(h->mu);
+  LSHX_REQUIRE(kernel != LSHX_KERNEL_TCGEN05 || tc_plan_f16_ok(h->tc),
+               "a projection row has no representable FP16 scale (largest |r| below 2^-114, infinite or NaN): "
+               "the scaled FP16x3 arm cannot hash with these projections");
   h->kernel_pref = kernel;
   return LSHX_OK;
 }
@@ -311,8 +314,17 @@ class CopyPool {
 }  // namespace
 
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  // 12 of 16 cores measured best for one process (48 GB/s).  Under torchrun every rank has its own pool:
+  // share the cores between the LOCAL_WORLD_SIZE processes of this host (8 ranks x 12 threads on 32 cores
+  // collapsed the pageable path to 2.5 M vectors/s per rank) and leave one for the thread that drives CUDA
   unsigned hw = std::thread::hardware_concurrency();
-  unsigned nt = hw >= 4 ? (hw * 3 / 4 > 12 ? 12 : hw * 3 / 4) : 1;   // 12 of 16 cores measured best (48 GB/s)
+  unsigned local_ranks = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 1024) local_ranks = (unsigned)v;
+  }
+  unsigned share = hw / local_ranks;
+  unsigned nt = share >= 4 ? (share * 3 / 4 > 12 ? 12 : share * 3 / 4) : (share >= 2 ? share - 1 : 1);
   if (const char* e = getenv("LSHX_COPY_THREADS")) {   // tuning knob
     const int v = atoi(e);
     if (v >= 1 && v <= 64) nt = (unsigned)v;
@@ -483,10 +495,11 @@ static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_o
   // operand split of the tcgen05 kernel: < 0 = the plan's default (scaled FP16x3)
   const int split = h->kernel_pref == LSHX_KERNEL_TCGEN05_3XTF32 ? 0
                     : h->kernel_pref == LSHX_KERNEL_TCGEN05_TF32BF16 ? 1 : -1;
-  const bool use_tc =
-      h->tc != nullptr && (h->kernel_pref == LSHX_KERNEL_TCGEN05 || split >= 0 ||
-                           (h->kernel_pref == LSHX_KERNEL_AUTO &&
-                            (reinterpret_cast<uintptr_t>(d_X) & 15) == 0));
+  // AUTO: tcgen05 (scaled FP16x3) for 16-byte aligned vectors, unless a projection row has no representable
+  // FP16 scale -- then the FP32 kernel, which has numpy's semantics for any finite or non-finite plane
+  const bool auto_tc = h->kernel_pref == LSHX_KERNEL_AUTO && (reinterpret_cast<uintptr_t>(d_X) & 15) == 0 &&
+                       (tc_plan_f16_ok(h->tc) || tc_plan_default_split(h->tc) != 2);
+  const bool use_tc = h->tc != nullptr && (h->kernel_pref == LSHX_KERNEL_TCGEN05 || split >= 0 || auto_tc);
   h->last_kernel = use_tc ? (split >= 0 ? h->kernel_pref : LSHX_KERNEL_TCGEN05) : LSHX_KERNEL_FFMA;
   // one launch takes < 2^31 rows (TMA coordinates / grid size are 32-bit): split larger batches
   const int64_t piece = 1ll << 30;
@@ -607,6 +620,55 @@ extern "C" int lshx_hash_batch_typed(lshx_hasher* h, const void* X, int dtype, i
   DeviceGuard g(h->device);
   LSHX_CUDA(cudaStreamSynchronize(nullptr));
   return hash_pageable(h, X, dtype, n, out, zero_flag);
+}
+
+extern "C" int lshx_env_overrides(void) {
+  static const char* const names[] = {"LSHX_TC_FLAGS", "LSHX_TC_SPLIT", "LSHX_COPY_THREADS", "LSHX_BOUNCE_MB"};
+  int mask = 0;
+  for (int i = 0; i < 4; ++i) {
+    const char* e = getenv(names[i]);
+    if (e != nullptr && *e) mask |= 1 << i;
+  }
+  return mask;
+}
+
+extern "C" int lshx_hasher_debug_accumulators(lshx_hasher* h, const float* X_host, int64_t n, float* acc_out,
+                                              int64_t acc_capacity, int* out_rows, int* out_cols) {
+  LSHX_REQUIRE(h != nullptr && X_host != nullptr && acc_out != nullptr && out_rows && out_cols, "null argument");
+  LSHX_REQUIRE(n > 0, "n must be > 0");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  LSHX_REQUIRE(h->tc != nullptr, "the tcgen05 kernel does not support this shape");
+  const HashShape& s = h->s;
+  int rc;
+  if ((rc = h->x_stage[0].reserve((size_t)n * s.dim * sizeof(float))) != LSHX_OK) return rc;
+  if ((rc = h->out_stage[0].reserve((size_t)n * s.sig_bytes)) != LSHX_OK) return rc;
+  if ((rc = tc_plan_set_debug(h->tc, true)) != LSHX_OK) return rc;
+  cudaStream_t st = h->streams[0];
+  LSHX_CUDA(cudaMemcpyAsync(h->x_stage[0].p, X_host, (size_t)n * s.dim * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int pref = h->kernel_pref;
+  if (pref == LSHX_KERNEL_AUTO || pref == LSHX_KERNEL_FFMA) h->kernel_pref = LSHX_KERNEL_TCGEN05;
+  rc = launch_hash(h, static_cast<const float*>(h->x_stage[0].p), n, static_cast<uint8_t*>(h->out_stage[0].p),
+                   nullptr, st);
+  h->kernel_pref = pref;
+  int cols = 0;
+  const float* d_acc = tc_plan_debug_buffer(h->tc, &cols);
+  // the 2-CTA variant works on 256-row tiles; report what the first tile held
+  const int tile_rows = (n >= 256) ? 256 : 128;
+  const int rows = (int)(n < tile_rows ? n : tile_rows);
+  if (rc == LSHX_OK && (int64_t)rows * cols > acc_capacity) {
+    set_error("acc_out holds %lld floats, %lld needed", (long long)acc_capacity, (long long)rows * cols);
+    rc = LSHX_ERR_INVALID_ARG;
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == LSHX_OK && e == cudaSuccess)
+    e = cudaMemcpy(acc_out, d_acc, (size_t)rows * cols * sizeof(float), cudaMemcpyDeviceToHost);
+  tc_plan_set_debug(h->tc, false);
+  if (rc != LSHX_OK) return rc;
+  LSHX_CUDA(e);
+  *out_rows = rows;
+  *out_cols = cols;
+  return LSHX_OK;
 }
 
 extern "C" int lshx_signatures_to_hex(const uint8_t* sig, int64_t n, int sig_bytes, char* hex_out) {

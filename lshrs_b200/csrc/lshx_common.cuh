@@ -59,9 +59,10 @@ struct HashShape {
 int launch_hash_ffma(const HashShape& s, const float* d_X, int64_t n, const float* d_Rp,
                      uint8_t* d_out, uint8_t* d_zero_flag, cudaStream_t stream);
 
-// Recompute mode of the same kernel: the 128-row tiles listed in d_tile_list[0 .. *d_tile_count).
+// Recompute mode of the same kernel: the 128-row tiles listed in d_tile_list[0 .. d_tile_count[0]).  The
+// kernel zeroes d_tile_count[0] (and its exit ticket d_tile_count[1]) when its last CTA leaves.
 int launch_hash_ffma_tiles(const HashShape& s, const float* d_X, int64_t n, const float* d_Rp, uint8_t* d_out,
-                           const int* d_tile_list, const int* d_tile_count, int num_ctas, cudaStream_t stream);
+                           const int* d_tile_list, int* d_tile_count, int num_ctas, cudaStream_t stream);
 
 // Small batches (<= hash_small_max_rows): one CTA per output byte, one warp per column.  `out` /
 // `zero_flag` may be mapped pinned host memory (the kernel stores straight into it).
@@ -73,6 +74,12 @@ struct TcPlan;  // opaque tcgen05 state (TMA descriptor of the split projections
 bool tc_shape_supported(const HashShape& s);
 int tc_plan_create(const HashShape& s, const float* d_Rp, TcPlan** out);
 void tc_plan_destroy(TcPlan* p);
+bool tc_plan_f16_ok(const TcPlan* p);       // false: a projection row has no representable FP16 scale
+int tc_plan_default_split(const TcPlan* p); // what split < 0 resolves to (2 unless LSHX_TC_SPLIT overrides)
+int tc_plan_flags(const TcPlan* p);         // TC_FLAG_* in effect (LSHX_TC_FLAGS overrides the default)
+// diagnostics (tests): keep the first tile's raw fp32 accumulators of every following launch
+int tc_plan_set_debug(TcPlan* p, bool on);
+const float* tc_plan_debug_buffer(const TcPlan* p, int* cols);
 // split: 0 = 3xTF32, 1 = TF32 hi.hi + BF16 cross terms, 2 = scaled FP16x3, < 0 = the plan's choice
 int launch_hash_tc(const HashShape& s, TcPlan* plan, int split, const float* d_X, int64_t n, uint8_t* d_out,
                    uint8_t* d_zero_flag, cudaStream_t stream);

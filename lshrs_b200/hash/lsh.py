@@ -70,7 +70,9 @@ class LSHHasher:
         self._device = _native.default_device() if device is None else int(device)
         self._lock = threading.Lock()
         self._handle: ctypes.c_void_p | None = None
-        self._uploaded_ids: tuple[int, ...] | None = None
+        # the arrays whose contents are on the device: held by reference so that CPython cannot recycle their
+        # id() for a new array while we still compare against it
+        self._uploaded: tuple[np.ndarray, ...] | None = None
         self._kernel = _native.KERNEL_AUTO
         # host draw, identical to the reference (float64 draws cast to float32, one rng, band order)
         rng = np.random.default_rng(seed)
@@ -86,11 +88,11 @@ class LSHHasher:
     @projections.setter
     def projections(self, value) -> None:
         self._projections = list(value)
-        self._uploaded_ids = None  # re-upload lazily
+        self._uploaded = None  # re-upload lazily
 
     def sync_projections(self) -> None:
         """Force a re-upload of ``projections`` (after in-place edits of the arrays)."""
-        self._uploaded_ids = None
+        self._uploaded = None
 
     def _stacked_projections(self) -> np.ndarray:
         mats = []
@@ -105,15 +107,18 @@ class LSHHasher:
             raise ValueError(f"expected {self.num_bands} projection matrices, found {len(mats)}")
         return np.ascontiguousarray(np.concatenate(mats, axis=0))
 
+    def _is_current(self) -> bool:
+        up, cur = self._uploaded, self._projections
+        return up is not None and len(up) == len(cur) and all(a is b for a, b in zip(up, cur))
+
     def _ensure_handle(self) -> ctypes.c_void_p:
-        ids = tuple(id(m) for m in self._projections)
-        if self._handle is not None and ids == self._uploaded_ids:
+        if self._handle is not None and self._is_current():
             return self._handle
         with self._lock:
-            ids = tuple(id(m) for m in self._projections)
-            if self._handle is not None and ids == self._uploaded_ids:
+            if self._handle is not None and self._is_current():
                 return self._handle
             lib = _native.lib()
+            current = tuple(self._projections)
             stacked = self._stacked_projections()
             if self._handle is None:
                 handle = ctypes.c_void_p()
@@ -126,7 +131,7 @@ class LSHHasher:
                     _native.check(lib.lshx_hasher_set_kernel(self._handle, self._kernel))
             else:
                 _native.check(lib.lshx_hasher_set_projections(self._handle, stacked.ctypes.data))
-            self._uploaded_ids = ids
+            self._uploaded = current
             return self._handle
 
     # ------------------------------------------------------------------ kernel choice
@@ -286,6 +291,18 @@ class LSHHasher:
             self.hash_into(x, n, out, x_on_device=True, out_on_device=True, zero_flag=zero_flag, stream=stream)
         return out
 
+    def debug_accumulators(self, vectors) -> np.ndarray:
+        """DIAGNOSTICS: the tcgen05 kernel's raw fp32 accumulators for the first tile of ``vectors``
+        (``lshx_hasher_debug_accumulators``): ``float32[rows, cols]``, column c = signature bit c for
+        byte-aligned bands.  Used by the tests to measure the split arithmetic on the hardware."""
+        arr = np.ascontiguousarray(self._validate_batch(np.asarray(vectors, dtype=np.float32)), dtype=np.float32)
+        handle = self._ensure_handle()
+        out = np.zeros((256, 256), dtype=np.float32)
+        rows, cols = ctypes.c_int(0), ctypes.c_int(0)
+        _native.check(_native.lib().lshx_hasher_debug_accumulators(
+            handle, arr.ctypes.data, arr.shape[0], out.ctypes.data, out.size, ctypes.byref(rows), ctypes.byref(cols)))
+        return out.reshape(-1)[: rows.value * cols.value].reshape(rows.value, cols.value).copy()
+
     # ------------------------------------------------------------------ lifetime
     def close(self) -> None:
         """Free the device copy of the projections and the staging buffers."""
@@ -293,7 +310,7 @@ class LSHHasher:
             if self._handle is not None:
                 _native.lib().lshx_hasher_destroy(self._handle)
                 self._handle = None
-                self._uploaded_ids = None
+                self._uploaded = None
 
     def __del__(self) -> None:  # pragma: no cover - best effort
         try:

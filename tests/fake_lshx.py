@@ -69,6 +69,9 @@ class FakeLshx:
     def lshx_launch_count(self):
         return self.launches
 
+    def lshx_env_overrides(self):
+        return 0
+
     def _new(self, obj, out_ref):
         self._next += 16
         self._handles[self._next] = obj

@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 KERNELS = ("ffma", "tcgen05", "tcgen05_3xtf32", "tcgen05_tf32bf16")
 TC_KERNELS = KERNELS[1:]
 REL_MARGIN = 1e-5  # north_star exempt margin
+MAX_FLIP_MARGIN = 1e-6  # largest |x.r| / (|x||r|) at which any arm may disagree with the fp32 oracle
 
 
 def _hasher(nb, r, dim, seed=42, kernel="ffma"):
@@ -41,8 +42,11 @@ def _assert_parity(got, X, projs, what=""):
     rep = oracle.compare_packed(got, want, oracle.projection_margins(projs, X), REL_MARGIN)
     assert rep["flips_outside_margin"] == 0, (what, rep)
     assert rep["nonzero_pad_bits"] == 0, (what, rep)
-    # flips inside the margin must be rare: no more than the bits that lie inside it
-    assert rep["flips_inside_margin"] <= rep["bits_inside_margin"], (what, rep)
+    # flips inside the margin must be rare -- at most 5 % of the bits that lie inside it (one flip of slack
+    # for shapes with a handful of exempt bits) -- and must sit an order of magnitude below the margin itself:
+    # a flip at 1e-6 * |x||r| would mean the arithmetic is 10x worse than the fp32 sgemm it stands in for
+    assert rep["flips_inside_margin"] <= max(1, math.ceil(0.05 * rep["bits_inside_margin"])), (what, rep)
+    assert rep["max_flipped_margin"] <= MAX_FLIP_MARGIN, (what, rep)
     return rep
 
 
