@@ -9,9 +9,9 @@ same ``(band_id, bytes, index)`` operations with the same flush boundaries.
 Bucket storage is NOT re-implemented: pass the reference's ``RedisStorage`` (or
 anything with its five methods) as ``storage=``.  ``save_to_disk`` /
 ``load_from_disk`` / pickling keep the reference's formats, ``create_signatures``
-takes the Arrow-buffer Parquet feed; the PostgreSQL loader stays in the reference
-(INTEGRATION.md shows the two-import patch that puts the reference's own
-``LSHRS`` on these kernels instead).
+takes the Arrow-buffer Parquet feed or the binary-COPY PostgreSQL feed
+(``lshrs_b200/io``; INTEGRATION.md shows the two-import patch that puts the
+reference's own ``LSHRS`` on these kernels instead).
 
 What is new is batching: ``index()`` hashes the whole batch in ONE kernel call
 with the zero-vector test fused in, and ``query_batch`` hashes all queries at
@@ -144,11 +144,10 @@ class LSHRS:
     def create_signatures(self, *, format: str = "postgres", **loader_kwargs: Any) -> None:
         """Stream ``(indices, vectors)`` batches from a loader into :meth:`index` (reference main.py:315-384)."""
         loader = self._resolve_loader(format)
-        batches = loader(**loader_kwargs)
-        if format.lower() in {"parquet", "pq"}:
-            from lshrs_b200.io.parquet import prefetched
+        from lshrs_b200.io.parquet import prefetched
 
-            batches = prefetched(batches)   # decode the next row group while this batch is hashed
+        # decode the next row group / read the next COPY block while this batch is hashed
+        batches = prefetched(loader(**loader_kwargs))
         for indices, vectors in batches:
             self.index(indices, vectors)
 
@@ -160,10 +159,8 @@ class LSHRS:
 
             return iter_parquet_vectors
         if normalized in {"postgres", "pg"}:
-            try:  # the PostgreSQL loader stays in the reference package, unchanged
-                from lshrs.io.postgres import iter_postgres_vectors  # type: ignore
-            except ImportError as exc:
-                raise ImportError("the PostgreSQL loader lives in the reference package (lshrs.io.postgres)") from exc
+            from lshrs_b200.io.postgres import iter_postgres_vectors
+
             return iter_postgres_vectors
         raise ValueError(f"Unsupported signature creation format '{format}'")
 

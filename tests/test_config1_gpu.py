@@ -78,9 +78,11 @@ def test_tensor_core_accumulators_against_fp64(kernel, n):
     good = margin > 0.01
     # per-row and per-column log2 scale from well-conditioned entries; they must be integers (exact powers of 2)
     lg_good = np.where(good, lg, np.nan)
-    col_ref = int(np.argmax(good.sum(axis=0)))
-    sx = np.rint(np.nanmedian(lg_good - lg_good[:, [col_ref]] , axis=1))    # relative to the reference column
-    base = np.rint(np.nanmedian(lg_good - sx[:, None], axis=0))             # per column (includes the reference)
+    assert good.sum(axis=1).min() >= 8 and good.sum(axis=0).min() >= 8      # every row / column has anchors
+    sx = np.rint(np.nanmedian(lg_good, axis=1))                             # alternate: rows given columns, ...
+    for _ in range(3):
+        base = np.rint(np.nanmedian(lg_good - sx[:, None], axis=0))         # ... columns given rows
+        sx = np.rint(np.nanmedian(lg_good - base[None, :], axis=1))
     scale = np.exp2(sx[:, None] + base[None, :])
     assert np.nanmax(np.abs(lg_good - np.log2(scale))) < 1e-3, "scales are not exact powers of two per row x column"
     if kernel != "tcgen05":
