@@ -4,25 +4,30 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One process per GPU; the work list is partitioned (weak scaling: every rank
-hashes its own resident shard of ``--rows`` vectors, 12.5 M = 100 M / 8 by
-default -- BASELINE.json config 2 at N = 8), the projection matrix is
-replicated, nothing is exchanged on the data path.  A "step" is one pass of the
-hot path over one resident shard: the projection kernel over every chunk of
-the shard plus the D2H of the signatures into pinned host memory, overlapped on
-a copy stream.  Timed with CUDA events on the launching stream, max over ranks.
+One process per GPU; the work list is partitioned (weak scaling: every rank hashes its own resident shard of
+``--rows`` vectors, 12.5 M = 100 M / 8 by default -- BASELINE.json config 2 at N = 8), the projection matrix is
+replicated, nothing is exchanged on the data path.  A "step" is one pass of the hot path over one resident shard:
+the projection kernel over every chunk of the shard plus the gather of the signatures into pinned host memory,
+overlapped on copy streams.  Timed with CUDA events on the launching stream, max over ranks.
+
+Multi-GPU (lshrs_b200/fabric.py): the host links of a box are not equal, so (a) a job on fewer GPUs than the box
+has takes the GPUs on the fastest links (rank 0 probes every visible GPU in a child process), and (b) every rank
+measures its own link with everybody copying and with only the faster half copying; when that pays, the ranks on
+slow links hand their signatures over NVLink (peer-to-peer copy engine, no NCCL) to a partner on a fast link that
+writes them into the sender's pinned host buffer.  The ``fabric`` block of the JSON line records the measured
+rates, the chosen plan and ``value`` as a fraction of what the measured links allow.
 
 The JSON line carries, beside the contract keys:
-  roofline      dominant (projection) kernel: executed tensor flops / its own
-                CUDA-event time inside the timed region vs the measured peak
-  e2e           same metric through the C ABI with HOST pinned buffers (H2D of
-                the vectors and D2H of the signatures inside the timed region)
-  cpu_baseline  the oracle port of the reference's numpy path timed on this
-                box's host cores on a bounded sample (rank 0, N = 1 only)
-  parity        band-key comparison of the GPU output with the oracle on that sample
-  rerank        config 4 (8192 queries x 2000 candidates x 768, k=10 and p=0.2)
-``--impl reference`` times the reference's CPU algorithm (oracle port; the
-reference is pure Python and cannot travel to the GPU box) on bounded samples.
+  roofline      dominant (projection) kernel: algorithmic flops / its own CUDA-event time inside the timed region
+  e2e           same metric through the C ABI with HOST pinned buffers (H2D of the vectors and D2H of the
+                signatures inside the timed region); at N > 1 the per-rank row counts follow the measured H2D rates
+  cpu_baseline  the reference's own LSHHasher.hash_batch (oracle/_ref/reference, staged by tools/make_ref.py; the
+                oracle port when it is not staged) timed on this box's host cores on a bounded sample (N = 1)
+  parity        band-key comparison of the GPU output with the CPU baseline's output on that sample
+  configs       BASELINE configs 3 and 5 (1536 -> 512 bits, SIFT-like 128 -> 64 bits): value, roofline, parity
+  rerank        config 4 (8192 queries x 2000 candidates x 768, k = 10 and p = 0.2)
+  fabric        measured host-link rates, device choice, relay plan (N > 1)
+``--impl reference`` times the reference's CPU implementation (same source as ``cpu_baseline``) on bounded samples.
 """
 
 from __future__ import annotations
@@ -41,38 +46,34 @@ import numpy as np
 REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
-DIM, NUM_BANDS, ROWS_PER_BAND, SEED = 768, 16, 16, 42
-NUM_PERM = NUM_BANDS * ROWS_PER_BAND
-SIG_BYTES = NUM_BANDS * ((ROWS_PER_BAND + 7) // 8)
-METRIC = "vectors hashed/sec (dim=768, num_perm=256)"
+T_PROCESS_START = time.time() - 2.0
+SEED = 42
 UNIT = "vectors/s"
-# BASELINE.json configs; "hash768" is the metric's configuration, the others are side measurements
+# BASELINE.json configs; "hash768" is the metric's configuration, the others ride along in `configs`
 WORKLOADS = {
     "hash768": dict(dim=768, bands=16, rows_per_band=16, rows=12_500_000, chunk=781_250, dist="gauss"),
     "hash1536": dict(dim=1536, bands=16, rows_per_band=32, rows=6_250_000, chunk=781_250, dist="gauss"),
     "hash128": dict(dim=128, bands=16, rows_per_band=4, rows=100_000_000, chunk=12_500_000, dist="sift"),
 }
-
-
-def select_workload(args) -> None:
-    global DIM, NUM_BANDS, ROWS_PER_BAND, NUM_PERM, SIG_BYTES, METRIC
-    w = WORKLOADS[args.workload]
-    DIM, NUM_BANDS, ROWS_PER_BAND = w["dim"], w["bands"], w["rows_per_band"]
-    NUM_PERM = NUM_BANDS * ROWS_PER_BAND
-    SIG_BYTES = NUM_BANDS * ((ROWS_PER_BAND + 7) // 8)
-    METRIC = f"vectors hashed/sec (dim={DIM}, num_perm={NUM_PERM})"
-    if args.rows is None:
-        args.rows = w["rows"]
-    if args.chunk is None:
-        args.chunk = w["chunk"]
-    args.chunk = min(args.chunk, args.rows)
-    args.e2e_rows = min(args.e2e_rows, args.rows)
-    args.dist = w["dist"]
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
-# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel PER ROW, from the ncu --set full
-# captures committed under profiles/ (r1_hash_tc_ncu.csv: 2.401 GB + 0.027 GB over 781 250 rows;
-# r1_hash_tc_dim128_ncu.csv: 6.400 GB + 0.201 GB over 12 500 000 rows); scaled to the rows of one launch
-ROOFLINE_TRAFFIC_PER_ROW = {("hash768", "tcgen05"): 2.428e9 / 781_250, ("hash128", "tcgen05"): 6.601e9 / 12_500_000}
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel PER ROW from the committed ncu --set full
+# captures (file, bytes per launch, rows per launch); scaled to the rows of one launch of the run
+NCU_TRAFFIC = {
+    "hash768": ("profiles/r1_hash_tc_ncu.csv", 2.428e9, 781_250),
+    "hash128": ("profiles/r1_hash_tc_dim128_ncu.csv", 6.601e9, 12_500_000),
+}
+
+
+class Shape:
+    """One hashing configuration (what LSHRS(dim=..., num_perm=...) auto-selects for the BASELINE shapes)."""
+
+    def __init__(self, name: str):
+        w = WORKLOADS[name]
+        self.name, self.dim, self.bands, self.rows_per_band = name, w["dim"], w["bands"], w["rows_per_band"]
+        self.num_perm = self.bands * self.rows_per_band
+        self.sig_bytes = self.bands * ((self.rows_per_band + 7) // 8)
+        self.rows, self.chunk, self.dist = w["rows"], w["chunk"], w["dist"]
+        self.metric = f"vectors hashed/sec (dim={self.dim}, num_perm={self.num_perm})"
 
 
 def log(*a):
@@ -92,35 +93,160 @@ def load_peaks() -> tuple[dict, str]:
     return dict(FALLBACK_PEAKS), "fallback"
 
 
-def bind_to_gpu_numa_node(device_index: int) -> str:
-    """Pin this rank to the CPUs next to its GPU before any pinned allocation (first-touch NUMA placement).
+def workload_config(args, shape: Shape) -> dict:
+    """The `config` object: identical for the b200 and the reference arm (the CPU arm's sample size is stated in
+    its cpu_baseline.sample, not here)."""
+    return {
+        "workload": f"LSHHasher dim={shape.dim} num_perm={shape.num_perm} ({shape.bands}x{shape.rows_per_band}); "
+                    f"{args.rows} synthetic {'Gaussian' if shape.dist == 'gauss' else 'SIFT-like non-negative'} "
+                    f"float32 vectors resident per GPU"
+                    + (" (BASELINE config 2: 100M vectors / 8 GPUs = 12.5M per GPU, weak scaling)"
+                       if shape.name == "hash768" else f" (BASELINE config '{shape.name}')"),
+        "rows_per_gpu": args.rows, "dim": shape.dim, "num_perm": shape.num_perm, "signature_bytes": shape.sig_bytes,
+        "chunk_rows": args.chunk, "e2e_rows_per_gpu": args.e2e_rows,
+        "l2": f"inputs larger than L2 ({args.rows * shape.dim * 4 / 1e9:.0f} GB resident shard, each row read once per step)",
+        "parallelism": f"row-sharded x{args.gpus}, projections replicated, no collective",
+    }
 
-    With 8 ranks each streaming signatures D2H and vectors H2D, pinned buffers on the wrong socket turn
-    the host fabric into the bottleneck.  Best effort: returns a description for the JSON line.
+
+# --------------------------------------------------------------------------------------
+# the CPU side: the reference itself when it is staged (oracle/_ref/reference), else the oracle port
+# --------------------------------------------------------------------------------------
+
+class CpuReference:
+    """The reference's CPU implementation of the path, as shipped.
+
+    ``kind == "reference"``: the unmodified mxngjxa/lshrs package staged by tools/make_ref.py under the
+    git-ignored oracle/_ref/reference (it travels to the GPU box with the snapshot; /root/reference does not
+    exist there), imported with the stub ``redis`` module beside it.  ``kind == "port"``: oracle/lshrs_oracle.py,
+    the numpy restatement pinned to the reference's outputs (tests/golden), when nothing is staged.
     """
-    try:
-        import torch
 
-        props = torch.cuda.get_device_properties(device_index)
-        bdf = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
-        base = Path("/sys/bus/pci/devices") / bdf
-        node = int((base / "numa_node").read_text().strip())
-        cpulist = (base / "local_cpulist").read_text().strip()
-        cpus: set[int] = set()
-        for part in cpulist.split(","):
-            if "-" in part:
-                a, b = part.split("-")
-                cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
-        allowed = os.sched_getaffinity(0)
-        cpus &= allowed
-        if node < 0 or not cpus or cpus == allowed:
-            return f"unchanged (gpu {bdf} numa_node={node}, local_cpulist={cpulist})"
-        os.sched_setaffinity(0, cpus)
-        return f"numa node {node} (gpu {bdf}, cpus {cpulist})"
+    def __init__(self):
+        ref = REPO / "oracle" / "_ref"
+        self.kind = "port"
+        if (ref / "reference" / "lshrs" / "hash" / "lsh.py").exists():
+            try:
+                sys.path[:0] = [str(ref / "reference"), str(ref / "stubs")]
+                from lshrs.hash.lsh import LSHHasher as RefHasher
+                from lshrs.utils.similarity import top_k_cosine as ref_topk
+
+                self._hasher_cls, self._topk, self.kind = RefHasher, ref_topk, "reference"
+            except Exception as exc:  # noqa: BLE001
+                log(f"staged reference not importable ({exc!r}); using the oracle port")
+                sys.path[:] = [p for p in sys.path if not p.startswith(str(ref))]
+        from oracle import lshrs_oracle as oracle
+
+        self.oracle = oracle
+        self.source = ("oracle/_ref/reference/lshrs (unmodified reference, tools/make_ref.py)" if self.kind == "reference"
+                       else "oracle/lshrs_oracle.py (numpy restatement pinned to tests/golden)")
+
+    def hasher(self, shape: Shape):
+        if self.kind == "reference":
+            h = self._hasher_cls(num_bands=shape.bands, rows_per_band=shape.rows_per_band, dim=shape.dim, seed=SEED)
+            return h, h.projections
+        projs = self.oracle.make_projections(shape.bands, shape.rows_per_band, shape.dim, SEED)
+        return None, projs
+
+    def hash_batch(self, h, projs, X):
+        """What the reference does: LSHHasher.hash_batch (one hash_vector per row, one sgemv per band)."""
+        if h is not None:
+            return h.hash_batch(X)
+        return self.oracle.hash_batch(projs, X)
+
+    @staticmethod
+    def packed(sigs, shape: Shape) -> np.ndarray:
+        bpb = (shape.rows_per_band + 7) // 8
+        flat = b"".join(b for s in sigs for b in s)
+        return np.frombuffer(flat, dtype=np.uint8).reshape(len(sigs), shape.bands, bpb)
+
+    def top_k_cosine(self, q, C, k):
+        if self.kind == "reference":
+            return self._topk(q, C, k=k)
+        return self.oracle.top_k_cosine(q, C, k=k)
+
+
+def cpu_hash_sample(shape: Shape, rows: int, seed: int = 0) -> np.ndarray:
+    return np.random.default_rng(seed).standard_normal((rows, shape.dim)).astype(np.float32)
+
+
+def _mp_hash_worker(job):
+    seed, rows = job
+    shape = Shape("hash768")
+    cpu = CpuReference()
+    h, projs = cpu.hasher(shape)
+    X = cpu_hash_sample(shape, rows, seed=seed)
+    t0 = time.perf_counter()
+    cpu.hash_batch(h, projs, X)
+    return time.perf_counter() - t0
+
+
+def multiprocess_rate(rows_per_worker: int = 4096) -> dict:
+    """The same per-vector loop sharded over every host core with one process each -- NOT something the
+    reference does (its API is one Python thread), printed so the single-thread figure is not the only one."""
+    import multiprocessing as mp
+
+    workers = len(os.sched_getaffinity(0))
+    try:
+        ctx = mp.get_context("fork")
+        t0 = time.perf_counter()
+        with ctx.Pool(workers) as pool:
+            pool.map(_mp_hash_worker, [(100 + i, rows_per_worker) for i in range(workers)])
+        wall = time.perf_counter() - t0
+        return {"value": workers * rows_per_worker / wall, "unit": UNIT, "cores": workers,
+                "sample": f"{workers} processes x {rows_per_worker} rows, wall clock incl. process start"}
     except Exception as exc:  # noqa: BLE001
-        return f"unchanged ({type(exc).__name__}: {exc})"
+        return {"value": None, "unit": UNIT, "cores": workers, "error": f"{type(exc).__name__}: {exc}"}
+
+
+def run_reference(args, shape: Shape) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    cpu = CpuReference()
+    h, projs = cpu.hasher(shape)
+    sample = 16384
+    X = cpu_hash_sample(shape, sample)
+    for _ in range(args.warmup):
+        cpu.hash_batch(h, projs, X[:1024])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.hash_batch(h, projs, X)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    # not reference code: one sgemm + packbits over every BLAS thread, for honesty (torchrun exports
+    # OMP_NUM_THREADS=1, so the BLAS pool is widened explicitly when threadpoolctl is there)
+    Xv = cpu_hash_sample(shape, 131072, seed=1)
+    try:
+        from threadpoolctl import threadpool_limits
+
+        blas_threads = threadpool_limits(limits=len(os.sched_getaffinity(0)))
+    except Exception:  # noqa: BLE001
+        blas_threads = None
+    cpu.oracle.hash_batch_vectorized(projs, Xv[:4096])
+    t1 = time.perf_counter()
+    cpu.oracle.hash_batch_vectorized(projs, Xv)
+    vec_value = Xv.shape[0] / (time.perf_counter() - t1)
+    if blas_threads is not None:
+        blas_threads.restore_original_limits()
+    line = {
+        "impl": "reference", "metric": shape.metric, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, shape),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": cpu.kind, "source": cpu.source,
+                         "sample": f"{sample} Gaussian vectors of the config's shape per step x {args.steps} steps "
+                                   "through LSHHasher.hash_batch -- per-vector, per-band sgemv, a single Python "
+                                   "thread by construction (reference lshrs/hash/lsh.py:169); a rate, so the "
+                                   "bounded sample stands for the config's 12.5 M rows per GPU",
+                         "sample_rows_per_step": sample, "host_cores": os.cpu_count(), "numpy": np.__version__,
+                         "vectorized_numpy_not_reference": {"value": vec_value, "unit": UNIT,
+                                                            "cores": len(os.sched_getaffinity(0))},
+                         "multiprocess_not_reference": multiprocess_rate()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    emit(line)
 
 
 class ClockSampler:
@@ -179,134 +305,216 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-# --------------------------------------------------------------------------------------
-# reference arm: the reference's CPU algorithm (oracle port) on this box's host cores
-# --------------------------------------------------------------------------------------
-
-def cpu_hash_sample(rows: int, seed: int = 0) -> np.ndarray:
-    x = np.random.default_rng(seed).standard_normal((rows, DIM)).astype(np.float32)
-    return x  # the reference arm always runs the metric's configuration (Gaussian, dim 768)
-
-
-def _mp_hash_worker(job):
-    from oracle import lshrs_oracle as oracle
-
-    seed, rows = job
-    projs = oracle.make_projections(NUM_BANDS, ROWS_PER_BAND, DIM, SEED)
-    X = cpu_hash_sample(rows, seed=seed)
-    t0 = time.perf_counter()
-    oracle.hash_batch_packed(projs, X)
-    return time.perf_counter() - t0
-
-
-def multiprocess_port_rate(rows_per_worker: int = 4096) -> dict:
-    """The same per-vector loop sharded over every host core with one process each -- NOT something the
-    reference does (its API is one Python thread), printed so the single-thread figure is not the only one."""
-    import multiprocessing as mp
-
-    workers = len(os.sched_getaffinity(0))
-    try:
-        ctx = mp.get_context("fork")
-        t0 = time.perf_counter()
-        with ctx.Pool(workers) as pool:
-            pool.map(_mp_hash_worker, [(100 + i, rows_per_worker) for i in range(workers)])
-        wall = time.perf_counter() - t0
-        return {"value": workers * rows_per_worker / wall, "unit": UNIT, "cores": workers,
-                "sample": f"{workers} processes x {rows_per_worker} rows, wall clock incl. process start"}
-    except Exception as exc:  # noqa: BLE001
-        return {"value": None, "unit": UNIT, "cores": workers, "error": f"{type(exc).__name__}: {exc}"}
-
-
-def run_reference(args) -> None:
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return  # rank 0 alone runs the CPU arm
-    from oracle import lshrs_oracle as oracle
-
-    projs = oracle.make_projections(NUM_BANDS, ROWS_PER_BAND, DIM, SEED)
-    sample = 16384
-    X = cpu_hash_sample(sample)
-    for _ in range(args.warmup):
-        oracle.hash_batch_packed(projs, X[:1024])
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        oracle.hash_batch_packed(projs, X)
-    dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
-    # not reference code: one sgemm + packbits over every BLAS thread, for honesty (torchrun exports
-    # OMP_NUM_THREADS=1, so the BLAS pool is widened explicitly when threadpoolctl is there)
-    Xv = cpu_hash_sample(131072, seed=1)
-    try:
-        from threadpoolctl import threadpool_limits
-
-        blas_threads = threadpool_limits(limits=len(os.sched_getaffinity(0)))
-    except Exception:  # noqa: BLE001
-        blas_threads = None
-    oracle.hash_batch_vectorized(projs, Xv[:4096])
-    t1 = time.perf_counter()
-    oracle.hash_batch_vectorized(projs, Xv)
-    vec_value = Xv.shape[0] / (time.perf_counter() - t1)
-    if blas_threads is not None:
-        blas_threads.restore_original_limits()
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{sample} Gaussian vectors x {args.steps} steps through the oracle's "
-                                   "per-vector, per-band sgemv loop (the reference's LSHHasher.hash_batch path; "
-                                   "single Python thread by construction)",
-                         "host_cores": os.cpu_count(), "numpy": np.__version__,
-                         "vectorized_numpy_not_reference": {"value": vec_value, "unit": UNIT,
-                                                            "cores": len(os.sched_getaffinity(0))},
-                         "multiprocess_port_not_reference": multiprocess_port_rate()},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    emit(line)
-
-
-def workload_config(args) -> dict:
-    return {
-        "workload": f"LSHHasher dim={DIM} num_perm={NUM_PERM} ({NUM_BANDS}x{ROWS_PER_BAND}); "
-                    f"{args.rows} synthetic {'Gaussian' if args.dist == 'gauss' else 'SIFT-like non-negative'} "
-                    f"float32 vectors resident per GPU"
-                    + (" (BASELINE config 2: 100M vectors / 8 GPUs = 12.5M per GPU, weak scaling)"
-                       if args.workload == "hash768" else f" (BASELINE config '{args.workload}', side measurement)"),
-        "rows_per_gpu": args.rows, "dim": DIM, "num_perm": NUM_PERM, "signature_bytes": SIG_BYTES,
-        "chunk_rows": args.chunk, "e2e_rows_per_gpu": args.e2e_rows,
-        "l2": f"inputs larger than L2 ({args.rows * DIM * 4 / 1e9:.0f} GB resident shard, each row read once per step)",
-        "parallelism": f"row-sharded x{args.gpus}, projections replicated, no collective",
-        "cpu_affinity_rank0": getattr(args, "cpu_affinity", None),
-    }
-
 
 # --------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------
 
-def run_b200(args) -> None:
+def make_shard(torch, dev, shape: Shape, rows: int, seed: int):
+    """The resident shard, generated on the device (seeded per rank): Gaussian, or SIFT-like non-negative
+    integer-valued floats in [0, 255] for the 128-dimensional configuration."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    X = torch.empty((rows, shape.dim), dtype=torch.float32, device=dev)
+    for r0 in range(0, rows, 1 << 20):
+        r1 = min(rows, r0 + (1 << 20))
+        X[r0:r1].normal_(generator=gen)
+        if shape.dist == "sift":
+            X[r0:r1].abs_().mul_(40.0).floor_().clamp_(max=255.0)
+    return X
+
+
+class ResidentRun:
+    """One rank's pass over its resident shard: the projection kernel per chunk on `compute`, the gather of each
+    chunk's signatures into pinned host memory on a copy stream (double-buffered) -- or, for a rank on a slow
+    host link, into its partner's device slot over NVLink (fabric.RelaySender); a partner rank also drains the
+    sender's chunks into the sender's host buffer (fabric.RelayReceiver)."""
+
+    def __init__(self, torch, dev, hasher, X, shape: Shape, chunk: int, out_host):
+        self.torch, self.dev, self.hasher, self.X, self.shape = torch, dev, hasher, X, shape
+        rows = X.shape[0]
+        self.rows = rows
+        self.chunks = [(r0, min(rows, r0 + chunk)) for r0 in range(0, rows, chunk)]
+        self.out_host = out_host
+        self.out_dev = [torch.empty((chunk, shape.sig_bytes), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.compute = torch.cuda.Stream(device=dev)
+        self.copy = torch.cuda.Stream(device=dev)
+        self.copied = [None, None]   # per output slot: the event after which it may be overwritten
+        self.sender = None
+        self.receiver = None
+        self.k = 0                   # relayed chunks issued so far (both partners count alike)
+
+    def one_step(self, kernel_events=None):
+        """Steps stream into each other: the gather of a step's last chunks overlaps the next step's first
+        kernels; the timed region ends only after every signature is in host memory (drain())."""
+        torch, compute, sig = self.torch, self.compute, self.shape.sig_bytes
+        for ci, (r0, r1) in enumerate(self.chunks):
+            slot = ci & 1
+            if self.copied[slot] is not None:
+                compute.wait_event(self.copied[slot])
+            if kernel_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(compute)
+            self.hasher.hash_into(self.X[r0:r1], r1 - r0, self.out_dev[slot], x_on_device=True, out_on_device=True,
+                                  stream=compute.cuda_stream)
+            if kernel_events is not None:
+                e1.record(compute)
+                kernel_events.append((e0, e1, r1 - r0))
+            done = torch.cuda.Event()
+            done.record(compute)
+            if self.sender is not None:
+                self.copied[slot] = self.sender.send(self.k, self.out_dev[slot][: r1 - r0], done)
+            else:
+                self.copy.wait_event(done)
+                with torch.cuda.stream(self.copy):
+                    self.out_host[r0:r1].copy_(self.out_dev[slot][: r1 - r0], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy)
+                self.copied[slot] = ev
+            if self.receiver is not None:
+                self.receiver.drain(self.k, (r1 - r0) * sig, r0 * sig)
+            if self.sender is not None or self.receiver is not None:
+                self.k += 1
+
+    def drain(self):
+        self.compute.wait_stream(self.copy)
+        if self.sender is not None:
+            self.compute.wait_stream(self.sender.stream)
+        if self.receiver is not None:
+            self.compute.wait_stream(self.receiver.stream)
+
+
+def roofline_block(shape: Shape, kernel_name: str, kern_ms: float, kern_rows: int, n_events: int, step_ms: float,
+                   peaks: dict, peak_src: str) -> dict:
+    """ALGORITHMIC flops (2*dim*num_perm per vector) and bytes (4*dim + signature bytes) over
+    the kernel's own CUDA-event time, against the measured ceilings.  Tensor ceiling: the measured dense TF32 rate
+    (= bf16_tflops_sustained / 2) divided by the tensor-time units the operand split spends per logical product
+    (3 for 3xTF32, 2 for TF32 + BF16 cross terms, 1.5 for the default scaled FP16x3).  The slower ceiling is the
+    bound."""
+    ncols = shape.sig_bytes * 8
+    useful_flop = 2.0 * shape.dim * shape.num_perm
+    mma_passes = {"tcgen05": 1.5, "tcgen05_tf32bf16": 2, "tcgen05_3xtf32": 3}.get(kernel_name, 1)
+    is_tc = kernel_name.startswith("tcgen05")
+    n_events = max(1, n_events)
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    split_units = {"tcgen05_3xtf32": 3.0, "tcgen05_tf32bf16": 2.0}.get(kernel_name, 1.5)
+    useful_peak = tf32_peak / split_units
+    achieved_tflops = useful_flop * kern_rows / (kern_ms * 1e-3) / 1e12
+    ncols_exec = (shape.num_perm + 15) // 16 * 16 if shape.rows_per_band % 8 else (ncols + 127) // 128 * 128
+    if not is_tc:
+        ncols_exec = (ncols + 127) // 128 * 128
+    executed_tflops = 2.0 * shape.dim * ncols_exec * mma_passes * kern_rows / (kern_ms * 1e-3) / 1e12
+    bytes_per_vec = 4.0 * shape.dim + shape.sig_bytes
+    hbm_gbs = bytes_per_vec * kern_rows / (kern_ms * 1e-3) / 1e9
+    tensor_frac, hbm_frac = achieved_tflops / useful_peak, hbm_gbs / peaks["hbm_gbs"]
+    traffic, traffic_src = None, None
+    if is_tc and kernel_name == "tcgen05" and shape.name in NCU_TRAFFIC:
+        f, per_launch, rows_per_launch = NCU_TRAFFIC[shape.name]
+        traffic = per_launch / rows_per_launch * kern_rows / n_events
+        traffic_src = f"{f}: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture, scaled by rows"
+    common = {
+        "kernel": f"hash_{kernel_name}", "traffic": traffic, "traffic_source": traffic_src,
+        "avg_launch_ms": kern_ms / n_events, "launches_timed": n_events,
+        "kernel_share_of_step": kern_ms / step_ms if step_ms else None,
+        "algorithmic_bytes_per_launch": bytes_per_vec * kern_rows / n_events,
+        "algorithmic_flops_per_launch": useful_flop * kern_rows / n_events,
+        "tensor": {"achieved_tflops": achieved_tflops, "peak_tflops": useful_peak, "frac": tensor_frac,
+                   "peak_source": f"{peak_src}: bf16_tflops_sustained / 2 (dense TF32) / {split_units:g} tensor-time "
+                                  "units per logical product of the operand split (3xTF32: 3; TF32 hi.hi + BF16 "
+                                  "cross terms: 2; scaled FP16x3: 1.5)",
+                   "flops_counted": "algorithmic: 2*dim*num_perm per vector",
+                   "executed_tflops": executed_tflops, "executed_vs_tf32_peak": executed_tflops / tf32_peak,
+                   "fp32_pipe_nominal_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},
+        "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": hbm_frac, "peak_source": peak_src,
+                "bytes_per_vector": bytes_per_vec},
+    }
+    if tensor_frac >= hbm_frac:  # the slower of the two ceilings is the bound
+        return {"bound": "tensor", "achieved": achieved_tflops, "peak": useful_peak, "unit": "TFLOP/s",
+                "frac": tensor_frac, **common}
+    return {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_frac, **common}
+
+
+def link_rate(torch, dev, direction: str, active: bool, barrier, mbytes: int = 256, chunk_mb: int = 25) -> float:
+    """This rank's D2H / H2D GB/s while every `active` rank copies at once (0.0 for a rank that sits out)."""
+    nbytes, chunk = mbytes << 20, chunk_mb << 20
+    if active:
+        d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        h = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        s = torch.cuda.Stream(dev)
+    best = 0.0
+    for rep in range(3):
+        barrier()
+        if not active:
+            continue
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s):
+            for o in range(0, nbytes, chunk):
+                if direction == "d2h":
+                    h[o:o + chunk].copy_(d[o:o + chunk], non_blocking=True)
+                else:
+                    d[o:o + chunk].copy_(h[o:o + chunk], non_blocking=True)
+        s.synchronize()
+        if rep:
+            best = max(best, nbytes / (time.perf_counter() - t0) / 1e9)
+    barrier()
+    return best
+
+
+def run_b200(args, shape: Shape) -> None:
     import torch
     import torch.distributed as dist
 
-    from lshrs_b200 import LSHHasher, _native
+    from lshrs_b200 import LSHHasher, _native, fabric
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    visible = torch.cuda.device_count()
+    fab: dict = {"visible_gpus": visible}
+
+    # ---- which GPU does this rank take?  (fewer ranks than GPUs: the ones on the fastest host links) ----------
+    device_index = local
+    if not args.no_fabric and world < visible:
+        # rank 0 measures every visible GPU's host link in a child process and leaves the result in /dev/shm; the
+        # other ranks (which must not touch CUDA before they know their GPU) wait for a file newer than themselves
+        probe_path = Path(f"/dev/shm/lshx_probe_{os.environ.get('MASTER_PORT', '0')}.json")
+        box = None
+        if rank == 0:
+            box = fabric.probe_links_subprocess()
+            tmp = probe_path.with_suffix(".tmp")
+            tmp.write_text(json.dumps({"probe": box, "world": world}))
+            os.replace(tmp, probe_path)
+        else:
+            deadline = time.time() + 240
+            while time.time() < deadline:
+                try:
+                    if probe_path.stat().st_mtime >= T_PROCESS_START:
+                        got = json.loads(probe_path.read_text())
+                        if got.get("world") == world:
+                            box = got["probe"]
+                            break
+                except (OSError, ValueError):
+                    pass
+                time.sleep(0.05)
+        devices = fabric.choose_devices(box, world, visible)
+        device_index = devices[local] if local < len(devices) else local
+        fab.update(box_probe=box, devices=devices,
+                   device_choice="the GPUs with the fastest D2H links while every visible GPU copies")
+    else:
+        fab.update(devices=list(range(world)), device_choice="identity (every visible GPU is used)" if world >= visible
+                   else "identity (--no-fabric)")
+    torch.cuda.set_device(device_index)
+    dev = torch.device("cuda", device_index)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    args.cpu_affinity = bind_to_gpu_numa_node(local)
-    log(f"[rank {rank}] cpu affinity: {args.cpu_affinity}")
+        # NCCL for the barrier and the MAX-reduction of the measured time, gloo for the small Python objects of
+        # the set-up (link rates, relay handles); nothing of either is on the data path
+        dist.init_process_group("cpu:gloo,cuda:nccl")
+    log(f"[rank {rank}] cuda:{device_index} of {visible} visible")
     peaks, peak_src = load_peaks()
 
     def barrier():
         if world > 1:
-            dist.barrier()
+            dist.barrier(device_ids=[device_index])
         torch.cuda.synchronize()
 
     def max_ranks(x: float) -> float:
@@ -316,74 +524,108 @@ def run_b200(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    hasher = LSHHasher(NUM_BANDS, ROWS_PER_BAND, DIM, seed=SEED, device=local)
+    def gather_obj(x):
+        if world == 1:
+            return [x]
+        out = [None] * world
+        dist.all_gather_object(out, x)
+        return out
+
+    hasher = LSHHasher(shape.bands, shape.rows_per_band, shape.dim, seed=SEED, device=device_index)
     if args.kernel != "auto":
         hasher._ensure_handle()
         hasher.set_kernel(args.kernel)
 
-    # ---- resident shard, generated on device (seeded per rank) --------------------------
+    # ---- resident shard + host buffer ---------------------------------------------------------------------
     rows, chunk = args.rows, args.chunk
-    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    X = torch.empty((rows, DIM), dtype=torch.float32, device=dev)
-    for r0 in range(0, rows, 1 << 20):
-        r1 = min(rows, r0 + (1 << 20))
-        X[r0:r1].normal_(generator=gen)
-        if args.dist == "sift":  # SIFT-like: non-negative integer-valued floats in [0, 255]
-            X[r0:r1].abs_().mul_(40.0).floor_().clamp_(max=255.0)
-    out_host = torch.empty((rows, SIG_BYTES), dtype=torch.uint8, pin_memory=True)
-    out_dev = [torch.empty((chunk, SIG_BYTES), dtype=torch.uint8, device=dev) for _ in range(2)]
-    chunks = [(r0, min(rows, r0 + chunk)) for r0 in range(0, rows, chunk)]
-    compute = torch.cuda.Stream(device=dev)
-    copy = torch.cuda.Stream(device=dev)
+    X = make_shard(torch, dev, shape, rows, 1000 + rank)
+    shm = None
+    if world > 1 and not args.no_fabric:
+        # POSIX shared memory, pinned: a partner rank may write this rank's signatures over ITS PCIe link
+        shm = fabric.SharedHostBuffer(f"lshx_sig_{os.environ.get('MASTER_PORT', '0')}_{rank}", rows * shape.sig_bytes,
+                                      create=True)
+        out_host = shm.pin().view(rows, shape.sig_bytes)
+    else:
+        out_host = torch.empty((rows, shape.sig_bytes), dtype=torch.uint8, pin_memory=True)
+    run = ResidentRun(torch, dev, hasher, X, shape, chunk, out_host)
 
-    copied = [None, None]   # per output slot: the event of its last D2H (persists across steps)
-
-    def one_step(kernel_events=None):
-        """Hash every chunk on `compute`, D2H each chunk's signatures on `copy` (double-buffered).
-
-        Steps stream into each other: the D2H of a step's last chunks overlaps the next step's first
-        kernels; the timed region ends only after every copy has landed (drain())."""
-        for ci, (r0, r1) in enumerate(chunks):
-            slot = ci & 1
-            if copied[slot] is not None:
-                compute.wait_event(copied[slot])  # out_dev[slot] is free again
-            if kernel_events is not None:
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(compute)
-            hasher.hash_into(X[r0:r1], r1 - r0, out_dev[slot], x_on_device=True, out_on_device=True,
-                             stream=compute.cuda_stream)
-            done = torch.cuda.Event()
-            if kernel_events is not None:
-                e1.record(compute)
-                kernel_events.append((e0, e1, r1 - r0))
-            done.record(compute)
-            copy.wait_event(done)
-            with torch.cuda.stream(copy):
-                out_host[r0:r1].copy_(out_dev[slot][: r1 - r0], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy)
-            copied[slot] = ev
-
-    def drain():
-        compute.wait_stream(copy)
-
+    kev: list = []
     for _ in range(args.warmup):
-        one_step()
-    drain()
+        run.one_step(kev)
+    run.drain()
     barrier()
+    warm_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in kev)
+    warm_rows = sum(r for _, _, r in kev)
+    kernel_gbs = shape.sig_bytes * warm_rows / (warm_ms * 1e-3) / 1e9     # signature bytes one GPU produces per s
+
+    # ---- host links: measured, then the gather plan ------------------------------------------------------------
+    plan = {"policy": "direct", "pairs": {}}
+    if world > 1 and not args.no_fabric:
+        d2h_all = gather_obj(link_rate(torch, dev, "d2h", True, barrier))
+        h2d_all = gather_obj(link_rate(torch, dev, "h2d", True, barrier))
+        order = sorted(range(world), key=lambda r: (-d2h_all[r], r))
+        writers = set(order[: world // 2])
+        d2h_writers = gather_obj(link_rate(torch, dev, "d2h", rank in writers, barrier))
+        plan = fabric.plan_relay(d2h_all, d2h_writers, kernel_gbs)
+        if args.relay == "off":
+            plan.update(policy="direct", pairs={}, forced="--relay off")
+        elif args.relay == "force" and world % 2 == 0 and plan["policy"] != "relay":
+            half = world // 2                          # bring-up / tests: relay even where it does not pay
+            plan.update(policy="relay", pairs={int(s): int(w) for s, w in zip(order[half:][::-1], order[:half])},
+                        writers=sorted(order[:half]), forced="--relay force")
+        fab.update(d2h_gbs_all_ranks_copying=[round(x, 2) for x in d2h_all],
+                   h2d_gbs_all_ranks_copying=[round(x, 2) for x in h2d_all],
+                   d2h_gbs_fast_half_copying=[round(x, 2) for x in d2h_writers],
+                   signature_gbs_one_gpu_produces=round(kernel_gbs, 2), plan=plan)
+        if plan["policy"] == "relay":
+            pairs = {int(s): int(w) for s, w in plan["pairs"].items()}
+            tag = f"{os.environ.get('MASTER_PORT', '0')}_{rank}"
+            mine, err = None, None
+            try:
+                if rank in pairs.values():
+                    run.receiver = fabric.RelayReceiver(dev, chunk * shape.sig_bytes, tag)
+                    mine = ("receiver", run.receiver.export())
+                elif rank in pairs:
+                    run.sender = fabric.RelaySender(dev, shm, tag)
+                    mine = ("sender", run.sender.export())
+            except Exception as exc:  # noqa: BLE001
+                err = repr(exc)
+            everyone = gather_obj((mine, err))
+            if not any(e for _, e in everyone):
+                try:
+                    if run.receiver is not None:
+                        partner = [s for s, w in pairs.items() if w == rank][0]
+                        run.receiver.attach(everyone[partner][0][1])
+                    if run.sender is not None:
+                        run.sender.attach(everyone[pairs[rank]][0][1])
+                except Exception as exc:  # noqa: BLE001
+                    err = repr(exc)
+            errors = [e for e in gather_obj(err) if e] + [e for _, e in everyone if e]
+            if errors:
+                # every rank falls back together: a relay that cannot be set up must not take the headline down
+                log(f"[rank {rank}] relay set-up failed somewhere ({errors[0]}); gathering directly")
+                run.sender = run.receiver = None
+                plan.update(policy="direct", pairs={}, relay_error=errors[0])
+            else:
+                barrier()
+                for _ in range(args.warmup):          # warm the relayed path (peer access, IPC mappings)
+                    run.one_step()
+                run.drain()
+                barrier()
+
     def timed_region():
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(device_index)
         if rank == 0:
             sampler.start()
         launches0 = _native.launch_count()
         events: list = []
         t_start = torch.cuda.Event(enable_timing=True); t_stop = torch.cuda.Event(enable_timing=True)
         barrier()
-        t_start.record(compute)
+        t_start.record(run.compute)
         for _ in range(args.steps):
-            one_step(events)
-        drain()                      # every signature of every step is in host memory before the clock stops
-        t_stop.record(compute)
+            run.one_step(events)
+        run.drain()                  # every signature of every step is in host memory before the clock stops
+        t_stop.record(run.compute)
         barrier()
         return (t_start, t_stop, events, _native.launch_count() - launches0,
                 sampler.stop() if rank == 0 else None)
@@ -391,28 +633,56 @@ def run_b200(args) -> None:
     start, stop, kernel_events, launches, clocks = timed_region()
     # a run that saw a hardware / thermal slowdown is rejected and taken again, once
     bad = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    redo = torch.tensor([1 if (clocks and bad & set(clocks.get("reasons", []))) else 0], device=dev)
+    redo = [bool(clocks and bad & set(clocks.get("reasons", [])))]
     if world > 1:
-        dist.broadcast(redo, src=0)
-    remeasured = bool(redo.item())
+        dist.broadcast_object_list(redo, src=0)
+    remeasured = bool(redo[0])
     if remeasured:
         log(f"[rank {rank}] clocks show {clocks and clocks.get('reasons')}: measuring the timed region again")
         start, stop, kernel_events, launches, clocks = timed_region()
     if clocks is not None:
         clocks["remeasured"] = remeasured
-    elapsed_ms = max_ranks(start.elapsed_time(stop))
+    my_ms = start.elapsed_time(stop)
+    elapsed_ms = max_ranks(my_ms)
     kern_ms = sum(e0.elapsed_time(e1) for e0, e1, _ in kernel_events)
     kern_rows = sum(r for _, _, r in kernel_events)
     value = rows * world * args.steps / (elapsed_ms * 1e-3)
     kernel_name = hasher.last_kernel
-    # the same job without the D2H gather: signatures left in HBM (sum of the kernels' own durations)
+    # the same job without the gather: signatures left in HBM (sum of the kernels' own durations)
     kernel_only_value = rows * world * args.steps / (max_ranks(kern_ms) * 1e-3)
 
-    # ---- e2e: host pinned buffers through the C ABI (H2D + kernel + D2H per step) --------
+    # every rank: the gathered bytes of its first and last chunk equal a direct recomputation of those chunks
+    if world > 1:
+        ok = True
+        for r0, r1 in (run.chunks[0], run.chunks[-1]):
+            fresh = hasher.hash_device(X[r0:r1]).reshape(r1 - r0, shape.sig_bytes).cpu()
+            ok = ok and bool(torch.equal(fresh, out_host[r0:r1]))
+        checks = gather_obj(ok)
+        per_rank_ms = gather_obj(round(my_ms / args.steps, 3))
+        total_gbs = shape.sig_bytes * rows * world * args.steps / (elapsed_ms * 1e-3) / 1e9
+        per_rank_link = plan.get("per_rank_gbs", {}).get(plan["policy"]) if plan.get("per_rank_gbs") else None
+        ceiling = None
+        if per_rank_link:
+            ceiling = min(per_rank_link, kernel_gbs) * world / shape.sig_bytes * 1e9
+        fab.update(gather_check_all_ranks=bool(all(checks)), ms_per_step_per_rank=per_rank_ms,
+                   gathered_gbs_all_ranks=round(total_gbs, 1),
+                   ceiling_value=ceiling, value_frac_of_ceiling=(value / ceiling) if ceiling else None,
+                   ceiling_note="world x min(measured per-rank link rate under the chosen plan, rate at which one "
+                                "GPU produces signatures) / signature bytes")
+
+    # ---- e2e: host pinned buffers through the C ABI (H2D + kernel + D2H per step) --------------------------------
     e2e_rows = args.e2e_rows
-    xh = torch.empty((e2e_rows, DIM), dtype=torch.float32, pin_memory=True)
-    xh.copy_(X[:e2e_rows])
-    oh = torch.empty((e2e_rows, SIG_BYTES), dtype=torch.uint8, pin_memory=True)
+    e2e_split = None
+    if world > 1 and not args.no_fabric:
+        # the vectors cross PCIe host -> device here: shards sized to each rank's measured H2D rate
+        e2e_split = fabric.weighted_rows(args.e2e_rows * world, fab["h2d_gbs_all_ranks_copying"])
+        e2e_rows = e2e_split[rank]
+    xh = torch.empty((e2e_rows, shape.dim), dtype=torch.float32, pin_memory=True)
+    take = min(e2e_rows, rows)
+    xh[:take].copy_(X[:take])
+    if take < e2e_rows:
+        xh[take:].copy_(X[: e2e_rows - take])
+    oh = torch.empty((e2e_rows, shape.sig_bytes), dtype=torch.uint8, pin_memory=True)
     torch.cuda.synchronize()
 
     def e2e_step():
@@ -429,33 +699,33 @@ def run_b200(args) -> None:
     t2.record()
     barrier()
     e2e_ms = max_ranks(s2.elapsed_time(t2))
-    e2e_value = e2e_rows * world * e2e_steps / (e2e_ms * 1e-3)
+    e2e_total_rows = sum(e2e_split) if e2e_split else e2e_rows * world
+    e2e_value = e2e_total_rows * e2e_steps / (e2e_ms * 1e-3)
     # the e2e path must produce the same bytes as the resident path
-    same = bool(torch.equal(oh, out_host[:e2e_rows]))
-    # the same call on an ordinary (pageable) numpy array: pinned bounce buffers + parallel memcpy in the library
-    pageable_value = None
+    same = bool(torch.equal(oh[:take], out_host[:take]))
+    pageable_value = f16_value = None
     if not args.no_e2e:
-        xp, op = xh.numpy().copy(), np.empty((e2e_rows, SIG_BYTES), dtype=np.uint8)
-        hasher.hash_into(xp, e2e_rows, op, x_on_device=False, out_on_device=False)
+        # the same call on an ordinary (pageable) numpy array: pinned bounce buffers + parallel memcpy in the library
+        pr = min(e2e_rows, 1_000_000)
+        xp, op = xh[:pr].numpy().copy(), np.empty((pr, shape.sig_bytes), dtype=np.uint8)
+        hasher.hash_into(xp, pr, op, x_on_device=False, out_on_device=False)
+        barrier()
         t_pg = time.perf_counter()
         for _ in range(3):
-            hasher.hash_into(xp, e2e_rows, op, x_on_device=False, out_on_device=False)
-        pageable_value = 3 * e2e_rows / (time.perf_counter() - t_pg)
-        same = same and bool(np.array_equal(op, oh.numpy()))
-        del xp, op
-    # a float16 numpy array (what embedding stores often hold): raw rows over PCIe, exact cast on the device
-    # (lshx_hash_batch_typed); the signatures must equal those of the same values given as float32
-    f16_value = None
-    if not args.no_e2e:
-        x16 = xh.numpy().astype(np.float16)
-        want16 = hasher.hash_batch_packed(x16.astype(np.float32)).reshape(e2e_rows, SIG_BYTES)
-        got16 = hasher.hash_batch_packed(x16).reshape(e2e_rows, SIG_BYTES)
+            hasher.hash_into(xp, pr, op, x_on_device=False, out_on_device=False)
+        pageable_value = 3 * pr / (time.perf_counter() - t_pg)
+        same = same and bool(np.array_equal(op, oh[:pr].numpy()))
+        # a float16 numpy array (what embedding stores often hold): raw rows over PCIe, exact cast on the device
+        # (lshx_hash_batch_typed); the signatures must equal those of the same values given as float32
+        x16 = xp.astype(np.float16)
+        want16 = hasher.hash_batch_packed(x16.astype(np.float32)).reshape(pr, shape.sig_bytes)
+        got16 = hasher.hash_batch_packed(x16).reshape(pr, shape.sig_bytes)
         t_16 = time.perf_counter()
         for _ in range(3):
             hasher.hash_batch_packed(x16)
-        f16_value = 3 * e2e_rows / (time.perf_counter() - t_16)
+        f16_value = 3 * pr / (time.perf_counter() - t_16)
         same = same and bool(np.array_equal(got16, want16))
-        del x16, want16, got16
+        del xp, op, x16, want16, got16
     # latency of the per-vector call LSHRS.ingest / query make (reference: one hash_vector per call)
     one = xh[:1].numpy().copy()
     for _ in range(20):
@@ -465,124 +735,144 @@ def run_b200(args) -> None:
         hasher.hash_vector(one[0])
     single_us = (time.perf_counter() - t_lat) / 200 * 1e6
 
-    # ---- roofline of the projection kernel ------------------------------------------------
-    ncols = SIG_BYTES * 8
-    useful_flop = 2.0 * DIM * NUM_PERM  # what the reference computes; padding columns are not useful work
-    # tensor-time units per logical product, in TF32 MMAs: 3xTF32 = 3; TF32 hi.hi + the two BF16 cross
-    # terms (one K-doubled BF16 MMA = one TF32 MMA of tensor time) = 2; scaled FP16x3 (three FP16 MMAs,
-    # each half a TF32 MMA) = 1.5
-    mma_passes = {"tcgen05": 1.5, "tcgen05_tf32bf16": 2, "tcgen05_3xtf32": 3}.get(kernel_name, 1)
-    is_tc = kernel_name.startswith("tcgen05")
-    per_kernel_ms = kern_ms / max(1, len(kernel_events))
-    # ALGORITHMIC flops (2*dim*num_perm per vector) against the ceiling for them: the
-    # measured dense TF32 rate (= bf16_tflops_sustained / 2) divided by the tensor-time units the split
-    # spends per logical product (SURVEY section 8d "useful ceiling": 3 for 3xTF32, 2 for TF32 + BF16
-    # cross terms, 1.5 for the default scaled FP16x3).  The FFMA arm is held to the default arm's
-    # ceiling: it is what the hardware can do for this arithmetic.
-    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
-    split_units = {"tcgen05_3xtf32": 3.0, "tcgen05_tf32bf16": 2.0}.get(kernel_name, 1.5)
-    useful_peak = tf32_peak / split_units
-    achieved_tflops = useful_flop * kern_rows / (kern_ms * 1e-3) / 1e12
-    ncols_exec = (NUM_PERM + 15) // 16 * 16 if ROWS_PER_BAND % 8 else (ncols + 127) // 128 * 128
-    if not is_tc:
-        ncols_exec = (ncols + 127) // 128 * 128
-    executed_tflops = 2.0 * DIM * ncols_exec * mma_passes * kern_rows / (kern_ms * 1e-3) / 1e12
-    bytes_per_vec = 4.0 * DIM + SIG_BYTES
-    hbm_gbs = bytes_per_vec * kern_rows / (kern_ms * 1e-3) / 1e9
-    tensor_frac, hbm_frac = achieved_tflops / useful_peak, hbm_gbs / peaks["hbm_gbs"]
-    common = {
-        "kernel": f"hash_{kernel_name}", "traffic": (ROOFLINE_TRAFFIC_PER_ROW[(args.workload, "tcgen05")] * kern_rows / max(1, len(kernel_events))
-                    if is_tc and (args.workload, "tcgen05") in ROOFLINE_TRAFFIC_PER_ROW else None),
-        "avg_launch_ms": per_kernel_ms, "launches_timed": len(kernel_events),
-        "kernel_share_of_step": kern_ms / (start.elapsed_time(stop)),
-        "algorithmic_bytes_per_launch": bytes_per_vec * kern_rows / max(1, len(kernel_events)),
-        "algorithmic_flops_per_launch": useful_flop * kern_rows / max(1, len(kernel_events)),
-        "tensor": {"achieved_tflops": achieved_tflops, "peak_tflops": useful_peak, "frac": tensor_frac,
-                   "peak_source": (f"{peak_src}: bf16_tflops_sustained / 2 (dense TF32) / 3 (3xTF32 split: three MMAs "
-                                   "per logical product)" if split_units == 3.0 else
-                                   f"{peak_src}: bf16_tflops_sustained / 2 (dense TF32) / 2 (split x = hi + lo: one TF32 MMA "
-                                   "for hi.hi + one K-doubled BF16 MMA of the same duration for both cross terms)"
-                                   if split_units == 2.0 else
-                                   f"{peak_src}: bf16_tflops_sustained / 3 (scaled FP16x3 split x = hi + lo: three dense "
-                                   "FP16 MMAs -- hi.hi, hi.lo, lo.hi -- per logical product; FP16 runs at the BF16 rate)"),
-                   "flops_counted": "algorithmic: 2*dim*num_perm per vector",
-                   "executed_tflops": executed_tflops, "executed_vs_tf32_peak": executed_tflops / tf32_peak,
-                   "fp32_pipe_nominal_tflops": 148 * 128 * 2 * 1.965e9 / 1e12},
-        "hbm": {"achieved_gbs": hbm_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": hbm_frac, "peak_source": peak_src,
-                "bytes_per_vector": bytes_per_vec},
-    }
-    if tensor_frac >= hbm_frac:  # the slower of the two ceilings is the bound
-        roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": useful_peak, "unit": "TFLOP/s",
-                    "frac": tensor_frac, **common}
-    else:
-        roofline = {"bound": "hbm", "achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": hbm_frac, **common}
+    roofline = roofline_block(shape, kernel_name, kern_ms, kern_rows, len(kernel_events), my_ms, peaks, peak_src)
 
     # ---- CPU baseline + parity on a bounded sample (rank 0, N = 1 only) ---------------------
-    cpu_baseline, parity = None, None
+    cpu_baseline, parity, cpu = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu:
-        from oracle import lshrs_oracle as oracle
-
-        projs = oracle.make_projections(NUM_BANDS, ROWS_PER_BAND, DIM, SEED)
-        sample = args.cpu_sample
-        idx = torch.linspace(0, rows - 1, sample, device=dev).long()
-        Xs = X[idx].cpu().numpy()
-        t0 = time.perf_counter()
-        ref = oracle.hash_batch_packed(projs, Xs)
-        dt = time.perf_counter() - t0
-        t1 = time.perf_counter()
-        oracle.hash_batch_vectorized(projs, Xs)
-        dtv = time.perf_counter() - t1
-        got = out_host[idx.cpu()].numpy().reshape(sample, NUM_BANDS, -1)
-        parity = oracle.compare_packed(got, ref, oracle.projection_margins(projs, Xs), 1e-5)
-        parity["sample_rows"] = sample
+        cpu = CpuReference()
+        cpu_baseline, parity = cpu_leg(cpu, shape, X, out_host, rows, args.cpu_sample, dev, torch)
         parity["e2e_equals_resident"] = same
-        cpu_baseline = {
-            "value": sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{sample} rows of the same shard through the oracle's per-vector, per-band sgemv loop "
-                      f"(reference LSHHasher.hash_batch path, single Python thread by construction), {dt:.1f} s",
-            "host_cores": os.cpu_count(), "numpy": np.__version__,
-            "vectorized_numpy_not_reference": {"value": sample / dtv, "unit": UNIT,
-                                               "cores": len(os.sched_getaffinity(0))},
-        }
 
-    # ---- rerank (config 4) ------------------------------------------------------------------
+    # ---- BASELINE configs 3 and 5, the API calls, rerank (config 4) -------------------------------------------------
+    configs = None
     rerank = None
     api = None
-    if rank == 0 and world == 1 and not args.no_e2e and args.workload == "hash768":
+    if rank == 0 and world == 1 and not args.no_e2e and shape.name == "hash768":
         try:
-            api = run_api(args, dev)
+            api = run_api(args, dev, shape)
         except Exception as exc:  # noqa: BLE001 -- a side measurement must not take the headline down
             api = {"error": repr(exc)}
+    del run, X
+    torch.cuda.empty_cache()
+    if world == 1 and shape.name == "hash768" and not args.no_configs:
+        configs = {}
+        for name in ("hash1536", "hash128"):
+            try:
+                configs[name] = side_config(torch, dev, device_index, Shape(name), args, peaks, peak_src,
+                                            cpu if not args.no_cpu else None)
+            except Exception as exc:  # noqa: BLE001
+                configs[name] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
     if not args.no_rerank:
-        del X, out_dev
-        torch.cuda.empty_cache()
-        rerank = run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks)
+        rerank = run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks, shape,
+                            cpu if (rank == 0 and world == 1 and not args.no_cpu) else None)
 
     if rank == 0:
+        per_gpu_rows = e2e_split if e2e_split else [e2e_rows] * world
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": shape.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": {"tcgen05": "f16x3", "tcgen05_tf32bf16": "tf32+bf16x2", "tcgen05_3xtf32": "tf32x3"}.get(kernel_name, "f32"),
-            "data": "synthetic", "config": workload_config(args), "impl": "b200", "kernel": kernel_name,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e2e_rows * DIM * 4,
-                    "d2h_bytes_per_step": e2e_rows * SIG_BYTES, "rows_per_step_per_gpu": e2e_rows,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"tcgen05": "f16x3", "tcgen05_tf32bf16": "tf32+bf16x2", "tcgen05_3xtf32": "tf32x3"}.get(kernel_name, "f32"),
+            "data": "synthetic", "config": workload_config(args, shape), "impl": "b200", "kernel": kernel_name,
+            "env_overrides": _native.env_overrides(),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(sum(per_gpu_rows) * shape.dim * 4 / world),
+                    "d2h_bytes_per_step": int(sum(per_gpu_rows) * shape.sig_bytes / world),
+                    "bytes_per_step_are": "per GPU (mean over ranks)", "rows_per_step_per_gpu": per_gpu_rows,
                     "ms_per_step": e2e_ms / e2e_steps,
                     "api": "lshx_hash_batch(host pinned X -> host pinned signatures)",
                     "single_vector_call_us": single_us,
                     "pageable_numpy_input_value": pageable_value, "float16_numpy_input_value": f16_value},
             "kernel_only": {"value": kernel_only_value, "unit": UNIT,
-                            "note": "signatures left in HBM (no D2H gather); value above includes the overlapped D2H "
+                            "note": "signatures left in HBM (no gather); value above includes the overlapped gather "
                                     "of every signature into pinned host memory"},
-            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks,
-            "cpu_baseline": cpu_baseline, "parity": parity, "rerank": rerank, "api": api,
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "fabric": fab,
+            "cpu_baseline": cpu_baseline, "parity": parity, "configs": configs, "rerank": rerank, "api": api,
         }
         emit(line)
+    if shm is not None:
+        barrier()
+        shm.close()
+    if rank == 0 and not args.no_fabric and world < visible:
+        try:
+            os.unlink(f"/dev/shm/lshx_probe_{os.environ.get('MASTER_PORT', '0')}.json")
+        except OSError:
+            pass
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_api(args, dev) -> dict:
+def cpu_leg(cpu: CpuReference, shape: Shape, X, out_host, rows: int, sample: int, dev, torch):
+    """The reference's CPU path on `sample` rows of the shard, and the GPU's bytes for the same rows against it."""
+    h, projs = cpu.hasher(shape)
+    idx = torch.linspace(0, rows - 1, sample, device=dev).long()
+    Xs = X[idx].cpu().numpy()
+    t0 = time.perf_counter()
+    ref = cpu.packed(cpu.hash_batch(h, projs, Xs), shape)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    cpu.oracle.hash_batch_vectorized(projs, Xs)
+    dtv = time.perf_counter() - t1
+    got = out_host[idx.cpu()].numpy().reshape(sample, shape.bands, -1)
+    parity = cpu.oracle.compare_packed(got, ref, cpu.oracle.projection_margins(projs, Xs), 1e-5)
+    parity["sample_rows"] = sample
+    parity["against"] = cpu.kind
+    base = {
+        "value": sample / dt, "unit": UNIT, "cores": 1, "kind": cpu.kind, "source": cpu.source,
+        "sample": f"{sample} rows of the same shard through LSHHasher.hash_batch -- per-vector, per-band sgemv, a "
+                  f"single Python thread by construction (reference lshrs/hash/lsh.py:169), {dt:.1f} s",
+        "host_cores": os.cpu_count(), "numpy": np.__version__,
+        "vectorized_numpy_not_reference": {"value": sample / dtv, "unit": UNIT, "cores": len(os.sched_getaffinity(0))},
+    }
+    return base, parity
+
+
+def side_config(torch, dev, device_index: int, shape: Shape, args, peaks, peak_src, cpu) -> dict:
+    """BASELINE configs 3 (1536 -> 512 bits) and 5 (SIFT-like 128 -> 64 bits) on one GPU: the same resident-shard
+    step as the headline (kernel per chunk + gather of the signatures), 5 timed steps, roofline recomputed from
+    4*dim + signature bytes / 2*dim*num_perm, and a parity sample against the CPU reference."""
+    from lshrs_b200 import LSHHasher
+
+    hasher = LSHHasher(shape.bands, shape.rows_per_band, shape.dim, seed=SEED, device=device_index)
+    rows, chunk = shape.rows, shape.chunk
+    X = make_shard(torch, dev, shape, rows, 2000)
+    out_host = torch.empty((rows, shape.sig_bytes), dtype=torch.uint8, pin_memory=True)
+    run = ResidentRun(torch, dev, hasher, X, shape, chunk, out_host)
+    for _ in range(3):
+        run.one_step()
+    run.drain()
+    torch.cuda.synchronize()
+    steps = 5
+    events: list = []
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(run.compute)
+    for _ in range(steps):
+        run.one_step(events)
+    run.drain()
+    t1.record(run.compute)
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    kern_ms = sum(a.elapsed_time(b) for a, b, _ in events)
+    kern_rows = sum(r for _, _, r in events)
+    out = {
+        "metric": shape.metric, "value": rows * steps / (ms * 1e-3), "unit": UNIT, "steps": steps, "warmup": 3,
+        "ms_per_step": ms / steps, "rows_per_gpu": rows, "chunk_rows": chunk, "kernel": hasher.last_kernel,
+        "kernel_only": {"value": kern_rows / (kern_ms * 1e-3), "unit": UNIT},
+        "data": "synthetic " + ("Gaussian" if shape.dist == "gauss" else "SIFT-like (non-negative integer-valued floats in [0, 255])"),
+        "roofline": roofline_block(shape, hasher.last_kernel, kern_ms, kern_rows, len(events), ms, peaks, peak_src),
+        "note": "value includes the gather of every signature into pinned host memory "
+                f"({shape.sig_bytes} B per vector over one PCIe link); kernel_only leaves them in HBM",
+    }
+    if cpu is not None:
+        out["cpu_baseline"], out["parity"] = cpu_leg(cpu, shape, X, out_host, rows, 16_384, dev, torch)
+    del run, X, out_host
+    hasher.close()
+    return out
+
+
+def run_api(args, dev, shape: Shape) -> dict:
     """Throughput of the reference-facing LSHRS calls on one GPU.
 
     Host data in, Python results out, in-memory bucket storage (the reference's Redis stays a host
@@ -597,12 +887,12 @@ def run_api(args, dev) -> dict:
 
     n_index, n_single, n_batch = 50_000, 300, 2_048
     rng = np.random.default_rng(11)
-    centers = rng.standard_normal((n_index // 8, DIM)).astype(np.float32)
-    Xh = (np.repeat(centers, 8, axis=0) + 0.15 * rng.standard_normal((n_index, DIM))).astype(np.float32)
-    extra = (Xh[:n_single] + 0.05 * rng.standard_normal((n_single, DIM))).astype(np.float32)
+    centers = rng.standard_normal((n_index // 8, shape.dim)).astype(np.float32)
+    Xh = (np.repeat(centers, 8, axis=0) + 0.15 * rng.standard_normal((n_index, shape.dim))).astype(np.float32)
+    extra = (Xh[:n_single] + 0.05 * rng.standard_normal((n_single, shape.dim))).astype(np.float32)
     allvec = np.concatenate([Xh, extra])          # id -> vector, what vector_fetch_fn serves
     corpus_dev = torch.from_numpy(allvec).to(dev)
-    lsh = LSHRS(dim=DIM, num_perm=NUM_PERM, storage=InMemoryStorage(), vector_fetch_fn=lambda ids: allvec[ids])
+    lsh = LSHRS(dim=shape.dim, num_perm=shape.num_perm, storage=InMemoryStorage(), vector_fetch_fn=lambda ids: allvec[ids])
     ids = list(range(n_index))
     t0 = time.perf_counter()
     lsh.index(ids, Xh)
@@ -612,7 +902,7 @@ def run_api(args, dev) -> dict:
         lsh.ingest(n_index + i, extra[i])
     lsh.flush()
     ingest_cps = n_single / (time.perf_counter() - t0)
-    Q = (Xh[rng.integers(0, n_index, n_batch)] + 0.05 * rng.standard_normal((n_batch, DIM))).astype(np.float32)
+    Q = (Xh[rng.integers(0, n_index, n_batch)] + 0.05 * rng.standard_normal((n_batch, shape.dim))).astype(np.float32)
     lsh.get_top_k(Q[-1], topk=10)        # first calls create the rerank handle / workspaces: off the clock
     lsh.get_above_p(Q[-1], p=0.2)
     t0 = time.perf_counter()
@@ -643,7 +933,7 @@ def run_api(args, dev) -> dict:
     }
 
 
-def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> dict:
+def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks, shape: Shape, cpu) -> dict:
     """BASELINE config 4: 8192 queries x 2000 candidates x 768 from a 1M-row corpus resident in HBM."""
     import torch
 
@@ -652,15 +942,15 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> d
 
     N, nq, nc = args.corpus, args.queries, 2000
     gen = torch.Generator(device=dev).manual_seed(1)
-    corpus = torch.empty((N, DIM), dtype=torch.float32, device=dev)
+    corpus = torch.empty((N, shape.dim), dtype=torch.float32, device=dev)
     corpus.normal_(generator=gen)
-    Q = torch.empty((nq, DIM), dtype=torch.float32, device=dev).normal_(generator=gen)
+    Q = torch.empty((nq, shape.dim), dtype=torch.float32, device=dev).normal_(generator=gen)
     # 2000 DISTINCT corpus rows per query: random start, random stride < N / nc
     first = torch.randint(0, N, (nq, 1), generator=gen, device=dev, dtype=torch.int64)
     stride = torch.randint(1, max(2, N // nc), (nq, 1), generator=gen, device=dev, dtype=torch.int64)
     ids = ((first + stride * torch.arange(nc, device=dev, dtype=torch.int64)[None, :]) % N).contiguous()
     offs = torch.arange(nq + 1, device=dev, dtype=torch.int64) * nc
-    rer = _get_reranker(DIM, dev.index)
+    rer = _get_reranker(shape.dim, dev.index)
     lib = _native.lib()
     out = {}
     for tag, k, p in (("k10", 10, 0.0), ("p0.2", 0, 0.2)):
@@ -686,7 +976,7 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> d
         t.record()
         barrier()
         ms = max_ranks(s.elapsed_time(t)) / args.steps
-        bytes_per_q = nc * (4 * DIM + 8) + 4 * DIM + 8 * limit
+        bytes_per_q = nc * (4 * shape.dim + 8) + 4 * shape.dim + 8 * limit
         gbs = bytes_per_q * nq / (ms * 1e-3) / 1e9
         # e2e: PINNED host queries / ids / results through the C ABI, corpus resident (on_device = 2)
         def pinned(t):
@@ -716,15 +1006,13 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> d
                     "d2h_bytes_per_step": int(ph.nbytes + sh.nbytes + ch.nbytes + zh.nbytes)},
             "device_equals_e2e": bool(np.array_equal(ph, pos.cpu().numpy())),
         }
-        if rank == 0 and world == 1 and not args.no_cpu:
-            from oracle import lshrs_oracle as oracle
-
+        if cpu is not None:
             nref = 64
             Ch = corpus.cpu().numpy()
             t1 = time.perf_counter()
             bad = 0
             for i in range(nref):
-                ref = oracle.top_k_cosine(Qh[i], Ch[idh[i * nc:(i + 1) * nc]], k=limit)
+                ref = cpu.top_k_cosine(Qh[i], Ch[idh[i * nc:(i + 1) * nc]], limit)
                 got_pos = ph[i, :limit]
                 ref_scores = np.array([sc for _, sc in ref])
                 if not np.allclose(sh[i, :limit], ref_scores, atol=1e-5, rtol=0):
@@ -732,14 +1020,17 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks) -> d
                 elif set(got_pos.tolist()) != {pp for pp, _ in ref}:
                     bad += 1
             dt = time.perf_counter() - t1
-            entry["cpu_baseline"] = {"value": nref / dt, "unit": "queries/s", "cores": 1, "kind": "port",
-                                     "sample": f"{nref} queries through the oracle's top_k_cosine"}
-            entry["parity"] = {"queries_checked": nref, "mismatching_queries": bad, "score_tol": 1e-5}
+            entry["cpu_baseline"] = {"value": nref / dt, "unit": "queries/s", "cores": 1, "kind": cpu.kind,
+                                     "source": cpu.source,
+                                     "sample": f"{nref} queries through top_k_cosine (reference "
+                                               "lshrs/utils/similarity.py:93-183)"}
+            entry["parity"] = {"queries_checked": nref, "mismatching_queries": bad, "score_tol": 1e-5,
+                               "against": cpu.kind}
             del Ch
         out[tag] = entry
-    out["config"] = {"workload": f"top_k_cosine rerank: {nq} queries x {nc} candidates, dim={DIM}, corpus {N} rows "
+    out["config"] = {"workload": f"top_k_cosine rerank: {nq} queries x {nc} candidates, dim={shape.dim}, corpus {N} rows "
                                  "resident in HBM, CSR int64 candidate ids", "l2": "6.1 MB of gathers per query, "
-                                 f"{nq * nc * DIM * 4 / 1e9:.1f} GB per step (larger than L2)"}
+                                 f"{nq * nc * shape.dim * 4 / 1e9:.1f} GB per step (larger than L2)"}
     return out
 
 
@@ -764,6 +1055,7 @@ def _route_stdout_to_stderr() -> None:
     os.dup2(2, 1)
 
 
+
 def main() -> None:
     _route_stdout_to_stderr()
     ap = argparse.ArgumentParser()
@@ -782,18 +1074,29 @@ def main() -> None:
     ap.add_argument("--no-rerank", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer legs (profiling runs)")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3 and 5 (the `configs` block)")
+    ap.add_argument("--no-fabric", action="store_true",
+                    help="multi-GPU: identity rank -> GPU map, equal e2e shards, no link probe, no relay")
+    ap.add_argument("--relay", choices=("auto", "off", "force"), default="auto",
+                    help="multi-GPU: let ranks on slow host links relay their signatures over NVLink (auto) or not")
     args = ap.parse_args()
     args.steps = max(1, args.steps)
     if args.impl == "reference":
         args.workload = "hash768"
-    select_workload(args)
+    shape = Shape(args.workload)
+    if args.rows is None:
+        args.rows = shape.rows
+    if args.chunk is None:
+        args.chunk = shape.chunk
+    args.chunk = min(args.chunk, args.rows)
+    args.e2e_rows = min(args.e2e_rows, args.rows)
     if args.workload != "hash768":
         args.no_rerank = True
     args.warmup = max(3, args.warmup) if args.impl == "b200" else max(0, args.warmup)
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, shape)
     else:
-        run_b200(args)
+        run_b200(args, shape)
 
 
 if __name__ == "__main__":

@@ -92,6 +92,8 @@ struct RerankArgs {
   int64_t n_vectors;
   const int64_t* offs;
   const int64_t* ids;  // may be null
+  const int32_t* cand_counts;  // may be null: query i has cand_counts[i] candidates starting at offs[i]
+                               // (lists that do not fill their slot range: the device join's output)
   int dim;
   int k;
   double p;
@@ -114,5 +116,26 @@ size_t rerank_scratch_bytes(const RerankArgs& a, int64_t* queries_per_pass);
 int launch_rerank(const RerankArgs& a, cudaStream_t stream);
 int launch_l2_normalize(const float* d_X, int64_t n, int dim, float* d_out, int32_t* d_zero,
                         cudaStream_t stream);
+
+// ---- device band index / candidate join (index_join.cu) ---------------------------
+// Segments: keys[b * cap + e], ids[b * cap + e] for band b, entry e < n.
+int index_append(const uint8_t* d_sig, const int64_t* d_ids, int64_t n, int nb, int bpb, uint64_t* keys, int64_t* ids,
+                 int64_t cap, int64_t at, unsigned long long* d_max_id, int* d_bad, cudaStream_t st);
+size_t index_sort_hist_entries(int64_t n, int nb);
+int index_sort(uint64_t* keys[2], int64_t* ids[2], int* cur, int64_t n, int64_t cap, int nb, int key_bytes,
+               int id_bytes, unsigned* d_hist, size_t hist_entries, cudaStream_t st);
+int index_tombstone(int64_t* ids, int64_t n, int64_t cap, int nb, const int64_t* d_gone_sorted, int64_t ngone,
+                    cudaStream_t st);
+int index_lookup_scan(const uint8_t* d_sig, int64_t nq, int nb, int bpb, const uint64_t* keys, int64_t n, int64_t cap,
+                      int64_t* d_lo, int* d_cnt, int* d_raw_count, int64_t* d_raw_off, int64_t* d_ws_off,
+                      int64_t* d_meta, cudaStream_t st);
+unsigned index_join_smem_cap();
+int index_join(int64_t nq, int nb, const int64_t* ids, int64_t cap, const int64_t* d_lo, const int* d_cnt,
+               const int* d_raw_count, const int64_t* d_raw_off, const int64_t* d_ws_off, uint64_t* d_ws,
+               int64_t ws_total, int64_t* d_out_ids, int* d_out_coll, int* d_uniq, cudaStream_t st);
+int index_topk(const int64_t* d_cand, const int64_t* d_raw_off, const int* d_uniq, int64_t nq, int k, int64_t* d_out,
+               int* d_out_count, cudaStream_t st);
+int index_pos_to_id(const int64_t* d_cand, const int64_t* d_raw_off, const int32_t* d_pos, const int32_t* d_count,
+                    int64_t nq, int stride, int64_t* d_out, cudaStream_t st);
 
 }  // namespace lshx

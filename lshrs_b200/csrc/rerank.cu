@@ -144,7 +144,7 @@ rerank_kernel(RerankArgs a, unsigned cap, int q_floats) {
     const float qnorm = sqrtf(qq);
 
     const int64_t base = a.offs[qi];
-    const int64_t n = a.offs[qi + 1] - base;
+    const int64_t n = a.cand_counts ? (int64_t)a.cand_counts[qi] : a.offs[qi + 1] - base;
 
     // result count: top_k_cosine's k and/or LSHRS.query's max(1, ceil(n * top_p))
     int64_t limit;
@@ -243,7 +243,7 @@ rerank_bigsort_kernel(RerankArgs a) {
   const int64_t qi = blockIdx.x;
   uint64_t* keys = a.big_keys + qi * a.big_stride;
   const uint64_t cap = (uint64_t)a.big_stride;
-  const int64_t n = a.offs[qi + 1] - a.offs[qi];
+  const int64_t n = a.cand_counts ? (int64_t)a.cand_counts[qi] : a.offs[qi + 1] - a.offs[qi];
 
   // phase 1: every BS_TILE-key tile fully sorted in shared memory, direction alternating like the network's
   for (uint64_t t0 = 0; t0 < cap; t0 += BS_TILE) {
@@ -402,6 +402,7 @@ int launch_rerank(const RerankArgs& a_in, cudaStream_t stream) {
       c.out_score = a_in.out_score + q0 * (int64_t)a_in.out_stride;
       c.out_count = a_in.out_count + q0;
       c.out_zero = a_in.out_zero ? a_in.out_zero + q0 : nullptr;
+      c.cand_counts = a_in.cand_counts ? a_in.cand_counts + q0 : nullptr;
       c.big_stride = stride;
       RerankArgs score = c;       // pass 1: score every candidate, keys to global memory, no in-SM selection
       score.select = false;
