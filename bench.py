@@ -807,7 +807,7 @@ def run_b200(args, shape: Shape) -> None:
 def cpu_leg(cpu: CpuReference, shape: Shape, X, out_host, rows: int, sample: int, dev, torch):
     """The reference's CPU path on `sample` rows of the shard, and the GPU's bytes for the same rows against it."""
     h, projs = cpu.hasher(shape)
-    idx = torch.linspace(0, rows - 1, sample, device=dev).long()
+    idx = (torch.arange(sample, device=dev, dtype=torch.int64) * (rows - 1)) // max(1, sample - 1)   # evenly spread, exact
     Xs = X[idx].cpu().numpy()
     t0 = time.perf_counter()
     ref = cpu.packed(cpu.hash_batch(h, projs, Xs), shape)

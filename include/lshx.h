@@ -73,6 +73,7 @@ typedef enum lshx_hash_kernel {
 
 typedef struct lshx_hasher lshx_hasher;   /* opaque */
 typedef struct lshx_reranker lshx_reranker; /* opaque */
+typedef struct lshx_index lshx_index;       /* opaque */
 
 /* ---- library ---------------------------------------------------------- */
 
@@ -267,6 +268,74 @@ int lshx_l2_normalize(lshx_reranker* r, const float* X, int64_t n, float* out,
                       int32_t* zero_rows, int on_device, void* stream);
 
 int lshx_rerank_destroy(lshx_reranker* r);
+
+/* ---- device band index: batched candidate generation ----
+ *
+ * Replaces, for BATCHES of queries, the bucket lookups and the collision counting of
+ * LSHRS._candidate_counts (reference lshrs/core/main.py:1088-1111: per band one
+ * SMEMBERS of the bucket the query's band key names, counts[id] += 1) and the
+ * ordering of LSHRS.query (main.py:614: (-collisions, id)).  A mirror of what
+ * index() sends to the bucket store -- the (band, key, id) triples -- stays in
+ * HBM, sorted by (band, key, id); Redis remains the system of record (every
+ * operation still goes to the storage backend unchanged).  Integer work: the
+ * candidate lists, their order and the collision counts are exactly the storage
+ * path's.  Band keys of at most 8 bytes (rows_per_band <= 64), at most 255 bands,
+ * ids in [0, 2^56).
+ */
+int lshx_index_create(int device, int num_bands, int bytes_per_band, lshx_index** out);
+int lshx_index_destroy(lshx_index* ix);
+/* Vectors added so far (removed ones included until they are compacted away). */
+int64_t lshx_index_size(const lshx_index* ix);
+
+/*
+ * Mirror of RedisStorage.batch_add for n vectors (reference lshrs/storage/redis.py
+ * batch_add, called from LSHRS.flush, main.py:413-440): signatures as
+ * lshx_hash_batch wrote them (n x num_bands x bytes_per_band), ids[n].  on_device:
+ * both pointers are device pointers produced on `stream` (signatures need not
+ * leave HBM); otherwise host pointers.  SET semantics: adding the same
+ * (band, key, id) twice counts once.
+ */
+int lshx_index_add(lshx_index* ix, const uint8_t* signatures, const int64_t* ids, int64_t n,
+                   int on_device, void* stream);
+/* Mirror of RedisStorage.remove_indices (LSHRS.delete, main.py:740-771): host ids. */
+int lshx_index_remove(lshx_index* ix, const int64_t* ids_host, int64_t n);
+/* Mirror of RedisStorage.clear (LSHRS.clear, main.py:773-791). */
+int lshx_index_clear(lshx_index* ix);
+
+/*
+ * Candidate lists of nq queries at once: for query i every id that shares at
+ * least one band key with signatures[i], ordered by (-collisions, id).  The
+ * result stays in handle-owned device buffers until the next query / add / remove /
+ * clear on this handle; total_candidates receives the number of candidate SLOTS
+ * (an upper bound of the sum of the list lengths: the buffer sizes lshx_index_fetch
+ * needs), max_candidates the largest per-query slot count.
+ */
+int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64_t nq, int on_device, void* stream,
+                     int64_t* total_candidates, int64_t* max_candidates);
+/*
+ * Host copies of the last query's lists: query i owns ids[offsets[i] ..
+ * offsets[i] + counts[i]) and, when collisions != NULL, the matching collision
+ * counts.  offsets has nq + 1 entries, ids / collisions total_candidates.  Any
+ * pointer may be NULL.
+ */
+int lshx_index_fetch(lshx_index* ix, int64_t* offsets, int32_t* counts, int64_t* ids, int32_t* collisions);
+/*
+ * get_top_k for the last query (main.py:616-623): the first min(top_k, counts[i])
+ * candidates of every list into out_ids[nq][top_k] (-1 padded), out_count[nq]. Host.
+ */
+int lshx_index_topk(lshx_index* ix, int top_k, int64_t* out_ids, int32_t* out_count);
+/*
+ * get_above_p / query(top_p=...) for the last query (main.py:625-658): rerank every
+ * list by cosine against `corpus_device` (float32 [n_vectors][dim] resident in HBM,
+ * candidate id = row: the device-side stand-in for vector_fetch_fn) with the rerank
+ * kernel of `r`, keep min(k, max(1, ceil(n_i * p))) (k <= 0: no k; p <= 0: no p)
+ * and return IDS (not positions): out_ids[nq][out_stride] (-1 padded), out_score,
+ * out_count, out_zero (zero-norm vectors met, as lshx_rerank_topk).  Q: the nq
+ * query vectors, host (q_on_device = 0) or device.  Outputs are host pointers.
+ */
+int lshx_index_rerank(lshx_index* ix, lshx_reranker* r, const float* Q, int q_on_device,
+                      const float* corpus_device, int64_t n_vectors, int k, double p, int out_stride,
+                      int64_t* out_ids, float* out_score, int32_t* out_count, int32_t* out_zero);
 
 #ifdef __cplusplus
 }

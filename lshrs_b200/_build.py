@@ -23,7 +23,7 @@ REPO = ROOT.parent
 CSRC = ROOT / "csrc"
 LIB_DIR = ROOT / "_lib"
 LIB_PATH = LIB_DIR / "liblshx.so"
-SOURCES = ["lshx_api.cu", "hash_ffma.cu", "hash_tc.cu", "rerank.cu"]
+SOURCES = ["lshx_api.cu", "hash_ffma.cu", "hash_tc.cu", "rerank.cu", "index_join.cu"]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -60,6 +60,16 @@ EXPORTED_SYMBOLS = (
     "lshx_rerank_scores",
     "lshx_l2_normalize",
     "lshx_rerank_destroy",
+    "lshx_index_create",
+    "lshx_index_destroy",
+    "lshx_index_size",
+    "lshx_index_add",
+    "lshx_index_remove",
+    "lshx_index_clear",
+    "lshx_index_query",
+    "lshx_index_fetch",
+    "lshx_index_topk",
+    "lshx_index_rerank",
 )
 
 
@@ -132,6 +142,27 @@ def _declare(cdll: ctypes.CDLL) -> None:
     cdll.lshx_l2_normalize.argtypes = [vp, vp, c_int64, vp, vp, c_int, vp]
     cdll.lshx_rerank_destroy.restype = c_int
     cdll.lshx_rerank_destroy.argtypes = [vp]
+
+    cdll.lshx_index_create.restype = c_int
+    cdll.lshx_index_create.argtypes = [c_int, c_int, c_int, POINTER(vp)]
+    cdll.lshx_index_destroy.restype = c_int
+    cdll.lshx_index_destroy.argtypes = [vp]
+    cdll.lshx_index_size.restype = c_int64
+    cdll.lshx_index_size.argtypes = [vp]
+    cdll.lshx_index_add.restype = c_int
+    cdll.lshx_index_add.argtypes = [vp, vp, vp, c_int64, c_int, vp]
+    cdll.lshx_index_remove.restype = c_int
+    cdll.lshx_index_remove.argtypes = [vp, vp, c_int64]
+    cdll.lshx_index_clear.restype = c_int
+    cdll.lshx_index_clear.argtypes = [vp]
+    cdll.lshx_index_query.restype = c_int
+    cdll.lshx_index_query.argtypes = [vp, vp, c_int64, c_int, vp, POINTER(c_int64), POINTER(c_int64)]
+    cdll.lshx_index_fetch.restype = c_int
+    cdll.lshx_index_fetch.argtypes = [vp, vp, vp, vp, vp]
+    cdll.lshx_index_topk.restype = c_int
+    cdll.lshx_index_topk.argtypes = [vp, c_int, vp, vp]
+    cdll.lshx_index_rerank.restype = c_int
+    cdll.lshx_index_rerank.argtypes = [vp, vp, vp, c_int, vp, c_int64, c_int, c_double, c_int, vp, vp, vp, vp]
 
 
 def lib() -> ctypes.CDLL:

@@ -21,6 +21,7 @@ once and reranks all of them in one launch.
 from __future__ import annotations
 
 import logging
+import math
 from collections.abc import Callable, Sequence
 from threading import Lock
 from typing import Any, Optional, Union
@@ -77,6 +78,7 @@ class LSHRS:
         decode_responses: bool = False,
         seed: int = 42,
         device: Optional[int] = None,
+        device_index: bool = False,
     ) -> None:
         if dim <= 0:
             raise ValueError("Vector dimensionality must be greater than zero")
@@ -102,6 +104,14 @@ class LSHRS:
         self._storage = storage
         self._buffer: list[BucketOperation] = []
         self._buffer_lock = Lock()
+        # optional mirror of the bucket store in HBM (lshrs_b200/storage/device.py): what reaches the store in a
+        # flush is added to it right after, so batched queries can generate their candidates on the GPU
+        self._dindex = None
+        self._mirror_pending: list[tuple[np.ndarray, np.ndarray]] = []   # (signatures, ids) of buffered operations
+        if device_index:
+            from lshrs_b200.storage.device import DeviceIndex
+
+            self._dindex = DeviceIndex(num_bands, self._hasher.bytes_per_band, device=self._hasher.device)
         self._config: dict[str, Any] = {
             "dim": dim, "num_perm": num_perm, "num_bands": num_bands, "rows_per_band": rows_per_band,
             "similarity_threshold": similarity_threshold, "buffer_size": buffer_size, "seed": seed,
@@ -171,6 +181,10 @@ class LSHRS:
         vec = self._prepare_vector(vector)
         signatures = self._hasher.hash_vector(vec)
         self._enqueue_operations(index, signatures)
+        if self._dindex is not None:
+            packed = np.frombuffer(b"".join(signatures), dtype=np.uint8)
+            with self._buffer_lock:
+                self._mirror_pending.append((packed, np.array([int(index)], dtype=np.int64)))
         self._flush_buffer_if_needed()
 
     def flush(self) -> None:
@@ -180,13 +194,17 @@ class LSHRS:
                 return
             pending = list(self._buffer)
             self._buffer.clear()
+            mirror, self._mirror_pending = self._mirror_pending, []
         try:
             self._storage.batch_add(pending)
         except Exception as exc:
             logger.error(f"Failed to flush buffer to Redis: {exc}")
             with self._buffer_lock:
                 self._buffer[0:0] = pending
+                self._mirror_pending[0:0] = mirror
             raise
+        for sig, ids in mirror:      # the store has them: now the device mirror may
+            self._dindex.add(sig, ids)
 
     def index(self, indices: Sequence[int], vectors: Optional[np.ndarray] = None) -> None:
         """Ingest a batch: ONE kernel call hashes every row and flags zero vectors.
@@ -218,18 +236,34 @@ class LSHRS:
         flags = zero_flag.tolist()
         band_ids = range(nb)
         buffer, lock, limit = self._buffer, self._buffer_lock, self._buffer_size
-        for row, idx in enumerate(indices):
-            idx = int(idx)
-            if idx < 0:
-                raise ValueError("index must be non-negative")
-            if flags[row]:
-                raise ValueError(_ZERO_VECTOR_MSG)
-            ops = [(b, key, idx) for b, key in zip(band_ids, keys[row])]
-            with lock:
-                buffer.extend(ops)
-                due = len(buffer) >= limit
-            if due:
-                self.flush()
+        mirrored = 0                # rows [0, mirrored) are already queued for the device mirror
+
+        def queue_mirror(upto: int) -> None:
+            nonlocal mirrored
+            if self._dindex is not None and upto > mirrored:
+                ids_arr = np.fromiter((int(i) for i in indices[mirrored:upto]), dtype=np.int64, count=upto - mirrored)
+                with lock:
+                    self._mirror_pending.append((packed[mirrored:upto], ids_arr))
+                mirrored = upto
+
+        try:
+            for row, idx in enumerate(indices):
+                idx = int(idx)
+                if idx < 0:
+                    raise ValueError("index must be non-negative")
+                if flags[row]:
+                    raise ValueError(_ZERO_VECTOR_MSG)
+                ops = [(b, key, idx) for b, key in zip(band_ids, keys[row])]
+                with lock:
+                    buffer.extend(ops)
+                    due = len(buffer) >= limit
+                if due:
+                    queue_mirror(row + 1)
+                    self.flush()
+        except ValueError:
+            queue_mirror(row)       # the rows before the invalid one stay buffered, as in the reference's loop
+            raise
+        queue_mirror(len(indices))
         self.flush()
 
     # ------------------------------------------------------------------ querying
@@ -279,43 +313,81 @@ class LSHRS:
         return list(self.query(vector, top_k=None, top_p=p))  # type: ignore[arg-type]
 
     def query_batch(self, vectors: np.ndarray, *, top_k: Optional[int] = 10, top_p: Optional[float] = None,
-                    corpus=None) -> list:
+                    corpus=None, device_index: bool = False, as_arrays: bool = False):
         """``query`` for many vectors: one hash launch, one rerank launch.
 
         Returns one result list per row, identical to calling :meth:`query` row
         by row.  With ``top_p``, candidate vectors come from ``corpus`` when given
         (a CUDA torch tensor ``(N, dim)`` resident in HBM, candidate id = row --
         the device-side stand-in for ``vector_fetch_fn``), else from ``vector_fetch_fn``.
+
+        ``device_index=True`` (needs ``LSHRS(device_index=True)``): the candidates come from the mirror of the
+        bucket store in HBM instead of ``num_bands`` bucket reads per query -- same lists, same order, same
+        results (``lshx_index_query``); with ``corpus`` the lists never leave the GPU before the rerank.
+        ``as_arrays=True`` returns numpy arrays instead of Python lists (-1 padded ids ``(nq, k)``, then scores
+        for ``top_p``, then counts): at several hundred thousand queries per second the lists are what costs.
         """
         arr = np.asarray(vectors, dtype=np.float32)
         if arr.ndim != 2 or arr.shape[1] != self._dim:
             raise ValueError(f"Vectors must have shape (n, {self._dim}); received {arr.shape}")
         nq = arr.shape[0]
+        if as_arrays and not device_index:
+            raise ValueError("as_arrays=True is only available with device_index=True")
+        if device_index and self._dindex is None:
+            raise RuntimeError("device_index=True needs an index built with LSHRS(..., device_index=True)")
         if nq == 0:
             return []
         if top_p is None and top_k is not None and top_k <= 0:
             raise ValueError("top_k must be greater than zero when provided")
         if top_p is not None and not 0 < top_p <= 1:
             raise ValueError("top_p must be within the range (0, 1]")
+        if top_p is not None and top_k is not None and top_k <= 0:
+            raise ValueError("top_k must be greater than zero when provided")
         packed, zero_flag = self._hasher.hash_batch_packed(arr, return_zero_flag=True)
         if zero_flag.any():
             raise ValueError(_ZERO_VECTOR_MSG)
         nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
-        # every (query, band) bucket in ONE storage round trip when the backend allows it
-        keys = np.ascontiguousarray(packed).reshape(nq, nb * bpb).view(f"V{bpb}").tolist()
-        buckets = self._fetch_buckets([(b, key) for row in keys for b, key in enumerate(row)])
-        ordered_all: list[list[int]] = []
-        for row in range(nq):
-            counts: dict[int, int] = {}
-            for members in buckets[row * nb:(row + 1) * nb]:
-                for cand in members:
-                    counts[cand] = counts.get(cand, 0) + 1
-            ordered = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))
-            ordered_all.append([idx for idx, _ in ordered])
+        if device_index:
+            _, maxc = self._dindex.query(packed)
+            if top_p is None and top_k is not None:
+                ids, counts = self._dindex.topk(top_k)
+                if as_arrays:
+                    return ids, counts
+                rows, cl = ids.tolist(), counts.tolist()
+                return [rows[i][:cl[i]] for i in range(nq)]
+            if top_p is not None and corpus is not None:
+                stride = max(1, math.ceil(maxc * top_p))
+                if top_k is not None:
+                    stride = min(stride, int(top_k))
+                rer = _get_reranker(self._dim, self._hasher.device)
+                ids, scores, counts, zero = self._dindex.rerank(rer, arr, corpus, k=int(top_k or 0), p=float(top_p),
+                                                                stride=stride)
+                if zero[counts > 0].any():
+                    raise ValueError("Cannot normalize zero vector")
+                if as_arrays:
+                    return ids, scores, counts
+                rows, sc, cl = ids.tolist(), scores.tolist(), counts.tolist()
+                return [list(zip(rows[i][:cl[i]], sc[i][:cl[i]])) for i in range(nq)]
+            offs, counts, flat = self._dindex.fetch()
+            if as_arrays and top_p is None:
+                return offs, counts, flat
+            if as_arrays:
+                raise ValueError("as_arrays=True with top_p needs corpus= (the rerank on the device)")
+            ordered_all = [flat[o:o + c].tolist() for o, c in zip(offs[:-1].tolist(), counts.tolist())]
+        else:
+            # every (query, band) bucket in ONE storage round trip when the backend allows it
+            keys = np.ascontiguousarray(packed).reshape(nq, nb * bpb).view(f"V{bpb}").tolist()
+            buckets = self._fetch_buckets([(b, key) for row in keys for b, key in enumerate(row)])
+            ordered_all = []
+            for row in range(nq):
+                counts: dict[int, int] = {}
+                for members in buckets[row * nb:(row + 1) * nb]:
+                    for cand in members:
+                        counts[cand] = counts.get(cand, 0) + 1
+                ordered = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))
+                ordered_all.append([idx for idx, _ in ordered])
         if top_p is None:
             return [ids if top_k is None else ids[:top_k] for ids in ordered_all]
-        if top_k is not None and top_k <= 0:
-            raise ValueError("top_k must be greater than zero when provided")
         lens = np.array([len(x) for x in ordered_all], dtype=np.int64)
         offsets = np.zeros(nq + 1, dtype=np.int64)
         np.cumsum(lens, out=offsets[1:])
@@ -349,10 +421,14 @@ class LSHRS:
     def delete(self, indices: Union[int, Sequence[int]]) -> None:
         to_remove = [indices] if isinstance(indices, int) else [int(i) for i in indices]
         self._storage.remove_indices(to_remove)
+        if self._dindex is not None:
+            self._dindex.remove(to_remove)
 
     def clear(self) -> None:
         self.flush()
         self._storage.clear()
+        if self._dindex is not None:
+            self._dindex.clear()
 
     def stats(self) -> dict[str, Any]:
         c = self._config

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <condition_variable>
 #include <thread>
+#include <algorithm>
 #include <vector>
 
 #include <cuda_fp16.h>
@@ -965,3 +966,377 @@ extern "C" int lshx_l2_normalize(lshx_reranker* r, const float* X, int64_t n, fl
   return LSHX_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// device band index (index_join.cu)
+// ---------------------------------------------------------------------------------------
+
+struct lshx_index {
+  int device = 0;
+  int nb = 0, bpb = 0;
+  int64_t n = 0;         // entries per band (tombstones included)
+  int64_t sorted_n = 0;  // leading entries of every segment that are in (key, id) order
+  int64_t cap = 0;       // entries each band segment can hold
+  uint64_t* keys[2] = {nullptr, nullptr};
+  int64_t* ids[2] = {nullptr, nullptr};
+  int cur = 0;
+  unsigned long long* d_max_id = nullptr;
+  int* d_bad = nullptr;
+  cudaStream_t stream = nullptr;
+  DevBuf hist, stage_sig, stage_ids, gone;
+  // state of the last query (device buffers, valid until the next query on this handle)
+  DevBuf q_sig, lo, cnt, raw_count, raw_off, ws_off, meta, ws, out_ids, out_coll, uniq, topk_ids, topk_cnt;
+  DevBuf rr_pos, rr_score, rr_count, rr_zero, rr_ids, rr_q;
+  int64_t last_nq = -1, last_total = 0, last_max = 0;
+  std::mutex mu;
+};
+
+static int index_reserve(lshx_index* ix, int64_t want) {
+  if (want <= ix->cap) return LSHX_OK;
+  int64_t cap = ix->cap ? ix->cap : 4096;
+  while (cap < want) cap += cap / 2 + 4096;
+  uint64_t* nk[2] = {nullptr, nullptr};
+  int64_t* ni[2] = {nullptr, nullptr};
+  const size_t bytes = (size_t)ix->nb * cap * 8;
+  for (int i = 0; i < 2; ++i) {
+    if (cudaMalloc(reinterpret_cast<void**>(&nk[i]), bytes) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&ni[i]), bytes) != cudaSuccess) {
+      (void)cudaGetLastError();
+      for (int j = 0; j < 2; ++j) {
+        if (nk[j]) cudaFree(nk[j]);
+        if (ni[j]) cudaFree(ni[j]);
+      }
+      set_error("cudaMalloc of %zu bytes for the band index failed", bytes);
+      return LSHX_ERR_OOM;
+    }
+  }
+  if (ix->n > 0) {   // only the current side carries data
+    LSHX_CUDA(cudaMemcpy2DAsync(nk[0], (size_t)cap * 8, ix->keys[ix->cur], (size_t)ix->cap * 8, (size_t)ix->n * 8,
+                                (size_t)ix->nb, cudaMemcpyDeviceToDevice, ix->stream));
+    LSHX_CUDA(cudaMemcpy2DAsync(ni[0], (size_t)cap * 8, ix->ids[ix->cur], (size_t)ix->cap * 8, (size_t)ix->n * 8,
+                                (size_t)ix->nb, cudaMemcpyDeviceToDevice, ix->stream));
+    LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (ix->keys[i]) cudaFree(ix->keys[i]);
+    if (ix->ids[i]) cudaFree(ix->ids[i]);
+    ix->keys[i] = nk[i];
+    ix->ids[i] = ni[i];
+  }
+  ix->cur = 0;
+  ix->cap = cap;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_create(int device, int num_bands, int bytes_per_band, lshx_index** out) {
+  LSHX_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  LSHX_REQUIRE(num_bands > 0 && num_bands <= 255, "num_bands must be in [1, 255] for the device index");
+  LSHX_REQUIRE(bytes_per_band > 0 && bytes_per_band <= 8,
+               "the device index takes band keys of at most 8 bytes (rows_per_band <= 64)");
+  int rc = check_device(device);
+  if (rc != LSHX_OK) return rc;
+  DeviceGuard g(device);
+  lshx_index* ix = new lshx_index();
+  ix->device = device;
+  ix->nb = num_bands;
+  ix->bpb = bytes_per_band;
+  if (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&ix->d_max_id), 8) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&ix->d_bad), 4) != cudaSuccess ||
+      cudaMemset(ix->d_max_id, 0, 8) != cudaSuccess || cudaMemset(ix->d_bad, 0, 4) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cannot create the band index on device %d", device);
+    lshx_index_destroy(ix);
+    return LSHX_ERR_CUDA;
+  }
+  *out = ix;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_destroy(lshx_index* ix) {
+  if (!ix) return LSHX_OK;
+  {
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+      if (ix->keys[i]) cudaFree(ix->keys[i]);
+      if (ix->ids[i]) cudaFree(ix->ids[i]);
+    }
+    if (ix->d_max_id) cudaFree(ix->d_max_id);
+    if (ix->d_bad) cudaFree(ix->d_bad);
+    for (DevBuf* b : {&ix->hist, &ix->stage_sig, &ix->stage_ids, &ix->gone, &ix->q_sig, &ix->lo, &ix->cnt,
+                      &ix->raw_count, &ix->raw_off, &ix->ws_off, &ix->meta, &ix->ws, &ix->out_ids, &ix->out_coll,
+                      &ix->uniq, &ix->topk_ids, &ix->topk_cnt, &ix->rr_pos, &ix->rr_score, &ix->rr_count,
+                      &ix->rr_zero, &ix->rr_ids, &ix->rr_q})
+      b->release();
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    (void)cudaGetLastError();
+  }
+  delete ix;
+  return LSHX_OK;
+}
+
+extern "C" int64_t lshx_index_size(const lshx_index* ix) { return ix ? ix->n : 0; }
+
+extern "C" int lshx_index_add(lshx_index* ix, const uint8_t* signatures, const int64_t* ids, int64_t n,
+                              int on_device, void* stream) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  LSHX_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0) return LSHX_OK;
+  LSHX_REQUIRE(signatures != nullptr && ids != nullptr, "null buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  int rc = index_reserve(ix, ix->n + n);
+  if (rc != LSHX_OK) return rc;
+  const size_t sig_bytes = (size_t)n * ix->nb * ix->bpb;
+  const uint8_t* d_sig = signatures;
+  const int64_t* d_ids = ids;
+  if (!on_device) {
+    if ((rc = ix->stage_sig.reserve(sig_bytes)) != LSHX_OK) return rc;
+    if ((rc = ix->stage_ids.reserve((size_t)n * 8)) != LSHX_OK) return rc;
+    LSHX_CUDA(cudaMemcpyAsync(ix->stage_sig.p, signatures, sig_bytes, cudaMemcpyHostToDevice, ix->stream));
+    LSHX_CUDA(cudaMemcpyAsync(ix->stage_ids.p, ids, (size_t)n * 8, cudaMemcpyHostToDevice, ix->stream));
+    d_sig = static_cast<const uint8_t*>(ix->stage_sig.p);
+    d_ids = static_cast<const int64_t*>(ix->stage_ids.p);
+  } else {
+    // the signatures were produced on the caller's stream: order ours after it
+    LSHX_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  }
+  rc = index_append(d_sig, d_ids, n, ix->nb, ix->bpb, ix->keys[ix->cur], ix->ids[ix->cur], ix->cap, ix->n,
+                    ix->d_max_id, ix->d_bad, ix->stream);
+  if (rc != LSHX_OK) return rc;
+  int bad = 0;
+  LSHX_CUDA(cudaMemcpyAsync(&bad, ix->d_bad, 4, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  if (bad) {
+    LSHX_CUDA(cudaMemset(ix->d_bad, 0, 4));
+    set_error("vector ids must lie in [0, 2^56) for the device index");
+    return LSHX_ERR_INVALID_ARG;   // the entries were not counted in: n is unchanged
+  }
+  ix->n += n;
+  ix->last_nq = -1;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_clear(lshx_index* ix) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->n = ix->sorted_n = 0;
+  ix->last_nq = -1;
+  LSHX_CUDA(cudaMemset(ix->d_max_id, 0, 8));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_remove(lshx_index* ix, const int64_t* ids_host, int64_t n) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  LSHX_REQUIRE(n >= 0, "n must be >= 0");
+  if (n == 0 || ix->n == 0) return LSHX_OK;
+  LSHX_REQUIRE(ids_host != nullptr, "null buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  std::vector<int64_t> sorted(ids_host, ids_host + n);
+  std::sort(sorted.begin(), sorted.end());
+  int rc = ix->gone.reserve((size_t)n * 8);
+  if (rc != LSHX_OK) return rc;
+  LSHX_CUDA(cudaMemcpyAsync(ix->gone.p, sorted.data(), (size_t)n * 8, cudaMemcpyHostToDevice, ix->stream));
+  rc = index_tombstone(ix->ids[ix->cur], ix->n, ix->cap, ix->nb, static_cast<const int64_t*>(ix->gone.p), n, ix->stream);
+  if (rc != LSHX_OK) return rc;
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  ix->last_nq = -1;
+  return LSHX_OK;
+}
+
+// sort what add() appended since the last query
+static int index_make_sorted(lshx_index* ix) {
+  if (ix->sorted_n == ix->n) return LSHX_OK;
+  unsigned long long max_id = 0;
+  LSHX_CUDA(cudaMemcpyAsync(&max_id, ix->d_max_id, 8, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  // bytes of max_id + 1: the all-ones pattern of a tombstone's low bytes then never equals a live id's, so
+  // tombstones sort after every live id of their bucket
+  int id_bytes = 1;
+  while (id_bytes < 8 && ((max_id + 1) >> (8 * id_bytes)) != 0) ++id_bytes;
+  const size_t hist_entries = index_sort_hist_entries(ix->n, ix->nb);
+  int rc = ix->hist.reserve(hist_entries * sizeof(unsigned));
+  if (rc != LSHX_OK) return rc;
+  rc = index_sort(ix->keys, ix->ids, &ix->cur, ix->n, ix->cap, ix->nb, ix->bpb, id_bytes,
+                  static_cast<unsigned*>(ix->hist.p), hist_entries, ix->stream);
+  if (rc != LSHX_OK) return rc;
+  ix->sorted_n = ix->n;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64_t nq, int on_device, void* stream,
+                                int64_t* total_candidates, int64_t* max_candidates) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  LSHX_REQUIRE(nq >= 0, "nq must be >= 0");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  ix->last_nq = -1;
+  if (total_candidates) *total_candidates = 0;
+  if (max_candidates) *max_candidates = 0;
+  if (nq == 0) {
+    ix->last_nq = 0;
+    ix->last_total = ix->last_max = 0;
+    return LSHX_OK;
+  }
+  LSHX_REQUIRE(signatures != nullptr, "null buffer");
+  int rc = index_make_sorted(ix);
+  if (rc != LSHX_OK) return rc;
+  const size_t sig_bytes = (size_t)nq * ix->nb * ix->bpb;
+  const uint8_t* d_sig = signatures;
+  if (!on_device) {
+    if ((rc = ix->q_sig.reserve(sig_bytes)) != LSHX_OK) return rc;
+    LSHX_CUDA(cudaMemcpyAsync(ix->q_sig.p, signatures, sig_bytes, cudaMemcpyHostToDevice, ix->stream));
+    d_sig = static_cast<const uint8_t*>(ix->q_sig.p);
+  } else {
+    LSHX_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  }
+  if ((rc = ix->lo.reserve((size_t)nq * ix->nb * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->cnt.reserve((size_t)nq * ix->nb * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->raw_count.reserve((size_t)nq * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->raw_off.reserve((size_t)(nq + 1) * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->ws_off.reserve((size_t)(nq + 1) * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->meta.reserve(32)) != LSHX_OK) return rc;
+  if ((rc = ix->uniq.reserve((size_t)nq * 4)) != LSHX_OK) return rc;
+  rc = index_lookup_scan(d_sig, nq, ix->nb, ix->bpb, ix->keys[ix->cur], ix->n, ix->cap,
+                         static_cast<int64_t*>(ix->lo.p), static_cast<int*>(ix->cnt.p),
+                         static_cast<int*>(ix->raw_count.p), static_cast<int64_t*>(ix->raw_off.p),
+                         static_cast<int64_t*>(ix->ws_off.p), static_cast<int64_t*>(ix->meta.p), ix->stream);
+  if (rc != LSHX_OK) return rc;
+  int64_t meta[3] = {0, 0, 0};
+  LSHX_CUDA(cudaMemcpyAsync(meta, ix->meta.p, sizeof(meta), cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  const int64_t total = meta[0], maxc = meta[1], ws_total = meta[2];
+  LSHX_REQUIRE(total < (1ll << 40), "query batch matches %lld bucket entries; split the batch", (long long)total);
+  if ((rc = ix->out_ids.reserve((size_t)(total > 0 ? total : 1) * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->out_coll.reserve((size_t)(total > 0 ? total : 1) * 4)) != LSHX_OK) return rc;
+  uint64_t* d_ws = nullptr;
+  if (maxc > (int64_t)index_join_smem_cap()) {   // a query too large for the shared-memory sort: global workspace
+    if ((rc = ix->ws.reserve((size_t)ws_total * 2 * 8)) != LSHX_OK) return rc;
+    d_ws = static_cast<uint64_t*>(ix->ws.p);
+  }
+  rc = index_join(nq, ix->nb, ix->ids[ix->cur], ix->cap, static_cast<const int64_t*>(ix->lo.p),
+                  static_cast<const int*>(ix->cnt.p), static_cast<const int*>(ix->raw_count.p),
+                  static_cast<const int64_t*>(ix->raw_off.p), static_cast<const int64_t*>(ix->ws_off.p), d_ws,
+                  ws_total, static_cast<int64_t*>(ix->out_ids.p), static_cast<int*>(ix->out_coll.p),
+                  static_cast<int*>(ix->uniq.p), ix->stream);
+  if (rc != LSHX_OK) return rc;
+  ix->last_nq = nq;
+  ix->last_total = total;
+  ix->last_max = maxc;
+  if (total_candidates) *total_candidates = total;
+  if (max_candidates) *max_candidates = maxc;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_fetch(lshx_index* ix, int64_t* offsets, int32_t* counts, int64_t* ids, int32_t* collisions) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  LSHX_REQUIRE(ix->last_nq >= 0, "no query result on this handle (lshx_index_query first; add / remove drop it)");
+  const int64_t nq = ix->last_nq;
+  if (nq == 0) {
+    if (offsets) offsets[0] = 0;
+    return LSHX_OK;
+  }
+  if (offsets)
+    LSHX_CUDA(cudaMemcpyAsync(offsets, ix->raw_off.p, (size_t)(nq + 1) * 8, cudaMemcpyDeviceToHost, ix->stream));
+  if (counts) LSHX_CUDA(cudaMemcpyAsync(counts, ix->uniq.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->stream));
+  if (ids && ix->last_total > 0)
+    LSHX_CUDA(cudaMemcpyAsync(ids, ix->out_ids.p, (size_t)ix->last_total * 8, cudaMemcpyDeviceToHost, ix->stream));
+  if (collisions && ix->last_total > 0)
+    LSHX_CUDA(cudaMemcpyAsync(collisions, ix->out_coll.p, (size_t)ix->last_total * 4, cudaMemcpyDeviceToHost,
+                              ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_topk(lshx_index* ix, int top_k, int64_t* out_ids, int32_t* out_count) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  LSHX_REQUIRE(top_k > 0, "top_k must be greater than zero when provided");
+  LSHX_REQUIRE(out_ids != nullptr && out_count != nullptr, "null buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  LSHX_REQUIRE(ix->last_nq >= 0, "no query result on this handle (lshx_index_query first)");
+  const int64_t nq = ix->last_nq;
+  if (nq == 0) return LSHX_OK;
+  int rc;
+  if ((rc = ix->topk_ids.reserve((size_t)nq * top_k * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->topk_cnt.reserve((size_t)nq * 4)) != LSHX_OK) return rc;
+  rc = index_topk(static_cast<const int64_t*>(ix->out_ids.p), static_cast<const int64_t*>(ix->raw_off.p),
+                  static_cast<const int*>(ix->uniq.p), nq, top_k, static_cast<int64_t*>(ix->topk_ids.p),
+                  static_cast<int*>(ix->topk_cnt.p), ix->stream);
+  if (rc != LSHX_OK) return rc;
+  LSHX_CUDA(cudaMemcpyAsync(out_ids, ix->topk_ids.p, (size_t)nq * top_k * 8, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaMemcpyAsync(out_count, ix->topk_cnt.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_rerank(lshx_index* ix, lshx_reranker* r, const float* Q, int q_on_device,
+                                 const float* corpus_device, int64_t n_vectors, int k, double p, int out_stride,
+                                 int64_t* out_ids, float* out_score, int32_t* out_count, int32_t* out_zero) {
+  LSHX_REQUIRE(ix != nullptr && r != nullptr, "null handle");
+  LSHX_REQUIRE(ix->device == r->device, "index and reranker live on different devices");
+  LSHX_REQUIRE(k > 0 || p > 0.0, "k must be > 0");
+  LSHX_REQUIRE(!(p > 1.0), "top_p must be within the range (0, 1]");
+  LSHX_REQUIRE(out_stride > 0 && out_ids && out_score && out_count, "null output buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  std::lock_guard<std::mutex> lk2(r->mu);
+  DeviceGuard g(ix->device);
+  LSHX_REQUIRE(ix->last_nq >= 0, "no query result on this handle (lshx_index_query first)");
+  const int64_t nq = ix->last_nq;
+  if (nq == 0) return LSHX_OK;
+  LSHX_REQUIRE(Q != nullptr && corpus_device != nullptr && n_vectors > 0, "null buffer");
+  const int dim = r->dim;
+  int rc;
+  const float* d_q = Q;
+  if (!q_on_device) {
+    if ((rc = ix->rr_q.reserve((size_t)nq * dim * sizeof(float))) != LSHX_OK) return rc;
+    LSHX_CUDA(cudaMemcpyAsync(ix->rr_q.p, Q, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    d_q = static_cast<const float*>(ix->rr_q.p);
+  }
+  if ((rc = ix->rr_pos.reserve((size_t)nq * out_stride * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->rr_score.reserve((size_t)nq * out_stride * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->rr_count.reserve((size_t)nq * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->rr_zero.reserve((size_t)nq * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->rr_ids.reserve((size_t)nq * out_stride * 8)) != LSHX_OK) return rc;
+  RerankArgs a{};
+  a.Q = d_q;
+  a.nq = nq;
+  a.V = corpus_device;
+  a.n_vectors = n_vectors;
+  a.offs = static_cast<const int64_t*>(ix->raw_off.p);
+  a.ids = static_cast<const int64_t*>(ix->out_ids.p);        // candidate id = row of the resident corpus
+  a.cand_counts = static_cast<const int32_t*>(ix->uniq.p);  // the lists do not fill their slot ranges
+  a.dim = dim;
+  a.k = k;
+  a.p = p;
+  a.out_stride = out_stride;
+  a.out_pos = static_cast<int32_t*>(ix->rr_pos.p);
+  a.out_score = static_cast<float*>(ix->rr_score.p);
+  a.out_count = static_cast<int32_t*>(ix->rr_count.p);
+  a.out_zero = static_cast<int32_t*>(ix->rr_zero.p);
+  a.max_cand = ix->last_max;
+  a.select = true;
+  if (const size_t need = rerank_scratch_bytes(a, nullptr)) {
+    if ((rc = r->big.reserve(need)) != LSHX_OK) return rc;
+    a.big_keys = static_cast<uint64_t*>(r->big.p);
+    a.big_bytes = r->big.cap;
+  }
+  if ((rc = launch_rerank(a, ix->stream)) != LSHX_OK) return rc;
+  rc = index_pos_to_id(static_cast<const int64_t*>(ix->out_ids.p), static_cast<const int64_t*>(ix->raw_off.p),
+                       a.out_pos, a.out_count, nq, out_stride, static_cast<int64_t*>(ix->rr_ids.p), ix->stream);
+  if (rc != LSHX_OK) return rc;
+  LSHX_CUDA(cudaMemcpyAsync(out_ids, ix->rr_ids.p, (size_t)nq * out_stride * 8, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaMemcpyAsync(out_score, ix->rr_score.p, (size_t)nq * out_stride * 4, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaMemcpyAsync(out_count, ix->rr_count.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->stream));
+  if (out_zero)
+    LSHX_CUDA(cudaMemcpyAsync(out_zero, ix->rr_zero.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  return LSHX_OK;
+}

@@ -219,6 +219,153 @@ class FakeLshx:
         return 0
 
 
+class _Index:
+    def __init__(self, nb, bpb):
+        self.nb, self.bpb = nb, bpb
+        self.buckets: list[dict[bytes, set[int]]] = [dict() for _ in range(nb)]
+        self.n = 0
+        self.result = None
+
+
+def _index_methods():
+    """The lshx_index_* entry points of the double: plain dicts of sets, the reference's own data model."""
+
+    def lshx_index_create(self, device, nb, bpb, out_ref):
+        if not (0 < nb <= 255 and 0 < bpb <= 8):
+            self._err = b"bad index shape"
+            return -1
+        return self._new(_Index(nb, bpb), out_ref)
+
+    def lshx_index_destroy(self, h):
+        return self.lshx_hasher_destroy(h)
+
+    def lshx_index_size(self, h):
+        return self._get(h).n
+
+    def lshx_index_add(self, h, sig_ptr, ids_ptr, n, on_dev, stream):
+        ix = self._get(h)
+        sig = _arr(sig_ptr, (n, ix.nb, ix.bpb), np.uint8)
+        ids = _arr(ids_ptr, (n,), np.int64)
+        if (ids < 0).any() or (ids >= 2 ** 56).any():
+            self._err = b"vector ids must lie in [0, 2^56) for the device index"
+            return -1
+        for i in range(n):
+            for b in range(ix.nb):
+                ix.buckets[b].setdefault(sig[i, b].tobytes(), set()).add(int(ids[i]))
+        ix.n += n
+        ix.result = None
+        return 0
+
+    def lshx_index_remove(self, h, ids_ptr, n):
+        ix = self._get(h)
+        gone = set(_arr(ids_ptr, (n,), np.int64).tolist())
+        for band in ix.buckets:
+            for members in band.values():
+                members -= gone
+        ix.result = None
+        return 0
+
+    def lshx_index_clear(self, h):
+        ix = self._get(h)
+        ix.buckets = [dict() for _ in range(ix.nb)]
+        ix.n = 0
+        ix.result = None
+        return 0
+
+    def lshx_index_query(self, h, sig_ptr, nq, on_dev, stream, total_ref, max_ref):
+        ix = self._get(h)
+        sig = _arr(sig_ptr, (nq, ix.nb, ix.bpb), np.uint8)
+        lists, raw = [], []
+        for q in range(nq):
+            counts: dict[int, int] = {}
+            slots = 0
+            for b in range(ix.nb):
+                members = ix.buckets[b].get(sig[q, b].tobytes(), ())
+                slots += len(members)
+                for m in members:
+                    counts[m] = counts.get(m, 0) + 1
+            order = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))
+            lists.append(order)
+            raw.append(slots)
+        ix.result = (lists, raw)
+        total_ref._obj.value = int(sum(raw))
+        max_ref._obj.value = int(max(raw) if raw else 0)
+        self.launches += 3
+        return 0
+
+    def lshx_index_fetch(self, h, offs_ptr, counts_ptr, ids_ptr, coll_ptr):
+        ix = self._get(h)
+        lists, raw = ix.result
+        nq = len(lists)
+        offs = np.concatenate([[0], np.cumsum(raw)]).astype(np.int64)
+        if not _null(offs_ptr):
+            _arr(offs_ptr, (nq + 1,), np.int64)[...] = offs
+        if not _null(counts_ptr) and nq:
+            _arr(counts_ptr, (nq,), np.int32)[...] = [len(x) for x in lists]
+        total = int(offs[-1])
+        for ptr, col, dt in ((ids_ptr, 0, np.int64), (coll_ptr, 1, np.int32)):
+            if not _null(ptr) and total:
+                out = _arr(ptr, (total,), dt)
+                for q, order in enumerate(lists):
+                    out[offs[q]:offs[q] + len(order)] = [kv[col] for kv in order]
+        return 0
+
+    def lshx_index_topk(self, h, k, ids_ptr, count_ptr):
+        ix = self._get(h)
+        lists, _ = ix.result
+        nq = len(lists)
+        out = _arr(ids_ptr, (nq, k), np.int64)
+        cnt = _arr(count_ptr, (nq,), np.int32)
+        out[...] = -1
+        for q, order in enumerate(lists):
+            take = order[:k]
+            out[q, :len(take)] = [i for i, _ in take]
+            cnt[q] = len(take)
+        self.launches += 1
+        return 0
+
+    def lshx_index_rerank(self, h, rh, Q_ptr, q_dev, V_ptr, nvec, k, p, stride, ids_ptr, score_ptr, count_ptr, zero_ptr):
+        ix = self._get(h)
+        dim = self._get(rh)["dim"]
+        lists, _ = ix.result
+        nq = len(lists)
+        Q = _arr(Q_ptr, (nq, dim), np.float32)
+        V = _arr(V_ptr, (nvec, dim), np.float32)
+        offs = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
+        flat = np.array([i for order in lists for i, _ in order], dtype=np.int64)
+        zero = np.zeros(nq, np.int32)
+        sc = self._scores(dim, Q, V, offs, flat, zero)
+        out_ids = _arr(ids_ptr, (nq, stride), np.int64)
+        out_sc = _arr(score_ptr, (nq, stride), np.float32)
+        cnt = _arr(count_ptr, (nq,), np.int32)
+        out_ids[...] = -1
+        for q in range(nq):
+            s = sc[offs[q]:offs[q + 1]]
+            n = s.shape[0]
+            limit = n
+            if p > 0:
+                limit = max(1, math.ceil(n * p)) if n else 0
+                if k > 0:
+                    limit = min(limit, k)
+            elif k > 0:
+                limit = min(k, n)
+            limit = min(limit, n, stride)
+            order = np.lexsort((np.arange(n), -np.nan_to_num(s, nan=-np.inf)))[:limit]
+            out_ids[q, :limit] = flat[offs[q]:offs[q + 1]][order]
+            out_sc[q, :limit] = s[order]
+            cnt[q] = limit
+        if not _null(zero_ptr):
+            _arr(zero_ptr, (nq,), np.int32)[...] = zero
+        self.launches += 2
+        return 0
+
+    return {k: v for k, v in locals().items() if k.startswith("lshx_index_")}
+
+
+for _name, _fn in _index_methods().items():
+    setattr(FakeLshx, _name, _fn)
+
+
 def install() -> FakeLshx:
     """Replace the loaded library inside lshrs_b200._native; returns the double."""
     from lshrs_b200 import _native

@@ -212,3 +212,110 @@ def test_fetch_buckets_strategies():
 
     pk = PerKey()
     assert _lsh(storage=pk)._fetch_buckets(keys) == [{0}, {1}, {0}] and pk.calls == 3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# device mirror of the bucket store (host logic; the C ABI is the oracle-backed double here, the kernels are
+# checked in tests/test_index_gpu.py)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def cpu_double():
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent))
+    import fake_lshx
+
+    from lshrs_b200 import _native
+
+    saved = _native._lib
+    fake = fake_lshx.install()
+    made: list = []
+    yield fake, made
+    for lsh in made:                       # handles of the double must never reach the real library
+        lsh._hasher.close()
+        if lsh._dindex is not None:
+            lsh._dindex.close()
+    from lshrs_b200.utils import similarity
+
+    for r in list(similarity._rerankers.values()):
+        r.close()
+    similarity._rerankers.clear()
+    _native._lib = saved
+
+
+def test_device_mirror_follows_the_bucket_store(cpu_double):
+    """What query_batch(device_index=True) sees is what the storage path sees: buffered (unflushed) operations are
+    in neither, flushed ones in both; delete / clear reach both; results are identical."""
+    fake, made = cpu_double
+    rng = np.random.default_rng(0)
+    n, dim = 400, 16
+    centers = rng.standard_normal((n // 4, dim)).astype(np.float32)
+    X = (np.repeat(centers, 4, axis=0) + 0.05 * rng.standard_normal((n, dim))).astype(np.float32)
+    lsh = LSHRS(dim=dim, num_perm=16, num_bands=8, rows_per_band=2, storage=InMemoryStorage(), buffer_size=1000,
+                vector_fetch_fn=lambda ids: X[np.asarray(ids, dtype=np.int64)], device_index=True)
+    made.append(lsh)
+    lsh.index(list(range(300)), X[:300])
+    for i in range(300, 320):
+        lsh.ingest(i, X[i])                # 20 x 8 = 160 operations stay in the buffer
+    Q = X[rng.integers(0, 320, 64)] + 0.01 * rng.standard_normal((64, dim)).astype(np.float32)
+
+    def same(**kw):
+        a = lsh.query_batch(Q, **kw)
+        b = lsh.query_batch(Q, device_index=True, **kw)
+        assert a == b
+        return a
+
+    before = same(top_k=None)
+    assert all(i < 300 for ids in before for i in ids)          # the buffered 20 are invisible to both paths
+    lsh.flush()
+    after = same(top_k=None)
+    assert any(i >= 300 for ids in after for i in ids)
+    same(top_k=5)
+    same(top_k=3, top_p=0.5)
+    same(top_k=None, top_p=1.0)
+    ids, counts = lsh.query_batch(Q, top_k=5, device_index=True, as_arrays=True)
+    assert ids.shape == (64, 5) and [row[:c].tolist() for row, c in zip(ids, counts)] == same(top_k=5)
+    lsh.delete([int(after[0][0]), 7])
+    gone = same(top_k=None)
+    assert int(after[0][0]) not in gone[0] and all(7 not in ids for ids in gone)
+    lsh.index([7], X[7:8])                                       # a removed id comes back
+    assert any(7 in ids for ids in same(top_k=None))
+    lsh.clear()
+    assert same(top_k=None) == [[] for _ in range(64)]
+    # rows before an invalid one are buffered, flushed by the next flush, and reach the mirror with it
+    bad = X[:10].copy()
+    bad[6] = 0
+    with pytest.raises(ValueError, match="zero vector"):
+        lsh.index(list(range(10)), bad)
+    lsh.flush()
+    assert sorted({i for ids in same(top_k=None) for i in ids}) == [i for i in range(6)
+                                                                    if any(i in ids for ids in same(top_k=None))]
+    with pytest.raises(RuntimeError, match="device_index=True needs"):
+        LSHRS(dim=dim, num_perm=16, num_bands=8, rows_per_band=2, storage=InMemoryStorage()).query_batch(
+            Q, device_index=True)
+
+
+def test_device_mirror_flush_failure_keeps_both_sides_unflushed(cpu_double):
+    fake, made = cpu_double
+
+    class Flaky(InMemoryStorage):
+        fail = True
+
+        def batch_add(self, operations):
+            if self.fail:
+                raise ConnectionError("down")
+            super().batch_add(operations)
+
+    st = Flaky()
+    lsh = LSHRS(dim=8, num_perm=8, num_bands=4, rows_per_band=2, storage=st, device_index=True)
+    made.append(lsh)
+    X = np.random.default_rng(1).standard_normal((5, 8)).astype(np.float32)
+    with pytest.raises(ConnectionError):
+        lsh.index(list(range(5)), X)
+    assert len(lsh._dindex) == 0 and len(lsh._buffer) == 20 and len(lsh._mirror_pending) == 1
+    st.fail = False
+    lsh.flush()
+    assert len(lsh._dindex) == 5 and not lsh._mirror_pending
+    got = lsh.query_batch(X, top_k=None, device_index=True)
+    assert all(i in got[i] for i in range(5)) and got == lsh.query_batch(X, top_k=None)
