@@ -892,7 +892,8 @@ def run_api(args, dev, shape: Shape) -> dict:
     extra = (Xh[:n_single] + 0.05 * rng.standard_normal((n_single, shape.dim))).astype(np.float32)
     allvec = np.concatenate([Xh, extra])          # id -> vector, what vector_fetch_fn serves
     corpus_dev = torch.from_numpy(allvec).to(dev)
-    lsh = LSHRS(dim=shape.dim, num_perm=shape.num_perm, storage=InMemoryStorage(), vector_fetch_fn=lambda ids: allvec[ids])
+    lsh = LSHRS(dim=shape.dim, num_perm=shape.num_perm, storage=InMemoryStorage(), vector_fetch_fn=lambda ids: allvec[ids],
+                device_index=True, device=dev.index)
     ids = list(range(n_index))
     t0 = time.perf_counter()
     lsh.index(ids, Xh)
@@ -918,6 +919,28 @@ def run_api(args, dev, shape: Shape) -> dict:
     # the batched call must return what the per-query call returns
     same = all([i for i, _ in batch[j]] == [i for i, _ in lsh.query(Q[j], top_k=10, top_p=0.2)]
                for j in range(0, 64))
+    # the same queries with the candidates generated on the GPU (device mirror of the bucket store):
+    # lists must equal the storage path's; 8192 queries per call like BASELINE config 4
+    nbig = 8192
+    Qbig = (Xh[rng.integers(0, n_index, nbig)] + 0.05 * rng.standard_normal((nbig, shape.dim))).astype(np.float32)
+    kw = dict(top_k=10, top_p=0.2, corpus=corpus_dev, device_index=True)
+    dev_batch = lsh.query_batch(Q, **kw)
+    same_dev = dev_batch == batch
+    lsh.query_batch(Qbig, **kw)
+
+    def rate(fn, reps=3):
+        best = 0.0
+        for _ in range(reps):
+            t = time.perf_counter()
+            fn()
+            best = max(best, nbig / (time.perf_counter() - t))
+        return best
+
+    dev_lists_qps = rate(lambda: lsh.query_batch(Qbig, **kw))
+    dev_arrays_qps = rate(lambda: lsh.query_batch(Qbig, as_arrays=True, **kw))
+    dev_topk_qps = rate(lambda: lsh.query_batch(Qbig, top_k=10, device_index=True, as_arrays=True))
+    same_topk = lsh.query_batch(Q, top_k=10, device_index=True) == lsh.query_batch(Q, top_k=10)
+    mean_cands = float(np.mean([len(x) for x in lsh.query_batch(Q, top_k=None, device_index=True)]))
     return {
         "storage": "InMemoryStorage (bucket sets in a Python dict; no Redis on the box)",
         "index": {"value": index_vps, "unit": "vectors/s", "rows": n_index},
@@ -928,6 +951,12 @@ def run_api(args, dev, shape: Shape) -> dict:
                         "mean_results": float(np.mean([len(r) for r in got_p]))},
         "query_batch": {"value": batch_qps, "unit": "queries/s", "queries": n_batch,
                         "corpus": "device-resident", "equals_per_query_calls": bool(same)},
+        "query_batch_device_index": {
+            "value": dev_arrays_qps, "unit": "queries/s", "queries_per_call": nbig, "mean_candidates": mean_cands,
+            "what": "query_batch(top_k=10, top_p=0.2, corpus=<HBM>, device_index=True, as_arrays=True): hash, join on "
+                    "the device mirror, rerank and id gather without leaving the GPU; host vectors in, numpy out",
+            "python_lists_value": dev_lists_qps, "top_k_only_value": dev_topk_qps,
+            "equals_storage_path": bool(same_dev and same_topk)},
         "reference_survey_values": {"index": 2.2e3, "get_top_k": 3.9e3, "get_above_p": 2.7e3,
                                     "note": "SURVEY section 8a, reference with its MockStorage in the build container"},
     }
