@@ -51,6 +51,16 @@ class LSHHasher:
     (``LSHRS.load_from_disk`` / ``__setstate__`` do, reference
     lshrs/core/main.py:981, 1044); the device copy is refreshed on the next
     hash.  After mutating an array IN PLACE call :meth:`sync_projections`.
+
+    Arithmetic and the call path.  In the reference ``hash_batch`` IS ``hash_vector`` per row, so a vector
+    always gets the same bytes.  Here a call of up to 32 host rows runs the FP32 latency kernel, larger
+    batches the tensor-core kernel (scaled FP16x3 split, FP32 accumulation) or the FFMA kernel (``dim % 4 != 0``,
+    unaligned input).  They agree -- and agree with the reference -- on every bit whose projection satisfies
+    ``|x.r| > 1e-5 |x||r|`` (measured: the largest margin at which any arm ever differed from the FP32 oracle
+    is 2.6e-7, tests/test_config1_gpu.py); a bit closer to zero than that is decided by rounding in ANY float32
+    implementation and may differ between ``index()`` (batch) and ``query()`` (one vector) of the same vector,
+    about one band key in 10^5 on Gaussian data.  ``set_kernel("ffma")`` pins one FP32 arithmetic for all batch
+    sizes above 32 rows when that matters more than throughput.
     """
 
     def __init__(self, num_bands: int, rows_per_band: int, dim: int, seed: int = 42, *, device: int | None = None) -> None:

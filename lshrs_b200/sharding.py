@@ -12,6 +12,10 @@ one host array.  Two ways to drive it:
   writes its own pinned slice and nothing is exchanged);
 * one process, one thread per GPU: :class:`ShardedHasher` (ctypes drops the
   GIL during the C call).
+
+The host links of a multi-GPU box are not equal (``lshrs_b200/fabric.py``):
+``ShardedHasher(balance="links")`` measures every GPU's H2D rate once and sizes
+the row blocks to it instead of splitting evenly.
 """
 
 from __future__ import annotations
@@ -21,7 +25,7 @@ from collections.abc import Sequence
 
 import numpy as np
 
-__all__ = ["shard_bounds", "shard_range", "max_over_ranks", "gather_rows", "ShardedHasher"]
+__all__ = ["shard_bounds", "weighted_bounds", "shard_range", "max_over_ranks", "gather_rows", "ShardedHasher"]
 
 _TILE = 128  # rows per CTA tile; shard edges are tile-aligned so no tile straddles two GPUs
 
@@ -42,6 +46,23 @@ def shard_bounds(n: int, world_size: int, align: int = _TILE) -> list[tuple[int,
         hi = min((start_tile + t) * align, n)
         bounds.append((lo, hi))
         start_tile += t
+    return bounds
+
+
+def weighted_bounds(n: int, weights: Sequence[float], align: int = _TILE) -> list[tuple[int, int]]:
+    """Contiguous ``align``-row-aligned ranges covering ``range(n)`` with sizes proportional to ``weights``."""
+    if not weights or min(weights) <= 0:
+        raise ValueError("weights must be positive")
+    if n < 0:
+        raise ValueError("n must be >= 0")
+    total = float(sum(weights))
+    bounds, start, acc = [], 0, 0.0
+    for i, w in enumerate(weights):
+        acc += w
+        stop = n if i == len(weights) - 1 else min(n, int(round(n * acc / total / align)) * align)
+        stop = max(stop, start)
+        bounds.append((start, stop))
+        start = stop
     return bounds
 
 
@@ -90,13 +111,21 @@ class ShardedHasher:
     """One ``LSHHasher`` per GPU with identical planes; ``hash_batch_packed`` splits rows across them."""
 
     def __init__(self, num_bands: int, rows_per_band: int, dim: int, seed: int = 42,
-                 devices: Sequence[int] | None = None) -> None:
+                 devices: Sequence[int] | None = None, balance: str = "equal") -> None:
         from lshrs_b200 import _native
         from lshrs_b200.hash.lsh import LSHHasher
 
         if devices is None:
             devices = list(range(max(1, _native.device_count())))
         self.devices = list(devices)
+        if balance not in ("equal", "links"):
+            raise ValueError("balance must be 'equal' or 'links'")
+        self.weights: list[float] | None = None
+        if balance == "links" and len(self.devices) > 1:
+            from lshrs_b200 import fabric
+
+            # host batches cross PCIe host -> device: shards sized to each GPU's measured H2D rate
+            self.weights = [max(r, 1e-3) for r in fabric.probe_links(self.devices)["h2d_gbs"]]
         self.hashers = [LSHHasher(num_bands, rows_per_band, dim, seed, device=d) for d in self.devices]
         self.num_bands, self.rows_per_band, self.dim = num_bands, rows_per_band, dim
         self.bytes_per_band = self.hashers[0].bytes_per_band
@@ -116,7 +145,7 @@ class ShardedHasher:
         arr = np.ascontiguousarray(arr, dtype=np.float32)   # (hash_into below takes float32 rows)
         n = arr.shape[0]
         out = np.empty((n, self.signature_bytes), dtype=np.uint8)
-        bounds = shard_bounds(n, len(self.hashers))
+        bounds = weighted_bounds(n, self.weights) if self.weights else shard_bounds(n, len(self.hashers))
         errors: list[BaseException] = []
 
         def work(h, lo, hi):

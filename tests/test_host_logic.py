@@ -7,7 +7,7 @@ import pytest
 
 from lshrs_b200 import LSHRS, HashSignatures, InMemoryStorage, LSHHasher, bucket_key
 from lshrs_b200._config.config import signatures_from_packed
-from lshrs_b200.sharding import shard_bounds
+from lshrs_b200.sharding import shard_bounds, weighted_bounds
 
 
 def test_hash_signatures_normalizes_iterables():
@@ -319,3 +319,15 @@ def test_device_mirror_flush_failure_keeps_both_sides_unflushed(cpu_double):
     assert len(lsh._dindex) == 5 and not lsh._mirror_pending
     got = lsh.query_batch(X, top_k=None, device_index=True)
     assert all(i in got[i] for i in range(5)) and got == lsh.query_batch(X, top_k=None)
+
+
+def test_weighted_bounds_cover_and_align():
+    b = weighted_bounds(1_000_003, [23.5] * 4 + [36.0] * 4)
+    assert b[0][0] == 0 and b[-1][1] == 1_000_003 and all(b[i][1] == b[i + 1][0] for i in range(7))
+    assert all((hi - lo) % 128 == 0 for lo, hi in b[:-1])
+    sizes = [hi - lo for lo, hi in b]
+    assert abs(sizes[4] / sizes[0] - 36.0 / 23.5) < 0.01
+    assert weighted_bounds(0, [1, 2]) == [(0, 0), (0, 0)]
+    assert sum(hi - lo for lo, hi in weighted_bounds(100, [1, 1, 1])) == 100
+    with pytest.raises(ValueError):
+        weighted_bounds(10, [1, 0])
