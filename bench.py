@@ -753,6 +753,7 @@ def run_b200(args, shape: Shape) -> None:
             api = run_api(args, dev, shape)
         except Exception as exc:  # noqa: BLE001 -- a side measurement must not take the headline down
             api = {"error": repr(exc)}
+    relay_pair = (run.sender, run.receiver)
     del run, X
     torch.cuda.empty_cache()
     if world == 1 and shape.name == "hash768" and not args.no_configs:
@@ -792,6 +793,12 @@ def run_b200(args, shape: Shape) -> None:
             "cpu_baseline": cpu_baseline, "parity": parity, "configs": configs, "rerank": rerank, "api": api,
         }
         emit(line)
+    if relay_pair[0] is not None:
+        relay_pair[0].close()          # the sender lets go of the partner's device slots first
+    if world > 1:
+        barrier()
+    if relay_pair[1] is not None:
+        relay_pair[1].close()
     if shm is not None:
         barrier()
         shm.close()
