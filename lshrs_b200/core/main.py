@@ -182,9 +182,8 @@ class LSHRS:
         signatures = self._hasher.hash_vector(vec)
         self._enqueue_operations(index, signatures)
         if self._dindex is not None:
-            packed = np.frombuffer(b"".join(signatures), dtype=np.uint8)
-            with self._buffer_lock:
-                self._mirror_pending.append((packed, np.array([int(index)], dtype=np.int64)))
+            with self._buffer_lock:   # (bytes, int): turned into arrays when the flush hands them to the mirror
+                self._mirror_pending.append((b"".join(signatures), int(index)))
         self._flush_buffer_if_needed()
 
     def flush(self) -> None:
@@ -203,8 +202,18 @@ class LSHRS:
                 self._buffer[0:0] = pending
                 self._mirror_pending[0:0] = mirror
             raise
-        for sig, ids in mirror:      # the store has them: now the device mirror may
-            self._dindex.add(sig, ids)
+        # the store has them: now the device mirror may (single ingests are coalesced into one add)
+        singles: list[tuple[bytes, int]] = []
+        for sig, ids in [*mirror, (None, None)]:
+            if isinstance(sig, bytes):
+                singles.append((sig, ids))
+                continue
+            if singles:
+                self._dindex.add(np.frombuffer(b"".join(s for s, _ in singles), dtype=np.uint8),
+                                 np.fromiter((i for _, i in singles), dtype=np.int64, count=len(singles)))
+                singles = []
+            if sig is not None:
+                self._dindex.add(sig, ids)
 
     def index(self, indices: Sequence[int], vectors: Optional[np.ndarray] = None) -> None:
         """Ingest a batch: ONE kernel call hashes every row and flags zero vectors.
