@@ -337,6 +337,29 @@ int lshx_index_rerank(lshx_index* ix, lshx_reranker* r, const float* Q, int q_on
                       const float* corpus_device, int64_t n_vectors, int k, double p, int out_stride,
                       int64_t* out_ids, float* out_score, int32_t* out_count, int32_t* out_zero);
 
+/* ---- multi-process plumbing for the signature relay (no reference counterpart) ----
+ *
+ * One rank per GPU (torchrun) cannot share device memory with, or order its streams
+ * against, another process without CUDA IPC.  lshrs_b200/fabric.py uses these to let
+ * a rank on a slow host link hand its signatures over NVLink to a partner on a fast
+ * one.  Plumbing only -- no arithmetic.  IPC handles are the
+ * 64 opaque bytes of cudaIpcMemHandle_t / cudaIpcEventHandle_t; `device` is the
+ * caller's GPU; `stream` a cudaStream_t of that GPU.
+ */
+int lshx_ipc_mem_alloc(int device, size_t bytes, void** dptr, unsigned char* handle_out /* 64 bytes */);
+/* Map another process's allocation; peer access from `device` is enabled lazily. */
+int lshx_ipc_mem_open(int device, const unsigned char* handle, void** dptr);
+int lshx_ipc_mem_close(void* dptr);
+int lshx_ipc_mem_free(int device, void* dptr);
+int lshx_ipc_event_create(int device, void** event, unsigned char* handle_out /* 64 bytes */);
+int lshx_ipc_event_open(int device, const unsigned char* handle, void** event);
+int lshx_ipc_event_record(int device, void* event, void* stream);
+/* cudaStreamWaitEvent: waits for the most recent record ISSUED before this call. */
+int lshx_ipc_event_wait(int device, void* event, void* stream);
+int lshx_ipc_event_destroy(void* event);
+/* cudaMemcpyAsync(cudaMemcpyDefault): peer-to-peer (NVLink), D2H or H2D on `stream`. */
+int lshx_memcpy_async(int device, void* dst, const void* src, size_t bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

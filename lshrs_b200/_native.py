@@ -70,6 +70,16 @@ EXPORTED_SYMBOLS = (
     "lshx_index_fetch",
     "lshx_index_topk",
     "lshx_index_rerank",
+    "lshx_ipc_mem_alloc",
+    "lshx_ipc_mem_open",
+    "lshx_ipc_mem_close",
+    "lshx_ipc_mem_free",
+    "lshx_ipc_event_create",
+    "lshx_ipc_event_open",
+    "lshx_ipc_event_record",
+    "lshx_ipc_event_wait",
+    "lshx_ipc_event_destroy",
+    "lshx_memcpy_async",
 )
 
 
@@ -163,6 +173,29 @@ def _declare(cdll: ctypes.CDLL) -> None:
     cdll.lshx_index_topk.argtypes = [vp, c_int, vp, vp]
     cdll.lshx_index_rerank.restype = c_int
     cdll.lshx_index_rerank.argtypes = [vp, vp, vp, c_int, vp, c_int64, c_int, c_double, c_int, vp, vp, vp, vp]
+
+    from ctypes import c_size_t
+
+    cdll.lshx_ipc_mem_alloc.restype = c_int
+    cdll.lshx_ipc_mem_alloc.argtypes = [c_int, c_size_t, POINTER(vp), vp]
+    cdll.lshx_ipc_mem_open.restype = c_int
+    cdll.lshx_ipc_mem_open.argtypes = [c_int, vp, POINTER(vp)]
+    cdll.lshx_ipc_mem_close.restype = c_int
+    cdll.lshx_ipc_mem_close.argtypes = [vp]
+    cdll.lshx_ipc_mem_free.restype = c_int
+    cdll.lshx_ipc_mem_free.argtypes = [c_int, vp]
+    cdll.lshx_ipc_event_create.restype = c_int
+    cdll.lshx_ipc_event_create.argtypes = [c_int, POINTER(vp), vp]
+    cdll.lshx_ipc_event_open.restype = c_int
+    cdll.lshx_ipc_event_open.argtypes = [c_int, vp, POINTER(vp)]
+    cdll.lshx_ipc_event_record.restype = c_int
+    cdll.lshx_ipc_event_record.argtypes = [c_int, vp, vp]
+    cdll.lshx_ipc_event_wait.restype = c_int
+    cdll.lshx_ipc_event_wait.argtypes = [c_int, vp, vp]
+    cdll.lshx_ipc_event_destroy.restype = c_int
+    cdll.lshx_ipc_event_destroy.argtypes = [vp]
+    cdll.lshx_memcpy_async.restype = c_int
+    cdll.lshx_memcpy_async.argtypes = [c_int, vp, vp, c_size_t, vp]
 
 
 def lib() -> ctypes.CDLL:

@@ -1340,3 +1340,109 @@ extern "C" int lshx_index_rerank(lshx_index* ix, lshx_reranker* r, const float* 
   LSHX_CUDA(cudaStreamSynchronize(ix->stream));
   return LSHX_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// multi-process plumbing for the signature relay (lshrs_b200/fabric.py): CUDA IPC memory and events,
+// peer / host copies on a caller's stream.  No arithmetic; one rank per GPU under torchrun cannot share
+// device memory or order its streams against another process's without these.
+// ---------------------------------------------------------------------------------------
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64 && sizeof(cudaIpcEventHandle_t) == 64, "IPC handles are 64 bytes");
+
+extern "C" int lshx_ipc_mem_alloc(int device, size_t bytes, void** dptr, unsigned char* handle_out) {
+  LSHX_REQUIRE(dptr != nullptr && handle_out != nullptr && bytes > 0, "bad argument");
+  int rc = check_device(device);
+  if (rc != LSHX_OK) return rc;
+  DeviceGuard g(device);
+  *dptr = nullptr;
+  LSHX_CUDA(cudaMalloc(dptr, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, *dptr);
+  if (e != cudaSuccess) {
+    cudaFree(*dptr);
+    *dptr = nullptr;
+    LSHX_CUDA(e);
+  }
+  std::memcpy(handle_out, &h, sizeof(h));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_ipc_mem_open(int device, const unsigned char* handle, void** dptr) {
+  LSHX_REQUIRE(dptr != nullptr && handle != nullptr, "bad argument");
+  int rc = check_device(device);
+  if (rc != LSHX_OK) return rc;
+  DeviceGuard g(device);   // the importing GPU: peer access to the exporting one is enabled lazily
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  LSHX_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_ipc_mem_close(void* dptr) {
+  if (dptr) LSHX_CUDA(cudaIpcCloseMemHandle(dptr));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_ipc_mem_free(int device, void* dptr) {
+  if (!dptr) return LSHX_OK;
+  DeviceGuard g(device);
+  LSHX_CUDA(cudaFree(dptr));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_ipc_event_create(int device, void** event, unsigned char* handle_out) {
+  LSHX_REQUIRE(event != nullptr && handle_out != nullptr, "bad argument");
+  int rc = check_device(device);
+  if (rc != LSHX_OK) return rc;
+  DeviceGuard g(device);
+  cudaEvent_t ev = nullptr;
+  LSHX_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventInterprocess));
+  cudaIpcEventHandle_t h;
+  cudaError_t e = cudaIpcGetEventHandle(&h, ev);
+  if (e != cudaSuccess) {
+    cudaEventDestroy(ev);
+    LSHX_CUDA(e);
+  }
+  std::memcpy(handle_out, &h, sizeof(h));
+  *event = ev;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_ipc_event_open(int device, const unsigned char* handle, void** event) {
+  LSHX_REQUIRE(event != nullptr && handle != nullptr, "bad argument");
+  int rc = check_device(device);
+  if (rc != LSHX_OK) return rc;
+  DeviceGuard g(device);
+  cudaIpcEventHandle_t h;
+  std::memcpy(&h, handle, sizeof(h));
+  cudaEvent_t ev = nullptr;
+  LSHX_CUDA(cudaIpcOpenEventHandle(&ev, h));
+  *event = ev;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_ipc_event_record(int device, void* event, void* stream) {
+  LSHX_REQUIRE(event != nullptr, "null event");
+  DeviceGuard g(device);
+  LSHX_CUDA(cudaEventRecord(static_cast<cudaEvent_t>(event), static_cast<cudaStream_t>(stream)));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_ipc_event_wait(int device, void* event, void* stream) {
+  LSHX_REQUIRE(event != nullptr, "null event");
+  DeviceGuard g(device);
+  LSHX_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(event), 0));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_ipc_event_destroy(void* event) {
+  if (event) LSHX_CUDA(cudaEventDestroy(static_cast<cudaEvent_t>(event)));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_memcpy_async(int device, void* dst, const void* src, size_t bytes, void* stream) {
+  LSHX_REQUIRE(dst != nullptr && src != nullptr, "null buffer");
+  DeviceGuard g(device);
+  LSHX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return LSHX_OK;
+}

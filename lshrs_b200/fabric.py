@@ -28,6 +28,7 @@ Host-side plumbing only: no arithmetic of the hot path lives here.
 
 from __future__ import annotations
 
+import ctypes  # noqa: F401  (annotations)
 import json
 import mmap
 import os
@@ -256,64 +257,126 @@ class RelayHandshake:
 SLOTS = 2
 
 
+def _handle_bytes() -> "ctypes.Array":
+    import ctypes
+
+    return (ctypes.c_ubyte * 64)()
+
+
+class _IpcEvent:
+    """An interprocess CUDA event (``lshx_ipc_event_*``): created here, or opened from a partner's 64-byte handle.
+
+    (torch's own ``Event.from_ipc_handle`` objects crash in ``Stream.wait_event`` in the torch of this image, so
+    the relay keeps its cross-process ordering inside liblshx.)"""
+
+    def __init__(self, device: int, handle: bytes | None = None) -> None:
+        import ctypes
+
+        from lshrs_b200 import _native
+
+        self.device = int(device)
+        self._lib = _native.lib()
+        ev = ctypes.c_void_p()
+        if handle is None:
+            buf = _handle_bytes()
+            _native.check(self._lib.lshx_ipc_event_create(self.device, ctypes.byref(ev), buf))
+            self.handle = bytes(buf)
+        else:
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(handle)
+            _native.check(self._lib.lshx_ipc_event_open(self.device, buf, ctypes.byref(ev)))
+            self.handle = handle
+        self._ev = ev
+
+    def record(self, stream) -> None:
+        from lshrs_b200 import _native
+
+        _native.check(self._lib.lshx_ipc_event_record(self.device, self._ev, stream.cuda_stream))
+
+    def wait(self, stream) -> None:
+        from lshrs_b200 import _native
+
+        _native.check(self._lib.lshx_ipc_event_wait(self.device, self._ev, stream.cuda_stream))
+
+    def destroy(self) -> None:
+        if self._ev is not None:
+            self._lib.lshx_ipc_event_destroy(self._ev)
+            self._ev = None
+
+
+def _copy_async(device: int, dst: int, src: int, nbytes: int, stream) -> None:
+    from lshrs_b200 import _native
+
+    _native.check(_native.lib().lshx_memcpy_async(int(device), dst, src, int(nbytes), stream.cuda_stream))
+
+
 class RelayReceiver:
     """The rank on the fast link: owns the device slots, writes its partner's signatures to the partner's buffer.
 
-    ``export()`` returns what the sender needs (pickled through the process group); ``attach()`` takes the
-    sender's half.  ``drain(chunk_index, nbytes, host_offset)`` enqueues: wait for the sender's full-event of the
-    slot, D2H the slot into the sender's shared host buffer at ``host_offset``, record the free-event.
+    ``export()`` returns what the sender needs (plain bytes / ints, picklable through the process group);
+    ``attach()`` takes the sender's half.  ``drain(k, nbytes, host_offset)`` enqueues: wait for the sender's
+    full-event of the slot, D2H the slot into the sender's shared host buffer at ``host_offset``, record the
+    free-event.
     """
 
     def __init__(self, device, slot_bytes: int, tag: str) -> None:
-        import torch
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes
 
-        self.device, self.slot_bytes, self.tag = device, int(slot_bytes), tag
-        self.slots = [torch.empty(self.slot_bytes, dtype=torch.uint8, device=device) for _ in range(SLOTS)]
-        self.free = [torch.cuda.Event(enable_timing=False, interprocess=True) for _ in range(SLOTS)]
-        self.stream = torch.cuda.Stream(device)
+        import torch
+
+        from lshrs_b200 import _native
+
+        self.device = int(torch.device(device).index)
+        self.slot_bytes, self.tag = int(slot_bytes), tag
+        self._lib = _native.lib()
+        self.slots, handles = [], []
+        for _ in range(SLOTS):
+            p, h = ctypes.c_void_p(), _handle_bytes()
+            _native.check(self._lib.lshx_ipc_mem_alloc(self.device, self.slot_bytes, ctypes.byref(p), h))
+            self.slots.append(p.value)
+            handles.append(bytes(h))
+        self.free = [_IpcEvent(self.device) for _ in range(SLOTS)]
+        self.stream = torch.cuda.Stream(torch.device("cuda", self.device))
         for ev in self.free:
             ev.record(self.stream)
         self.counters = SharedHostBuffer(f"lshx_relay_{tag}_ctr", 8 * 2 * SLOTS, create=True)
         self.counters.array[:] = 0
         self.hs = RelayHandshake(self.counters.array.view(np.int64), SLOTS)
-        self._export = {"slots": [reduce_tensor(t)[1] for t in self.slots],
-                        "free": [ev.ipc_handle() for ev in self.free], "device": int(torch.device(device).index),
-                        "counters": self.counters.name}
-        self._keep = self._export["slots"]      # the producer side of torch's CUDA-IPC ref counting
+        self._export = {"slots": handles, "free": [ev.handle for ev in self.free], "device": self.device,
+                        "counters": self.counters.name, "slot_bytes": self.slot_bytes}
         self.full = None
-        self.host = None
+        self.host_buf = None
+        self.host_ptr = 0
         self.uses = [0] * SLOTS
 
     def export(self) -> dict:
         return self._export
 
     def attach(self, sender: dict) -> None:
-        import torch
-
-        self.full = [torch.cuda.Event.from_ipc_handle(torch.device("cuda", sender["device"]), h)
-                     for h in sender["full"]]
+        self.full = [_IpcEvent(self.device, h) for h in sender["full"]]
         self.host_buf = SharedHostBuffer(sender["host_name"], sender["host_bytes"], create=False)
-        self.host = self.host_buf.pin()
+        self.host_ptr = int(self.host_buf.pin().data_ptr())
 
     def drain(self, k: int, nbytes: int, host_offset: int) -> None:
-        import torch
-
         s = k % SLOTS
         use = self.uses[s]
-        self.hs.wait_sent(s, use)
-        self.stream.wait_event(self.full[s])
-        with torch.cuda.stream(self.stream):
-            self.host[host_offset:host_offset + nbytes].copy_(self.slots[s][:nbytes], non_blocking=True)
+        self.hs.wait_sent(s, use)                 # the sender has ISSUED the full-event of this use
+        self.full[s].wait(self.stream)
+        _copy_async(self.device, self.host_ptr + host_offset, self.slots[s], nbytes, self.stream)
         self.free[s].record(self.stream)
         self.hs.mark_drained(s, use)
         self.uses[s] = use + 1
 
     def close(self) -> None:
         self.stream.synchronize()
-        if self.host is not None:
-            self.host = None
+        for ev in (self.full or []) + self.free:
+            ev.destroy()
+        self.full, self.free = None, []
+        for p in self.slots:
+            self._lib.lshx_ipc_mem_free(self.device, p)
+        self.slots = []
+        if self.host_buf is not None:
             self.host_buf.close()
+            self.host_buf = None
         self.counters.close()
 
 
@@ -323,26 +386,36 @@ class RelaySender:
     def __init__(self, device, host_buf: SharedHostBuffer, tag: str) -> None:
         import torch
 
-        self.device, self.tag = device, tag
-        self.full = [torch.cuda.Event(enable_timing=False, interprocess=True) for _ in range(SLOTS)]
-        self.stream = torch.cuda.Stream(device)
+        from lshrs_b200 import _native
+
+        self.device, self.tag = int(torch.device(device).index), tag
+        self._lib = _native.lib()
+        self.full = [_IpcEvent(self.device) for _ in range(SLOTS)]
+        self.stream = torch.cuda.Stream(torch.device("cuda", self.device))
         for ev in self.full:
             ev.record(self.stream)
-        self._export = {"full": [ev.ipc_handle() for ev in self.full], "host_name": host_buf.name,
-                        "host_bytes": host_buf.nbytes, "device": int(torch.device(device).index)}
-        self.slots = None
+        self._export = {"full": [ev.handle for ev in self.full], "host_name": host_buf.name,
+                        "host_bytes": host_buf.nbytes, "device": self.device}
+        self.slots: list[int] = []
+        self.free: list[_IpcEvent] = []
+        self.counters = None
         self.uses = [0] * SLOTS
 
     def export(self) -> dict:
         return self._export
 
     def attach(self, receiver: dict) -> None:
-        import torch
-        from torch.multiprocessing.reductions import rebuild_cuda_tensor
+        import ctypes
 
-        self.slots = [rebuild_cuda_tensor(*args) for args in receiver["slots"]]
-        peer = torch.device("cuda", receiver["device"])
-        self.free = [torch.cuda.Event.from_ipc_handle(peer, h) for h in receiver["free"]]
+        from lshrs_b200 import _native
+
+        for h in receiver["slots"]:
+            p = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            _native.check(self._lib.lshx_ipc_mem_open(self.device, buf, ctypes.byref(p)))
+            self.slots.append(p.value)
+        self.slot_bytes = int(receiver["slot_bytes"])
+        self.free = [_IpcEvent(self.device, h) for h in receiver["free"]]
         self.counters = SharedHostBuffer(receiver["counters"], 8 * 2 * SLOTS, create=False)
         self.hs = RelayHandshake(self.counters.array.view(np.int64), SLOTS)
 
@@ -353,14 +426,16 @@ class RelaySender:
         ``src`` may be overwritten."""
         import torch
 
+        nbytes = int(src.numel() * src.element_size())
+        if nbytes > self.slot_bytes:
+            raise ValueError(f"chunk of {nbytes} bytes does not fit the partner's {self.slot_bytes}-byte slot")
         s = k % SLOTS
         use = self.uses[s]
         self.stream.wait_event(produced_event)
         self.hs.wait_drained(s, use)               # the receiver has ISSUED the free-event of the previous use
         if use > 0:
-            self.stream.wait_event(self.free[s])
-        with torch.cuda.stream(self.stream):
-            self.slots[s][: src.numel()].copy_(src.view(-1), non_blocking=True)   # P2P over NVLink (copy engine)
+            self.free[s].wait(self.stream)
+        _copy_async(self.device, self.slots[s], int(src.data_ptr()), nbytes, self.stream)   # P2P over NVLink
         self.full[s].record(self.stream)
         self.hs.mark_sent(s, use)
         self.uses[s] = use + 1
@@ -370,6 +445,12 @@ class RelaySender:
 
     def close(self) -> None:
         self.stream.synchronize()
-        self.slots = None
-        if getattr(self, "counters", None) is not None:
+        for p in self.slots:
+            self._lib.lshx_ipc_mem_close(p)
+        self.slots = []
+        for ev in self.free + self.full:
+            ev.destroy()
+        self.free, self.full = [], []
+        if self.counters is not None:
             self.counters.close()
+            self.counters = None

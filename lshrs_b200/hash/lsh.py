@@ -56,8 +56,8 @@ class LSHHasher:
     always gets the same bytes.  Here a call of up to 32 host rows runs the FP32 latency kernel, larger
     batches the tensor-core kernel (scaled FP16x3 split, FP32 accumulation) or the FFMA kernel (``dim % 4 != 0``,
     unaligned input).  They agree -- and agree with the reference -- on every bit whose projection satisfies
-    ``|x.r| > 1e-5 |x||r|`` (measured: the largest margin at which any arm ever differed from the FP32 oracle
-    is 2.6e-7, tests/test_config1_gpu.py); a bit closer to zero than that is decided by rounding in ANY float32
+    ``|x.r| > 1e-5 |x||r|`` (measured: the largest margin at which any arm ever differed from a plain FP32
+    computation is 2.6e-7, tests/test_config1_gpu.py); a bit closer to zero than that is decided by rounding in ANY float32
     implementation and may differ between ``index()`` (batch) and ``query()`` (one vector) of the same vector,
     about one band key in 10^5 on Gaussian data.  ``set_kernel("ffma")`` pins one FP32 arithmetic for all batch
     sizes above 32 rows when that matters more than throughput.

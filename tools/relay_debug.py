@@ -55,48 +55,54 @@ def proc(rank, tag, q01, q10):
         assert recv.get(timeout=30) == "wrote"
         say(rank, "stage 1: partner's D2H visible here:", int(host.array[0]), int(host.array[n // 2 - 1]), int(host.array[n // 2]))
 
-    # ---- stage 2: interprocess events
+    # ---- stage 2: interprocess events (liblshx)
     say(rank, "stage 2: creating ipc event")
-    ev = torch.cuda.Event(enable_timing=False, interprocess=True)
     s = torch.cuda.Stream(dev)
+    ev = fb._IpcEvent(rank)
     ev.record(s)
-    h = ev.ipc_handle()
-    say(rank, "stage 2: handle", type(h), len(h))
-    send.put((rank, h))
+    send.put((rank, ev.handle))
     prank, ph = recv.get(timeout=30)
     say(rank, "stage 2: opening partner's handle")
-    pev = torch.cuda.Event.from_ipc_handle(torch.device("cuda", prank), ph)
+    pev = fb._IpcEvent(rank, ph)
     say(rank, "stage 2: opened; waiting on it")
-    s.wait_event(pev)
+    pev.wait(s)
     s.synchronize()
     say(rank, "stage 2: ok")
 
-    # ---- stage 3: CUDA-IPC tensor + peer copy
-    from torch.multiprocessing.reductions import rebuild_cuda_tensor, reduce_tensor
+    # ---- stage 3: CUDA-IPC memory + peer copy (liblshx)
+    import ctypes
 
+    from lshrs_b200 import _native
+
+    lib = _native.lib()
     if rank == 1:
-        slot = torch.zeros(4 << 20, dtype=torch.uint8, device=dev)
-        say(rank, "stage 3: reducing tensor")
-        args = reduce_tensor(slot)[1]
-        say(rank, "stage 3: reduced, sending")
-        send.put(args)
+        p, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        _native.check(lib.lshx_ipc_mem_alloc(rank, 4 << 20, ctypes.byref(p), h))
+        say(rank, "stage 3: allocated, sending handle")
+        send.put(bytes(h))
         assert recv.get(timeout=60) == "copied"
-        torch.cuda.synchronize()
-        say(rank, "stage 3: slot now holds", int(slot[0]), int(slot[-1]))
-        send.put("seen")
-    else:
-        args = recv.get(timeout=60)
-        say(rank, "stage 3: rebuilding partner's tensor")
-        peer = rebuild_cuda_tensor(*args)
-        say(rank, "stage 3: rebuilt on", peer.device, "; peer copy")
-        src = torch.full((4 << 20,), 7, dtype=torch.uint8, device=dev)
-        with torch.cuda.stream(s):
-            peer.copy_(src, non_blocking=True)
+        back = torch.empty(4 << 20, dtype=torch.uint8, pin_memory=True)
+        fb._copy_async(rank, back.data_ptr(), p.value, 4 << 20, s)
         s.synchronize()
-        say(rank, "stage 3: copied")
+        say(rank, "stage 3: slot now holds", int(back[0]), int(back[-1]))
+        send.put("seen")
+        lib.lshx_ipc_mem_free(rank, p)
+    else:
+        h = recv.get(timeout=60)
+        say(rank, "stage 3: opening partner's memory")
+        p = ctypes.c_void_p()
+        _native.check(lib.lshx_ipc_mem_open(rank, (ctypes.c_ubyte * 64).from_buffer_copy(h), ctypes.byref(p)))
+        say(rank, "stage 3: opened; peer copy")
+        src = torch.full((4 << 20,), 7, dtype=torch.uint8, device=dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            fb._copy_async(rank, p.value, src.data_ptr(), 4 << 20, s)
+        s.synchronize()
+        say(rank, "stage 3: copied; peer copy rate %.1f GB/s" % (20 * (4 << 20) / (time.perf_counter() - t0) / 1e9))
         send.put("copied")
         assert recv.get(timeout=60) == "seen"
-        del peer
+        lib.lshx_ipc_mem_close(p)
 
     # ---- stage 4: the pair
     CH, NB = 16, 1 << 20
