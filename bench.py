@@ -61,6 +61,7 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustain
 NCU_TRAFFIC = {
     "hash768": ("profiles/r1_hash_tc_ncu.csv", 2.428e9, 781_250),
     "hash128": ("profiles/r1_hash_tc_dim128_ncu.csv", 6.601e9, 12_500_000),
+    "rerank": ("profiles/r1_rerank_ncu.csv", 12.34e9, 2048),          # per 2048-query launch of 2000 x 768 candidates
 }
 
 
@@ -1034,7 +1035,11 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks, shap
         entry = {
             "value": nq * world / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "results_per_query": limit,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "frac": gbs / peaks["hbm_gbs"],
+                         "traffic": (NCU_TRAFFIC["rerank"][1] / NCU_TRAFFIC["rerank"][2] * nq
+                                     if (nc, shape.dim) == (2000, 768) else None),
+                         "traffic_source": f"{NCU_TRAFFIC['rerank'][0]}: DRAM bytes of one ncu --set full capture, "
+                                           "scaled by queries", "peak_source": peak_src,
                          "bytes_per_query": bytes_per_q},
             "e2e": {"value": nq * world / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": int(Qh.nbytes + idh.nbytes + offh.nbytes),
@@ -1042,7 +1047,7 @@ def run_rerank(args, dev, rank, world, peaks, peak_src, barrier, max_ranks, shap
             "device_equals_e2e": bool(np.array_equal(ph, pos.cpu().numpy())),
         }
         if cpu is not None:
-            nref = 64
+            nref = 256
             Ch = corpus.cpu().numpy()
             t1 = time.perf_counter()
             bad = 0

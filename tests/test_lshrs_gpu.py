@@ -225,9 +225,11 @@ def test_full_size_config_autoconfig_and_bucket_keys():
     from pathlib import Path
 
     manifest = json.loads((Path(__file__).parent / "golden" / "manifest.json").read_text())
+    by_key = {st.bucket_key(b, h): members for (b, h), members in st._buckets.items()}
+    assert sorted(by_key) == sorted(st.keys())
     for row, keys in zip((10, 11), manifest["bucket_keys_768"]):
-        for key in keys:
-            assert row in st._buckets[key]
+        for key in keys:                      # the reference's own Redis key strings for these two vectors
+            assert row in by_key[key]
 
 
 def test_create_signatures_from_parquet(tmp_path, rng):
