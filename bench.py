@@ -47,6 +47,7 @@ REPO = Path(__file__).resolve().parent
 sys.path.insert(0, str(REPO))
 
 T_PROCESS_START = time.time() - 2.0
+NBUF = 4   # device-side signature buffers per rank: kernels run up to NBUF - 1 chunks ahead of the gather
 SEED = 42
 UNIT = "vectors/s"
 # BASELINE.json configs; "hash768" is the metric's configuration, the others ride along in `configs`
@@ -326,7 +327,7 @@ def make_shard(torch, dev, shape: Shape, rows: int, seed: int):
 
 class ResidentRun:
     """One rank's pass over its resident shard: the projection kernel per chunk on `compute`, the gather of each
-    chunk's signatures into pinned host memory on a copy stream (double-buffered) -- or, for a rank on a slow
+    chunk's signatures into pinned host memory on a copy stream (a ring of NBUF device buffers) -- or, for a rank on a slow
     host link, into its partner's device slot over NVLink (fabric.RelaySender); a partner rank also drains the
     sender's chunks into the sender's host buffer (fabric.RelayReceiver)."""
 
@@ -336,20 +337,23 @@ class ResidentRun:
         self.rows = rows
         self.chunks = [(r0, min(rows, r0 + chunk)) for r0 in range(0, rows, chunk)]
         self.out_host = out_host
-        self.out_dev = [torch.empty((chunk, shape.sig_bytes), dtype=torch.uint8, device=dev) for _ in range(2)]
+        self.nbuf = NBUF
+        self.out_dev = [torch.empty((chunk, shape.sig_bytes), dtype=torch.uint8, device=dev) for _ in range(self.nbuf)]
         self.compute = torch.cuda.Stream(device=dev)
         self.copy = torch.cuda.Stream(device=dev)
-        self.copied = [None, None]   # per output slot: the event after which it may be overwritten
+        self.copied = [None] * self.nbuf   # per output slot: the event after which it may be overwritten
         self.sender = None
         self.receiver = None
         self.k = 0                   # relayed chunks issued so far (both partners count alike)
+        self.next_slot = 0
 
     def one_step(self, kernel_events=None):
         """Steps stream into each other: the gather of a step's last chunks overlaps the next step's first
         kernels; the timed region ends only after every signature is in host memory (drain())."""
         torch, compute, sig = self.torch, self.compute, self.shape.sig_bytes
-        for ci, (r0, r1) in enumerate(self.chunks):
-            slot = ci & 1
+        for r0, r1 in self.chunks:
+            slot = self.next_slot
+            self.next_slot = (slot + 1) % self.nbuf
             if self.copied[slot] is not None:
                 compute.wait_event(self.copied[slot])
             if kernel_events is not None:

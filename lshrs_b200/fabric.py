@@ -17,7 +17,7 @@ Three tools, all driven by a measurement taken at start-up instead of a hard-wir
   measured rates with everybody copying vs. only the fast half copying.  This is the one place NVLink earns its
   keep on this path; no collective, no NCCL on the data path -- a peer-to-peer copy-engine transfer per chunk.
 * :class:`RelaySender` / :class:`RelayReceiver` -- the relay between two PROCESSES (one rank per GPU under
-  torchrun): the receiver owns two device slots (CUDA IPC), the sender owns the pinned host buffer the
+  torchrun): the receiver owns a few device slots (CUDA IPC), the sender owns the pinned host buffer the
   signatures finally land in (POSIX shared memory, registered by both ranks), interprocess CUDA events order the
   copies on the GPUs and :class:`RelayHandshake` orders the two host threads that enqueue them.
 * :func:`weighted_rows` -- row counts proportional to measured link rates (the host-fed e2e path, where the
@@ -254,7 +254,7 @@ class RelayHandshake:
 
 
 # ----------------------------------------------------------------------------------------------- the relay pair
-SLOTS = 2
+SLOTS = 4   # device slots per relay pair: the sender may run SLOTS - 1 chunks ahead of the receiver's D2H
 
 
 def _handle_bytes() -> "ctypes.Array":
