@@ -952,6 +952,47 @@ def run_api(args, dev, shape: Shape) -> dict:
     dev_topk_qps = rate(lambda: lsh.query_batch(Qbig, top_k=10, device_index=True, as_arrays=True))
     same_topk = lsh.query_batch(Q, top_k=10, device_index=True) == lsh.query_batch(Q, top_k=10)
     mean_cands = float(np.mean([len(x) for x in lsh.query_batch(Q, top_k=None, device_index=True)]))
+    # the same calls with the bucket store itself in HBM (DeviceBucketStorage): index() hands over packed signatures,
+    # single queries join on the device; results must equal the dict store's
+    from lshrs_b200 import DeviceBucketStorage
+
+    dst = LSHRS(dim=shape.dim, num_perm=shape.num_perm, storage=DeviceBucketStorage(), vector_fetch_fn=lambda ids: allvec[ids],
+                device=dev.index)
+    dst.index(ids[:4096], Xh[:4096])        # first call sizes the segments and staging buffers: off the clock
+    dst.clear()
+    t0 = time.perf_counter()
+    dst.index(ids, Xh)
+    d_index_vps = n_index / (time.perf_counter() - t0)
+    n_more = 1_000_000                       # a second, larger batch: 1 M x 768 (3 GB of host vectors) in one call
+    rep = -(-n_more // n_index)
+    Xbig = np.tile(Xh, (rep, 1))[:n_more]
+    big = LSHRS(dim=shape.dim, num_perm=shape.num_perm, storage=DeviceBucketStorage(), device=dev.index)
+    big.index(ids[:4096], Xh[:4096])
+    big.clear()
+    t0 = time.perf_counter()
+    big.index(np.arange(n_more), Xbig)
+    big.query_batch(Q[:8], top_k=10)         # the first query sorts the segments: on the clock
+    d_index_big_vps = n_more / (time.perf_counter() - t0)
+    big._storage.index.close()
+    big._hasher.close()
+    del Xbig, big
+    t0 = time.perf_counter()
+    for i in range(n_single):
+        dst.ingest(n_index + i, extra[i])
+    dst.flush()
+    d_ingest_cps = n_single / (time.perf_counter() - t0)
+    dst.get_top_k(Q[-1], topk=10)
+    dst.get_above_p(Q[-1], p=0.2)
+    t0 = time.perf_counter()
+    d_got_k = [dst.get_top_k(Q[i], topk=10) for i in range(n_single)]
+    d_topk_qps = n_single / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    d_got_p = [dst.get_above_p(Q[i], p=0.2) for i in range(n_single)]
+    d_above_qps = n_single / (time.perf_counter() - t0)
+    same_store = (d_got_k == got_k and [[i for i, _ in r] for r in d_got_p] == [[i for i, _ in r] for r in got_p]
+                  and dst.query_batch(Q, top_k=10, top_p=0.2, corpus=corpus_dev) == dev_batch)
+    dst.query_batch(Qbig, as_arrays=True, **kw)
+    d_arrays_qps = rate(lambda: dst.query_batch(Qbig, as_arrays=True, **kw))
     return {
         "storage": "InMemoryStorage (bucket sets in a Python dict; no Redis on the box)",
         "index": {"value": index_vps, "unit": "vectors/s", "rows": n_index},
@@ -968,6 +1009,16 @@ def run_api(args, dev, shape: Shape) -> dict:
                     "the device mirror, rerank and id gather without leaving the GPU; host vectors in, numpy out",
             "python_lists_value": dev_lists_qps, "top_k_only_value": dev_topk_qps,
             "equals_storage_path": bool(same_dev and same_topk)},
+        "device_storage": {
+            "storage": "DeviceBucketStorage (the bucket store itself in HBM; LSHRS(storage=DeviceBucketStorage()))",
+            "index": {"value": d_index_vps, "unit": "vectors/s", "rows": n_index},
+            "index_1m_rows": {"value": d_index_big_vps, "unit": "vectors/s", "rows": n_more,
+                              "note": "host float32 vectors in: PCIe-bound like e2e"},
+            "ingest": {"value": d_ingest_cps, "unit": "calls/s", "calls": n_single},
+            "get_top_k": {"value": d_topk_qps, "unit": "queries/s", "calls": n_single},
+            "get_above_p": {"value": d_above_qps, "unit": "queries/s", "calls": n_single},
+            "query_batch": {"value": d_arrays_qps, "unit": "queries/s", "queries_per_call": nbig},
+            "equals_dict_store": bool(same_store)},
         "reference_survey_values": {"index": 2.2e3, "get_top_k": 3.9e3, "get_above_p": 2.7e3,
                                     "note": "SURVEY section 8a, reference with its MockStorage in the build container"},
     }

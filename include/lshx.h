@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define LSHX_ABI_VERSION 2
+#define LSHX_ABI_VERSION 3
 
 typedef enum lshx_status {
   LSHX_OK = 0,
@@ -297,6 +297,13 @@ int64_t lshx_index_size(const lshx_index* ix);
  */
 int lshx_index_add(lshx_index* ix, const uint8_t* signatures, const int64_t* ids, int64_t n,
                    int on_device, void* stream);
+/*
+ * Single (band, key, id) operations (RedisStorage.add_to_bucket / a batch_add whose
+ * operations are not whole vectors, reference lshrs/storage/redis.py:227-262): n rows
+ * of num_bands entries each, ids_per_band[n][num_bands] with -1 = "nothing for this
+ * band" (the row's key bytes there are ignored).  Host pointers.
+ */
+int lshx_index_add_entries(lshx_index* ix, const uint8_t* signatures, const int64_t* ids_per_band, int64_t n);
 /* Mirror of RedisStorage.remove_indices (LSHRS.delete, main.py:740-771): host ids. */
 int lshx_index_remove(lshx_index* ix, const int64_t* ids_host, int64_t n);
 /* Mirror of RedisStorage.clear (LSHRS.clear, main.py:773-791). */
@@ -312,6 +319,25 @@ int lshx_index_clear(lshx_index* ix);
  */
 int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64_t nq, int on_device, void* stream,
                      int64_t* total_candidates, int64_t* max_candidates);
+/*
+ * RedisStorage.get_bucket (SMEMBERS, reference lshrs/storage/redis.py:264-301) for m
+ * buckets at once -- what makes the index usable as the bucket STORE, not only as
+ * a mirror: bucket t = (band_ids[t], keys[t * bytes_per_band ..]); its members (live
+ * ids, each once, ascending) go to ids_out[offsets[t] .. offsets[t + 1]).  With
+ * ids_out == NULL only sizes are computed: offsets then bound the member counts from
+ * above (removed ids and repeats still counted) and *needed is the ids_out capacity
+ * a second call needs.  Host pointers; drops the last lshx_index_query result.
+ */
+int lshx_index_get_buckets(lshx_index* ix, const int32_t* band_ids, const uint8_t* keys, int64_t m,
+                           int64_t* offsets, int64_t* ids_out, int64_t ids_capacity, int64_t* needed);
+/*
+ * Everything the index holds, for persistence (the reference leaves bucket data to
+ * Redis' own RDB/AOF; an HBM store needs a way out): *n_out = entries per band;
+ * keys_out[num_bands][n][bytes_per_band], ids_out[num_bands][n] (-1 = removed), both
+ * host buffers of `capacity` entries per band >= n, or both NULL for the size only.
+ * Re-import with lshx_index_add_entries (one row per entry).
+ */
+int lshx_index_export(lshx_index* ix, uint8_t* keys_out, int64_t* ids_out, int64_t capacity, int64_t* n_out);
 /*
  * Host copies of the last query's lists: query i owns ids[offsets[i] ..
  * offsets[i] + counts[i]) and, when collisions != NULL, the matching collision

@@ -16,6 +16,7 @@ from lshrs_b200._config.config import HashSignatures
 from lshrs_b200._native import LshxError, LshxUnavailable
 from lshrs_b200.core.main import LSHRS, lshrs
 from lshrs_b200.hash.lsh import LSHHasher
+from lshrs_b200.storage.device import DeviceBucketStorage, DeviceIndex
 from lshrs_b200.storage.memory import BucketOperation, InMemoryStorage, bucket_key
 from lshrs_b200.utils.norm import l2_norm, l2_norm_batch
 from lshrs_b200.utils.similarity import Reranker, cosine_similarity, top_k_cosine, top_k_cosine_batch
@@ -34,6 +35,8 @@ __all__ = [
     "l2_norm",
     "l2_norm_batch",
     "InMemoryStorage",
+    "DeviceBucketStorage",
+    "DeviceIndex",
     "BucketOperation",
     "bucket_key",
     "LshxError",

@@ -31,7 +31,7 @@ __all__ = [
     "EXPORTED_SYMBOLS",
 ]
 
-ABI_VERSION = 2   # LSHX_ABI_VERSION of include/lshx.h this binding was written against
+ABI_VERSION = 3   # LSHX_ABI_VERSION of include/lshx.h this binding was written against
 KERNEL_AUTO, KERNEL_FFMA, KERNEL_TCGEN05 = 0, 1, 2
 KERNEL_TCGEN05_3XTF32 = 4
 KERNEL_TCGEN05_TF32BF16 = 5
@@ -64,7 +64,10 @@ EXPORTED_SYMBOLS = (
     "lshx_index_destroy",
     "lshx_index_size",
     "lshx_index_add",
+    "lshx_index_add_entries",
     "lshx_index_remove",
+    "lshx_index_get_buckets",
+    "lshx_index_export",
     "lshx_index_clear",
     "lshx_index_query",
     "lshx_index_fetch",
@@ -161,6 +164,12 @@ def _declare(cdll: ctypes.CDLL) -> None:
     cdll.lshx_index_size.argtypes = [vp]
     cdll.lshx_index_add.restype = c_int
     cdll.lshx_index_add.argtypes = [vp, vp, vp, c_int64, c_int, vp]
+    cdll.lshx_index_add_entries.restype = c_int
+    cdll.lshx_index_add_entries.argtypes = [vp, vp, vp, c_int64]
+    cdll.lshx_index_get_buckets.restype = c_int
+    cdll.lshx_index_get_buckets.argtypes = [vp, vp, vp, c_int64, vp, vp, c_int64, POINTER(c_int64)]
+    cdll.lshx_index_export.restype = c_int
+    cdll.lshx_index_export.argtypes = [vp, vp, vp, c_int64, POINTER(c_int64)]
     cdll.lshx_index_remove.restype = c_int
     cdll.lshx_index_remove.argtypes = [vp, vp, c_int64]
     cdll.lshx_index_clear.restype = c_int

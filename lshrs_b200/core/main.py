@@ -108,7 +108,14 @@ class LSHRS:
         # flush is added to it right after, so batched queries can generate their candidates on the GPU
         self._dindex = None
         self._mirror_pending: list[tuple[np.ndarray, np.ndarray]] = []   # (signatures, ids) of buffered operations
-        if device_index:
+        # storage=DeviceBucketStorage(): the store itself lives in HBM -- no mirror to keep, index() hands it packed
+        # signatures, queries join on the device
+        self._store_on_device = False
+        if hasattr(storage, "add_packed") and hasattr(storage, "bind"):
+            storage.bind(num_bands, self._hasher.bytes_per_band, self._hasher.device)
+            self._dindex = storage.index
+            self._store_on_device = True
+        elif device_index:
             from lshrs_b200.storage.device import DeviceIndex
 
             self._dindex = DeviceIndex(num_bands, self._hasher.bytes_per_band, device=self._hasher.device)
@@ -181,7 +188,7 @@ class LSHRS:
         vec = self._prepare_vector(vector)
         signatures = self._hasher.hash_vector(vec)
         self._enqueue_operations(index, signatures)
-        if self._dindex is not None:
+        if self._dindex is not None and not self._store_on_device:
             with self._buffer_lock:   # (bytes, int): turned into arrays when the flush hands them to the mirror
                 self._mirror_pending.append((b"".join(signatures), int(index)))
         self._flush_buffer_if_needed()
@@ -240,6 +247,8 @@ class LSHRS:
             )
         packed, zero_flag = self._hasher.hash_batch_packed(arr, return_zero_flag=True)
         nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
+        if self._store_on_device:
+            return self._index_packed(indices, packed, zero_flag)
         # every band key as an exact-length bytes object, created in C (void-dtype tolist)
         keys = np.ascontiguousarray(packed).reshape(len(indices), nb * bpb).view(f"V{bpb}").tolist()
         flags = zero_flag.tolist()
@@ -274,6 +283,52 @@ class LSHRS:
             raise
         queue_mirror(len(indices))
         self.flush()
+
+    def _index_packed(self, indices: Sequence[int], packed: np.ndarray, zero_flag: np.ndarray) -> None:
+        """``index()`` on a store that takes packed signatures (``DeviceBucketStorage.add_packed``).
+
+        No ``(band, bytes, id)`` tuples are built.  What the store holds afterwards, what stays buffered when a row
+        is invalid and the order of operations equal the reference's per-row loop (main.py:504-518): that loop
+        flushes after the row at which the buffer reaches ``buffer_size`` and once at the end, so on an invalid
+        row ``stop`` the rows since the last such flush point stay in the buffer (as tuples, the rare path)."""
+        n, nb, bpb = len(indices), self._hasher.num_bands, self._hasher.bytes_per_band
+        try:
+            ids = np.asarray(indices)
+            if ids.dtype.kind not in "iu" or ids.shape != (n,):
+                raise TypeError
+            ids = ids.astype(np.int64, copy=False)
+        except (TypeError, ValueError, OverflowError):
+            ids = np.fromiter((int(i) for i in indices), dtype=np.int64, count=n)
+        negative = ids < 0
+        invalid = negative | (zero_flag != 0)
+        stop = int(np.argmax(invalid)) if invalid.any() else n
+        with self._buffer_lock:
+            pre = len(self._buffer)
+        per_flush = max(1, -(-self._buffer_size // nb))            # rows between two flushes of the loop
+        first = max(1, -(-(self._buffer_size - pre) // nb))        # rows until its first flush
+        if stop == n:
+            sent = n
+        else:
+            sent = 0 if stop < first else first + (stop - first) // per_flush * per_flush
+
+        def as_ops(lo: int, hi: int) -> list[BucketOperation]:
+            keys = np.ascontiguousarray(packed[lo:hi]).reshape(hi - lo, nb * bpb).view(f"V{bpb}").tolist()
+            return [(b, key, idx) for row, idx in zip(keys, ids[lo:hi].tolist()) for b, key in enumerate(row)]
+
+        if sent:
+            self.flush()                    # operations buffered by earlier ingest() calls go first, in order
+            try:
+                self._storage.add_packed(packed[:sent], ids[:sent])
+            except Exception as exc:
+                logger.error(f"Failed to flush buffer to Redis: {exc}")
+                with self._buffer_lock:     # like flush(): nothing is lost, the operations are buffered again
+                    self._buffer[0:0] = as_ops(0, stop)
+                raise
+        if stop < n:
+            if stop > sent:
+                with self._buffer_lock:
+                    self._buffer.extend(as_ops(sent, stop))
+            raise ValueError("index must be non-negative" if negative[stop] else _ZERO_VECTOR_MSG)
 
     # ------------------------------------------------------------------ querying
     def query(self, vector: np.ndarray, *, top_k: Optional[int] = 10,
@@ -322,7 +377,7 @@ class LSHRS:
         return list(self.query(vector, top_k=None, top_p=p))  # type: ignore[arg-type]
 
     def query_batch(self, vectors: np.ndarray, *, top_k: Optional[int] = 10, top_p: Optional[float] = None,
-                    corpus=None, device_index: bool = False, as_arrays: bool = False):
+                    corpus=None, device_index: Optional[bool] = None, as_arrays: bool = False):
         """``query`` for many vectors: one hash launch, one rerank launch.
 
         Returns one result list per row, identical to calling :meth:`query` row
@@ -330,9 +385,10 @@ class LSHRS:
         (a CUDA torch tensor ``(N, dim)`` resident in HBM, candidate id = row --
         the device-side stand-in for ``vector_fetch_fn``), else from ``vector_fetch_fn``.
 
-        ``device_index=True`` (needs ``LSHRS(device_index=True)``): the candidates come from the mirror of the
-        bucket store in HBM instead of ``num_bands`` bucket reads per query -- same lists, same order, same
-        results (``lshx_index_query``); with ``corpus`` the lists never leave the GPU before the rerank.
+        ``device_index=True`` (needs ``LSHRS(device_index=True)`` or ``storage=DeviceBucketStorage()``, with which
+        it is the default): the candidates come from the band index in HBM instead of ``num_bands`` bucket reads
+        per query -- same lists, same order, same results (``lshx_index_query``); with ``corpus`` the lists never
+        leave the GPU before the rerank.
         ``as_arrays=True`` returns numpy arrays instead of Python lists (-1 padded ids ``(nq, k)``, then scores
         for ``top_p``, then counts): at several hundred thousand queries per second the lists are what costs.
         """
@@ -340,6 +396,8 @@ class LSHRS:
         if arr.ndim != 2 or arr.shape[1] != self._dim:
             raise ValueError(f"Vectors must have shape (n, {self._dim}); received {arr.shape}")
         nq = arr.shape[0]
+        if device_index is None:
+            device_index = self._store_on_device
         if as_arrays and not device_index:
             raise ValueError("as_arrays=True is only available with device_index=True")
         if device_index and self._dindex is None:
@@ -357,32 +415,10 @@ class LSHRS:
             raise ValueError(_ZERO_VECTOR_MSG)
         nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
         if device_index:
-            _, maxc = self._dindex.query(packed)
-            if top_p is None and top_k is not None:
-                ids, counts = self._dindex.topk(top_k)
-                if as_arrays:
-                    return ids, counts
-                rows, cl = ids.tolist(), counts.tolist()
-                return [rows[i][:cl[i]] for i in range(nq)]
-            if top_p is not None and corpus is not None:
-                stride = max(1, math.ceil(maxc * top_p))
-                if top_k is not None:
-                    stride = min(stride, int(top_k))
-                rer = _get_reranker(self._dim, self._hasher.device)
-                ids, scores, counts, zero = self._dindex.rerank(rer, arr, corpus, k=int(top_k or 0), p=float(top_p),
-                                                                stride=stride)
-                if zero[counts > 0].any():
-                    raise ValueError("Cannot normalize zero vector")
-                if as_arrays:
-                    return ids, scores, counts
-                rows, sc, cl = ids.tolist(), scores.tolist(), counts.tolist()
-                return [list(zip(rows[i][:cl[i]], sc[i][:cl[i]])) for i in range(nq)]
-            offs, counts, flat = self._dindex.fetch()
-            if as_arrays and top_p is None:
-                return offs, counts, flat
-            if as_arrays:
-                raise ValueError("as_arrays=True with top_p needs corpus= (the rerank on the device)")
-            ordered_all = [flat[o:o + c].tolist() for o, c in zip(offs[:-1].tolist(), counts.tolist())]
+            with self._dindex.lock:     # the result of query() lives in the handle until it is consumed
+                done, ordered_all = self._query_batch_on_device(arr, packed, top_k, top_p, corpus, as_arrays)
+            if done:
+                return ordered_all
         else:
             # every (query, band) bucket in ONE storage round trip when the backend allows it
             keys = np.ascontiguousarray(packed).reshape(nq, nb * bpb).view(f"V{bpb}").tolist()
@@ -426,17 +462,47 @@ class LSHRS:
             out.append([(ids[int(pos[row, i])], float(score[row, i])) for i in range(int(count[row]))] if ids else [])
         return out
 
+    def _query_batch_on_device(self, arr, packed, top_k, top_p, corpus, as_arrays):
+        """The device-index branch of :meth:`query_batch`; ``(True, result)`` or ``(False, candidate lists)``."""
+        nq = arr.shape[0]
+        _, maxc = self._dindex.query(packed)
+        if top_p is None and top_k is not None:
+            ids, counts = self._dindex.topk(top_k)
+            if as_arrays:
+                return True, (ids, counts)
+            rows, cl = ids.tolist(), counts.tolist()
+            return True, [rows[i][:cl[i]] for i in range(nq)]
+        if top_p is not None and corpus is not None:
+            stride = max(1, math.ceil(maxc * top_p))
+            if top_k is not None:
+                stride = min(stride, int(top_k))
+            rer = _get_reranker(self._dim, self._hasher.device)
+            ids, scores, counts, zero = self._dindex.rerank(rer, arr, corpus, k=int(top_k or 0), p=float(top_p),
+                                                            stride=stride)
+            if zero[counts > 0].any():
+                raise ValueError("Cannot normalize zero vector")
+            if as_arrays:
+                return True, (ids, scores, counts)
+            rows, sc, cl = ids.tolist(), scores.tolist(), counts.tolist()
+            return True, [list(zip(rows[i][:cl[i]], sc[i][:cl[i]])) for i in range(nq)]
+        offs, counts, flat = self._dindex.fetch()
+        if as_arrays and top_p is None:
+            return True, (offs, counts, flat)
+        if as_arrays:
+            raise ValueError("as_arrays=True with top_p needs corpus= (the rerank on the device)")
+        return False, [flat[o:o + c].tolist() for o, c in zip(offs[:-1].tolist(), counts.tolist())]
+
     # ------------------------------------------------------------------ maintenance
     def delete(self, indices: Union[int, Sequence[int]]) -> None:
         to_remove = [indices] if isinstance(indices, int) else [int(i) for i in indices]
         self._storage.remove_indices(to_remove)
-        if self._dindex is not None:
+        if self._dindex is not None and not self._store_on_device:
             self._dindex.remove(to_remove)
 
     def clear(self) -> None:
         self.flush()
         self._storage.clear()
-        if self._dindex is not None:
+        if self._dindex is not None and not self._store_on_device:
             self._dindex.clear()
 
     def stats(self) -> dict[str, Any]:
@@ -496,7 +562,7 @@ class LSHRS:
             "config": dict(self._config), "redis_config": dict(self._redis_config),
             "projections": [np.asarray(m, dtype=np.float32) for m in self._hasher.projections],
             # the reference does not persist its storage (a Redis connection); the in-memory double travels
-            "storage": self._storage if isinstance(self._storage, InMemoryStorage) else None,
+            "storage": self._storage if isinstance(self._storage, InMemoryStorage) or self._store_on_device else None,
         }
 
     def __setstate__(self, state: dict[str, Any]) -> None:
@@ -521,6 +587,11 @@ class LSHRS:
         return arr
 
     def _candidate_counts(self, query_vector: np.ndarray) -> dict[int, int]:
+        if self._store_on_device:
+            # one join on the device instead of num_bands bucket reads; the list arrives in (-collisions, id) order
+            packed = self._hasher.hash_batch_packed(np.asarray(query_vector, dtype=np.float32).reshape(1, self._dim))
+            ids, coll = self._dindex.query_one(packed)
+            return dict(zip(ids.tolist(), coll.tolist()))
         signatures = self._hasher.hash_vector(query_vector)
         counts: dict[int, int] = {}
         for band_id, hash_val in enumerate(signatures):

@@ -33,10 +33,12 @@ constexpr uint64_t ID_MASK = (1ull << ID_BITS) - 1;
 // ---------------------------------------------------------------------------------------------------
 // append
 // ---------------------------------------------------------------------------------------------------
+// ids: one per vector, or (per_band) one per (vector, band) with -1 = "no entry in this band" (stored as a
+// tombstone, which no query ever returns): how single (band, key, id) operations reach the equal-length segments
 __global__ void index_append_kernel(const uint8_t* __restrict__ sig, const int64_t* __restrict__ ids, int64_t n,
                                     int nb, int bpb, uint64_t* __restrict__ keys, int64_t* __restrict__ out_ids,
                                     int64_t cap, int64_t at, unsigned long long* __restrict__ max_id,
-                                    int* __restrict__ bad) {
+                                    int* __restrict__ bad, int per_band) {
   const int64_t total = n * nb;
   unsigned long long local_max = 0;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
@@ -45,8 +47,8 @@ __global__ void index_append_kernel(const uint8_t* __restrict__ sig, const int64
     const uint8_t* src = sig + (i * nb + b) * (int64_t)bpb;
     uint64_t key = 0;
     for (int j = 0; j < bpb; ++j) key |= (uint64_t)src[j] << (8 * j);
-    const int64_t id = ids[i];
-    if (id < 0 || (uint64_t)id > ID_MASK) *bad = 1;
+    const int64_t id = per_band ? ids[t] : ids[i];
+    if ((id < 0 && !(per_band && id == -1)) || (id >= 0 && (uint64_t)id > ID_MASK)) *bad = 1;
     keys[b * cap + at + i] = key;
     out_ids[b * cap + at + i] = id;
     if (id > 0 && (unsigned long long)id > local_max) local_max = (unsigned long long)id;
@@ -401,6 +403,42 @@ __global__ void index_pos_to_id_kernel(const int64_t* __restrict__ cand, const i
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// single buckets (the storage protocol's get_bucket, reference lshrs/storage/redis.py get_bucket = SMEMBERS)
+// ---------------------------------------------------------------------------------------------------
+__global__ void index_bucket_lookup_kernel(const int* __restrict__ band_ids, const uint64_t* __restrict__ want, int64_t m,
+                                           const uint64_t* __restrict__ keys, int64_t n, int64_t cap,
+                                           int64_t* __restrict__ lo_out, int64_t* __restrict__ cnt_out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < m; t += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = want[t];
+    const uint64_t* k = keys + band_ids[t] * cap;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(k + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    int64_t lo2 = lo, hi2 = n;
+    while (lo2 < hi2) {
+      const int64_t mid = (lo2 + hi2) >> 1;
+      if (__ldg(k + mid) <= key) lo2 = mid + 1; else hi2 = mid;
+    }
+    lo_out[t] = lo;
+    cnt_out[t] = lo2 - lo;
+  }
+}
+
+// one CTA per bucket: its id range, as stored (ascending ids, duplicates adjacent, tombstones last), to out + off[t]
+__global__ void index_bucket_gather_kernel(const int* __restrict__ band_ids, const int64_t* __restrict__ lo,
+                                           const int64_t* __restrict__ off, int64_t m, const int64_t* __restrict__ ids,
+                                           int64_t cap, int64_t* __restrict__ out) {
+  for (int64_t t = blockIdx.x; t < m; t += gridDim.x) {
+    const int64_t c = off[t + 1] - off[t];
+    const int64_t* src = ids + band_ids[t] * cap + lo[t];
+    int64_t* dst = out + off[t];
+    for (int64_t i = threadIdx.x; i < c; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
 unsigned grid_for(int64_t work, int threads) {
   int64_t g = (work + threads - 1) / threads;
   if (g < 1) g = 1;
@@ -414,9 +452,10 @@ unsigned grid_for(int64_t work, int threads) {
 // host-side launchers
 // ---------------------------------------------------------------------------------------------------
 int index_append(const uint8_t* d_sig, const int64_t* d_ids, int64_t n, int nb, int bpb, uint64_t* keys, int64_t* ids,
-                 int64_t cap, int64_t at, unsigned long long* d_max_id, int* d_bad, cudaStream_t st) {
+                 int64_t cap, int64_t at, unsigned long long* d_max_id, int* d_bad, int per_band, cudaStream_t st) {
   if (n <= 0) return LSHX_OK;
-  index_append_kernel<<<grid_for(n * nb, 256), 256, 0, st>>>(d_sig, d_ids, n, nb, bpb, keys, ids, cap, at, d_max_id, d_bad);
+  index_append_kernel<<<grid_for(n * nb, 256), 256, 0, st>>>(d_sig, d_ids, n, nb, bpb, keys, ids, cap, at, d_max_id, d_bad,
+                                                             per_band);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;
@@ -462,6 +501,25 @@ int index_lookup_scan(const uint8_t* d_sig, int64_t nq, int nb, int bpb, const u
   index_lookup_kernel<<<grid_for(nq * nb, 256), 256, 0, st>>>(d_sig, nq, nb, bpb, keys, n, cap, d_lo, d_cnt, d_raw_count);
   index_scan_kernel<<<1, 1024, 0, st>>>(d_raw_count, nq, d_raw_off, d_ws_off, d_meta);
   count_launch(2);
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
+
+int index_bucket_lookup(const int* d_band_ids, const uint64_t* d_want, int64_t m, const uint64_t* keys, int64_t n,
+                        int64_t cap, int64_t* d_lo, int64_t* d_cnt, cudaStream_t st) {
+  if (m <= 0) return LSHX_OK;
+  index_bucket_lookup_kernel<<<grid_for(m, 128), 128, 0, st>>>(d_band_ids, d_want, m, keys, n, cap, d_lo, d_cnt);
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
+
+int index_bucket_gather(const int* d_band_ids, const int64_t* d_lo, const int64_t* d_off, int64_t m, const int64_t* ids,
+                        int64_t cap, int64_t* d_out, cudaStream_t st) {
+  if (m <= 0) return LSHX_OK;
+  index_bucket_gather_kernel<<<(unsigned)(m < 148 * 8 ? m : 148 * 8), 256, 0, st>>>(d_band_ids, d_lo, d_off, m, ids, cap,
+                                                                                    d_out);
+  count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;
 }

@@ -1079,8 +1079,8 @@ extern "C" int lshx_index_destroy(lshx_index* ix) {
 
 extern "C" int64_t lshx_index_size(const lshx_index* ix) { return ix ? ix->n : 0; }
 
-extern "C" int lshx_index_add(lshx_index* ix, const uint8_t* signatures, const int64_t* ids, int64_t n,
-                              int on_device, void* stream) {
+static int index_add_common(lshx_index* ix, const uint8_t* signatures, const int64_t* ids, int64_t n, int on_device,
+                            void* stream, int per_band) {
   LSHX_REQUIRE(ix != nullptr, "null handle");
   LSHX_REQUIRE(n >= 0, "n must be >= 0");
   if (n == 0) return LSHX_OK;
@@ -1090,13 +1090,14 @@ extern "C" int lshx_index_add(lshx_index* ix, const uint8_t* signatures, const i
   int rc = index_reserve(ix, ix->n + n);
   if (rc != LSHX_OK) return rc;
   const size_t sig_bytes = (size_t)n * ix->nb * ix->bpb;
+  const size_t id_bytes = (size_t)n * 8 * (per_band ? ix->nb : 1);
   const uint8_t* d_sig = signatures;
   const int64_t* d_ids = ids;
   if (!on_device) {
     if ((rc = ix->stage_sig.reserve(sig_bytes)) != LSHX_OK) return rc;
-    if ((rc = ix->stage_ids.reserve((size_t)n * 8)) != LSHX_OK) return rc;
+    if ((rc = ix->stage_ids.reserve(id_bytes)) != LSHX_OK) return rc;
     LSHX_CUDA(cudaMemcpyAsync(ix->stage_sig.p, signatures, sig_bytes, cudaMemcpyHostToDevice, ix->stream));
-    LSHX_CUDA(cudaMemcpyAsync(ix->stage_ids.p, ids, (size_t)n * 8, cudaMemcpyHostToDevice, ix->stream));
+    LSHX_CUDA(cudaMemcpyAsync(ix->stage_ids.p, ids, id_bytes, cudaMemcpyHostToDevice, ix->stream));
     d_sig = static_cast<const uint8_t*>(ix->stage_sig.p);
     d_ids = static_cast<const int64_t*>(ix->stage_ids.p);
   } else {
@@ -1104,7 +1105,7 @@ extern "C" int lshx_index_add(lshx_index* ix, const uint8_t* signatures, const i
     LSHX_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
   }
   rc = index_append(d_sig, d_ids, n, ix->nb, ix->bpb, ix->keys[ix->cur], ix->ids[ix->cur], ix->cap, ix->n,
-                    ix->d_max_id, ix->d_bad, ix->stream);
+                    ix->d_max_id, ix->d_bad, per_band, ix->stream);
   if (rc != LSHX_OK) return rc;
   int bad = 0;
   LSHX_CUDA(cudaMemcpyAsync(&bad, ix->d_bad, 4, cudaMemcpyDeviceToHost, ix->stream));
@@ -1117,6 +1118,15 @@ extern "C" int lshx_index_add(lshx_index* ix, const uint8_t* signatures, const i
   ix->n += n;
   ix->last_nq = -1;
   return LSHX_OK;
+}
+
+extern "C" int lshx_index_add(lshx_index* ix, const uint8_t* signatures, const int64_t* ids, int64_t n,
+                              int on_device, void* stream) {
+  return index_add_common(ix, signatures, ids, n, on_device, stream, 0);
+}
+
+extern "C" int lshx_index_add_entries(lshx_index* ix, const uint8_t* signatures, const int64_t* ids_per_band, int64_t n) {
+  return index_add_common(ix, signatures, ids_per_band, n, 0, nullptr, 1);
 }
 
 extern "C" int lshx_index_clear(lshx_index* ix) {
@@ -1230,6 +1240,110 @@ extern "C" int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64
   ix->last_max = maxc;
   if (total_candidates) *total_candidates = total;
   if (max_candidates) *max_candidates = maxc;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_get_buckets(lshx_index* ix, const int32_t* band_ids, const uint8_t* keys, int64_t m,
+                                      int64_t* offsets, int64_t* ids_out, int64_t ids_capacity, int64_t* needed) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  LSHX_REQUIRE(m >= 0, "m must be >= 0");
+  LSHX_REQUIRE(offsets != nullptr, "null buffer");
+  if (needed) *needed = 0;
+  offsets[0] = 0;
+  if (m == 0) return LSHX_OK;
+  LSHX_REQUIRE(band_ids != nullptr && keys != nullptr, "null buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  std::vector<uint64_t> want((size_t)m);
+  for (int64_t t = 0; t < m; ++t) {
+    LSHX_REQUIRE(band_ids[t] >= 0 && band_ids[t] < ix->nb, "band id %d outside [0, %d)", band_ids[t], ix->nb);
+    uint64_t k = 0;
+    for (int j = 0; j < ix->bpb; ++j) k |= (uint64_t)keys[t * ix->bpb + j] << (8 * j);
+    want[(size_t)t] = k;
+  }
+  if (ix->n == 0) {
+    for (int64_t t = 0; t < m; ++t) offsets[t + 1] = 0;
+    return LSHX_OK;
+  }
+  int rc = index_make_sorted(ix);
+  if (rc != LSHX_OK) return rc;
+  // scratch in the query buffers (their contents die with last_nq below)
+  ix->last_nq = -1;
+  if ((rc = ix->q_sig.reserve((size_t)m * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->cnt.reserve((size_t)m * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->lo.reserve((size_t)m * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->raw_off.reserve((size_t)(m + 1) * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->ws_off.reserve((size_t)m * 8)) != LSHX_OK) return rc;
+  LSHX_CUDA(cudaMemcpyAsync(ix->q_sig.p, want.data(), (size_t)m * 8, cudaMemcpyHostToDevice, ix->stream));
+  LSHX_CUDA(cudaMemcpyAsync(ix->cnt.p, band_ids, (size_t)m * 4, cudaMemcpyHostToDevice, ix->stream));
+  rc = index_bucket_lookup(static_cast<const int*>(ix->cnt.p), static_cast<const uint64_t*>(ix->q_sig.p), m,
+                           ix->keys[ix->cur], ix->n, ix->cap, static_cast<int64_t*>(ix->lo.p),
+                           static_cast<int64_t*>(ix->ws_off.p), ix->stream);
+  if (rc != LSHX_OK) return rc;
+  std::vector<int64_t> raw((size_t)m + 1);
+  LSHX_CUDA(cudaMemcpyAsync(raw.data() + 1, ix->ws_off.p, (size_t)m * 8, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  raw[0] = 0;
+  for (int64_t t = 0; t < m; ++t) raw[(size_t)t + 1] += raw[(size_t)t];
+  const int64_t total = raw[(size_t)m];
+  if (needed) *needed = total;
+  if (ids_out == nullptr || ids_capacity < total) {
+    // sizes only: an upper bound per bucket (stored entries, removed ones and repeats included)
+    for (int64_t t = 0; t <= m; ++t) offsets[t] = raw[(size_t)t];
+    if (ids_out != nullptr) {
+      set_error("ids_out holds %lld entries, the buckets may need %lld", (long long)ids_capacity, (long long)total);
+      return LSHX_ERR_INVALID_ARG;
+    }
+    return LSHX_OK;
+  }
+  if (total == 0) {
+    for (int64_t t = 0; t < m; ++t) offsets[t + 1] = 0;
+    return LSHX_OK;
+  }
+  if ((rc = ix->out_ids.reserve((size_t)total * 8)) != LSHX_OK) return rc;
+  LSHX_CUDA(cudaMemcpyAsync(ix->raw_off.p, raw.data(), (size_t)(m + 1) * 8, cudaMemcpyHostToDevice, ix->stream));
+  rc = index_bucket_gather(static_cast<const int*>(ix->cnt.p), static_cast<const int64_t*>(ix->lo.p),
+                           static_cast<const int64_t*>(ix->raw_off.p), m, ix->ids[ix->cur], ix->cap,
+                           static_cast<int64_t*>(ix->out_ids.p), ix->stream);
+  if (rc != LSHX_OK) return rc;
+  std::vector<int64_t> stored((size_t)total);
+  LSHX_CUDA(cudaMemcpyAsync(stored.data(), ix->out_ids.p, (size_t)total * 8, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  // SET members: live ids, each once (they are stored in ascending order, removed ones as -1 at the end)
+  int64_t w = 0;
+  for (int64_t t = 0; t < m; ++t) {
+    const int64_t begin = w;
+    for (int64_t e = raw[(size_t)t]; e < raw[(size_t)t + 1]; ++e) {
+      const int64_t id = stored[(size_t)e];
+      if (id < 0 || (w > begin && ids_out[w - 1] == id)) continue;
+      ids_out[w++] = id;
+    }
+    offsets[t + 1] = w;
+  }
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_export(lshx_index* ix, uint8_t* keys_out, int64_t* ids_out, int64_t capacity, int64_t* n_out) {
+  LSHX_REQUIRE(ix != nullptr && n_out != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  *n_out = ix->n;
+  if (keys_out == nullptr && ids_out == nullptr) return LSHX_OK;   // size only
+  LSHX_REQUIRE(keys_out != nullptr && ids_out != nullptr, "null buffer");
+  LSHX_REQUIRE(capacity >= ix->n, "buffers hold %lld entries per band, the index has %lld", (long long)capacity,
+               (long long)ix->n);
+  if (ix->n == 0) return LSHX_OK;
+  int rc = index_make_sorted(ix);
+  if (rc != LSHX_OK) return rc;
+  const int64_t n = ix->n;
+  std::vector<uint64_t> k((size_t)ix->nb * n);
+  LSHX_CUDA(cudaMemcpy2DAsync(k.data(), (size_t)n * 8, ix->keys[ix->cur], (size_t)ix->cap * 8, (size_t)n * 8,
+                              (size_t)ix->nb, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaMemcpy2DAsync(ids_out, (size_t)n * 8, ix->ids[ix->cur], (size_t)ix->cap * 8, (size_t)n * 8,
+                              (size_t)ix->nb, cudaMemcpyDeviceToHost, ix->stream));
+  LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+  for (size_t e = 0; e < k.size(); ++e)
+    for (int j = 0; j < ix->bpb; ++j) keys_out[e * ix->bpb + j] = (uint8_t)(k[e] >> (8 * j));
   return LSHX_OK;
 }
 

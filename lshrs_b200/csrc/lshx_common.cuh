@@ -120,7 +120,11 @@ int launch_l2_normalize(const float* d_X, int64_t n, int dim, float* d_out, int3
 // ---- device band index / candidate join (index_join.cu) ---------------------------
 // Segments: keys[b * cap + e], ids[b * cap + e] for band b, entry e < n.
 int index_append(const uint8_t* d_sig, const int64_t* d_ids, int64_t n, int nb, int bpb, uint64_t* keys, int64_t* ids,
-                 int64_t cap, int64_t at, unsigned long long* d_max_id, int* d_bad, cudaStream_t st);
+                 int64_t cap, int64_t at, unsigned long long* d_max_id, int* d_bad, int per_band, cudaStream_t st);
+int index_bucket_lookup(const int* d_band_ids, const uint64_t* d_want, int64_t m, const uint64_t* keys, int64_t n,
+                        int64_t cap, int64_t* d_lo, int64_t* d_cnt, cudaStream_t st);
+int index_bucket_gather(const int* d_band_ids, const int64_t* d_lo, const int64_t* d_off, int64_t m, const int64_t* ids,
+                        int64_t cap, int64_t* d_out, cudaStream_t st);
 size_t index_sort_hist_entries(int64_t n, int nb);
 int index_sort(uint64_t* keys[2], int64_t* ids[2], int* cur, int64_t n, int64_t cap, int nb, int key_bytes,
                int id_bytes, unsigned* d_hist, size_t hist_entries, cudaStream_t st);

@@ -256,6 +256,65 @@ def _index_methods():
         ix.result = None
         return 0
 
+    def lshx_index_add_entries(self, h, sig_ptr, ids_ptr, n):
+        ix = self._get(h)
+        sig = _arr(sig_ptr, (n, ix.nb, ix.bpb), np.uint8)
+        ids = _arr(ids_ptr, (n, ix.nb), np.int64)
+        if (ids < -1).any() or (ids >= 2 ** 56).any():
+            self._err = b"vector ids must lie in [0, 2^56) for the device index"
+            return -1
+        for i in range(n):
+            for b in range(ix.nb):
+                if ids[i, b] >= 0:
+                    ix.buckets[b].setdefault(sig[i, b].tobytes(), set()).add(int(ids[i, b]))
+        ix.n += n
+        ix.result = None
+        return 0
+
+    def lshx_index_get_buckets(self, h, bands_ptr, keys_ptr, m, offs_ptr, ids_ptr, cap, need_ref):
+        ix = self._get(h)
+        offs = _arr(offs_ptr, (m + 1,), np.int64)
+        offs[...] = 0
+        if m == 0:
+            need_ref._obj.value = 0
+            return 0
+        bands = _arr(bands_ptr, (m,), np.int32)
+        keys = _arr(keys_ptr, (m, ix.bpb), np.uint8)
+        members = [sorted(ix.buckets[int(bands[t])].get(keys[t].tobytes(), ())) for t in range(m)]
+        offs[1:] = np.cumsum([len(x) for x in members])
+        need_ref._obj.value = int(offs[-1])
+        ix.result = None
+        if _null(ids_ptr):
+            return 0
+        if cap < offs[-1]:
+            self._err = b"ids_out too small"
+            return -1
+        if offs[-1]:
+            _arr(ids_ptr, (int(offs[-1]),), np.int64)[...] = [i for x in members for i in x]
+        self.launches += 2
+        return 0
+
+    def lshx_index_export(self, h, keys_ptr, ids_ptr, cap, n_ref):
+        ix = self._get(h)
+        rows = [[(k, i) for k, members in sorted(band.items()) for i in sorted(members)] for band in ix.buckets]
+        n = max((len(r) for r in rows), default=0)
+        n_ref._obj.value = n
+        if _null(keys_ptr) and _null(ids_ptr):
+            return 0
+        if cap < n:
+            self._err = b"export buffers too small"
+            return -1
+        if n:
+            keys = _arr(keys_ptr, (ix.nb, n, ix.bpb), np.uint8)
+            ids = _arr(ids_ptr, (ix.nb, n), np.int64)
+            keys[...] = 0
+            ids[...] = -1
+            for b, r in enumerate(rows):
+                for e, (k, i) in enumerate(r):
+                    keys[b, e] = np.frombuffer(k, dtype=np.uint8)
+                    ids[b, e] = i
+        return 0
+
     def lshx_index_remove(self, h, ids_ptr, n):
         ix = self._get(h)
         gone = set(_arr(ids_ptr, (n,), np.int64).tolist())

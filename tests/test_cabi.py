@@ -24,7 +24,7 @@ def test_library_builds_and_loads():
     path = _build.build()
     assert path.exists()
     lib = _native.lib()
-    assert lib.lshx_abi_version() == _native.ABI_VERSION == 2
+    assert lib.lshx_abi_version() == _native.ABI_VERSION == 3
 
 
 def test_every_declared_symbol_is_exported():
