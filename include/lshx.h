@@ -320,6 +320,20 @@ int lshx_index_clear(lshx_index* ix);
 int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64_t nq, int on_device, void* stream,
                      int64_t* total_candidates, int64_t* max_candidates);
 /*
+ * Latency path of LSHRS.query / get_top_k / get_above_p (reference lshrs/core/main.py:
+ * 524-658 hash ONE vector per call and read num_bands buckets): hash nq <= 32 host
+ * vectors with `h` (the FP32 small-batch kernel of lshx_hash_batch), look their band
+ * keys up and join, all in two launches and one synchronisation.  Query i: its first
+ * min(out_count[i], capacity) candidates, ordered by (-collisions, id), in
+ * out_ids / out_collisions[i * capacity ..]; out_count[i] = the full list length, or
+ * -1 when the query matches more than 4096 bucket entries (take lshx_index_query +
+ * lshx_index_fetch then).  zero_flag (optional, nq bytes) as in lshx_hash_batch.
+ * capacity <= 4096.  Host pointers; drops the last lshx_index_query result.
+ */
+int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const float* X, int nq, int capacity,
+                             int64_t* out_ids, int32_t* out_collisions, int32_t* out_count,
+                             uint8_t* zero_flag);
+/*
  * RedisStorage.get_bucket (SMEMBERS, reference lshrs/storage/redis.py:264-301) for m
  * buckets at once -- what makes the index usable as the bucket STORE, not only as
  * a mirror: bucket t = (band_ids[t], keys[t * bytes_per_band ..]); its members (live

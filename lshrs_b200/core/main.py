@@ -335,6 +335,8 @@ class LSHRS:
               top_p: Optional[float] = None) -> Union[list[int], CandidateScores]:
         """Candidates by band collisions; with ``top_p`` reranked by cosine on the GPU."""
         q = self._prepare_vector(vector)
+        if self._store_on_device and top_p is None and top_k is not None and top_k > 0:
+            return self._device_candidates(q, top_k)[0].tolist()     # only the slice crosses PCIe
         counts = self._candidate_counts(q)
         if not counts:
             return []
@@ -588,9 +590,7 @@ class LSHRS:
 
     def _candidate_counts(self, query_vector: np.ndarray) -> dict[int, int]:
         if self._store_on_device:
-            # one join on the device instead of num_bands bucket reads; the list arrives in (-collisions, id) order
-            packed = self._hasher.hash_batch_packed(np.asarray(query_vector, dtype=np.float32).reshape(1, self._dim))
-            ids, coll = self._dindex.query_one(packed)
+            ids, coll = self._device_candidates(query_vector, None)
             return dict(zip(ids.tolist(), coll.tolist()))
         signatures = self._hasher.hash_vector(query_vector)
         counts: dict[int, int] = {}
@@ -598,6 +598,24 @@ class LSHRS:
             for candidate in self._storage.get_bucket(band_id, hash_val):
                 counts[candidate] = counts.get(candidate, 0) + 1
         return counts
+
+    def _device_candidates(self, query_vector: np.ndarray, limit: Optional[int]):
+        """Candidates of one query from the store in HBM, ordered by (-collisions, id): ``(ids, collisions)``,
+        the first ``limit`` of them when given.  One join on the device instead of ``num_bands`` bucket reads
+        (reference main.py:1088-1111); two launches and one synchronisation on the latency path."""
+        from lshrs_b200 import _native
+
+        ix, hasher = self._dindex, self._hasher
+        vec = np.asarray(query_vector, dtype=np.float32).reshape(1, self._dim)
+        if hasher._kernel == _native.KERNEL_AUTO and self._dim * 4 <= 65536:
+            cap = ix.SMALL_MAX_CAPACITY if limit is None else max(1, min(int(limit), ix.SMALL_MAX_CAPACITY))
+            ids, coll, counts, _ = ix.query_vectors(hasher, vec, cap)
+            c = int(counts[0])
+            if 0 <= c <= cap or (c > cap and limit is not None and limit <= cap):
+                take = min(c, cap)
+                return ids[0, :take], coll[0, :take]
+        ids, coll = ix.query_one(hasher.hash_batch_packed(vec))   # lists beyond the latency path's sizes
+        return (ids, coll) if limit is None else (ids[:limit], coll[:limit])
 
     def _fetch_buckets(self, keys: list) -> list:
         """Members of many ``(band_id, band_bytes)`` buckets, in order.

@@ -379,6 +379,95 @@ index_join_kernel(JoinArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// latency path: lookup + join + emit of a FEW queries in one launch (LSHRS.query / get_top_k hash ONE vector per
+// call, main.py:524-658).  One CTA per query; thread b searches band b; the lists go straight into mapped pinned
+// host memory (no copy call), count = -1 when the raw candidates do not fit the shared-memory sort (the caller
+// then takes the batched path).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(JN_THREADS)
+index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const uint64_t* __restrict__ keys,
+                         const int64_t* __restrict__ ids, int64_t n, int64_t cap, int out_cap,
+                         int64_t* __restrict__ out_ids, int* __restrict__ out_coll, int* __restrict__ out_count) {
+  extern __shared__ __align__(16) uint64_t sm[];
+  __shared__ int64_t s_lo[256];
+  __shared__ int s_cnt[256];
+  __shared__ int band_off[256];
+  __shared__ int heads, n_raw_s;
+  const int tid = threadIdx.x;
+  const int64_t q = blockIdx.x;
+  if (tid < nb) {
+    const uint8_t* src = sig + (q * nb + tid) * (int64_t)bpb;
+    uint64_t key = 0;
+    for (int j = 0; j < bpb; ++j) key |= (uint64_t)src[j] << (8 * j);
+    const uint64_t* k = keys + tid * cap;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(k + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    int64_t lo2 = lo, hi2 = n;
+    while (lo2 < hi2) {
+      const int64_t mid = (lo2 + hi2) >> 1;
+      if (__ldg(k + mid) <= key) lo2 = mid + 1; else hi2 = mid;
+    }
+    s_lo[tid] = lo;
+    const int64_t c = lo2 - lo;
+    s_cnt[tid] = (int)(c > 0x7fffffff ? 0x7fffffff : c);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long acc = 0;
+    for (int b = 0; b < nb; ++b) { band_off[b] = (int)(acc > 0x7fffffff ? 0x7fffffff : acc); acc += s_cnt[b]; }
+    n_raw_s = acc > (long long)JN_SMEM_CAP ? -1 : (int)acc;
+    heads = 0;
+  }
+  __syncthreads();
+  const int n_raw = n_raw_s;
+  if (n_raw <= 0) {
+    if (tid == 0) out_count[q] = n_raw;     // 0 = no candidate, -1 = too many for this path
+    return;
+  }
+  const unsigned P = pow2_at_least((unsigned)n_raw);
+  uint64_t* buf = sm;
+  uint64_t* buf2 = sm + JN_SMEM_CAP;
+  for (int b = 0; b < nb; ++b) {
+    const int c = s_cnt[b];
+    const int64_t* src = ids + b * cap + s_lo[b];
+    for (int i = tid; i < c; i += JN_THREADS) {
+      const int64_t id = src[i];
+      const bool dup = (i > 0 && src[i - 1] == id);
+      buf[band_off[b] + i] = (id < 0 || dup) ? EMPTY : (uint64_t)id;
+    }
+  }
+  for (unsigned i = n_raw + tid; i < P; i += JN_THREADS) buf[i] = EMPTY;
+  __syncthreads();
+  bitonic_asc(buf, P, tid);
+  int mine = 0;
+  for (unsigned i = tid; i < P; i += JN_THREADS) {
+    const uint64_t v = buf[i];
+    uint64_t key2 = EMPTY;
+    if (v != EMPTY && (i == 0 || buf[i - 1] != v)) {
+      unsigned run = 1;
+      while (i + run < P && buf[i + run] == v) ++run;
+      key2 = ((uint64_t)(255u - run) << ID_BITS) | v;
+      ++mine;
+    }
+    buf2[i] = key2;
+  }
+  if (mine) atomicAdd(&heads, mine);
+  __syncthreads();
+  bitonic_asc(buf2, P, tid);
+  const int u = heads;
+  const int take = u < out_cap ? u : out_cap;
+  for (int i = tid; i < take; i += JN_THREADS) {
+    const uint64_t k2 = buf2[i];
+    out_ids[q * out_cap + i] = (int64_t)(k2 & ID_MASK);
+    out_coll[q * out_cap + i] = 255 - (int)(k2 >> ID_BITS);
+  }
+  if (tid == 0) out_count[q] = u;
+}
+
 // dense [nq][k] prefix of the candidate lists (get_top_k mode, main.py:616-623)
 __global__ void index_topk_kernel(const int64_t* __restrict__ cand, const int64_t* __restrict__ raw_off,
                                   const int* __restrict__ uniq, int64_t nq, int k, int64_t* __restrict__ out,
@@ -540,6 +629,18 @@ int index_join(int64_t nq, int nb, const int64_t* ids, int64_t cap, const int64_
   } else {
     index_join_kernel<false><<<grid, JN_THREADS, 0, st>>>(a);
   }
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
+
+int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint64_t* keys, const int64_t* ids, int64_t n,
+                      int64_t cap, int out_cap, int64_t* out_ids, int* out_coll, int* out_count, cudaStream_t st) {
+  if (nq <= 0) return LSHX_OK;
+  const size_t smem = 2 * (size_t)JN_SMEM_CAP * sizeof(uint64_t);
+  LSHX_CUDA(cudaFuncSetAttribute(index_query_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  index_query_small_kernel<<<(unsigned)nq, JN_THREADS, smem, st>>>(d_sig, nb, bpb, keys, ids, n, cap, out_cap, out_ids,
+                                                                  out_coll, out_count);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;

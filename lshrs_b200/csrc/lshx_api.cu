@@ -988,8 +988,13 @@ struct lshx_index {
   DevBuf q_sig, lo, cnt, raw_count, raw_off, ws_off, meta, ws, out_ids, out_coll, uniq, topk_ids, topk_cnt;
   DevBuf rr_pos, rr_score, rr_count, rr_zero, rr_ids, rr_q;
   int64_t last_nq = -1, last_total = 0, last_max = 0;
+  // latency path (lshx_index_query_vectors): pinned + mapped result block the kernel stores into
+  uint8_t* pin_res = nullptr;
   std::mutex mu;
 };
+
+constexpr int IDX_SMALL_MAX_Q = 32;
+constexpr int IDX_SMALL_MAX_CAP = 4096;
 
 static int index_reserve(lshx_index* ix, int64_t want) {
   if (want <= ix->cap) return LSHX_OK;
@@ -1065,6 +1070,7 @@ extern "C" int lshx_index_destroy(lshx_index* ix) {
     }
     if (ix->d_max_id) cudaFree(ix->d_max_id);
     if (ix->d_bad) cudaFree(ix->d_bad);
+    if (ix->pin_res) cudaFreeHost(ix->pin_res);
     for (DevBuf* b : {&ix->hist, &ix->stage_sig, &ix->stage_ids, &ix->gone, &ix->q_sig, &ix->lo, &ix->cnt,
                       &ix->raw_count, &ix->raw_off, &ix->ws_off, &ix->meta, &ix->ws, &ix->out_ids, &ix->out_coll,
                       &ix->uniq, &ix->topk_ids, &ix->topk_cnt, &ix->rr_pos, &ix->rr_score, &ix->rr_count,
@@ -1344,6 +1350,80 @@ extern "C" int lshx_index_export(lshx_index* ix, uint8_t* keys_out, int64_t* ids
   LSHX_CUDA(cudaStreamSynchronize(ix->stream));
   for (size_t e = 0; e < k.size(); ++e)
     for (int j = 0; j < ix->bpb; ++j) keys_out[e * ix->bpb + j] = (uint8_t)(k[e] >> (8 * j));
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const float* X, int nq, int capacity,
+                                        int64_t* out_ids, int32_t* out_collisions, int32_t* out_count,
+                                        uint8_t* zero_flag) {
+  LSHX_REQUIRE(ix != nullptr && h != nullptr, "null handle");
+  LSHX_REQUIRE(ix->device == h->device, "index and hasher live on different devices");
+  LSHX_REQUIRE(nq >= 0 && nq <= IDX_SMALL_MAX_Q, "lshx_index_query_vectors takes at most %d vectors", IDX_SMALL_MAX_Q);
+  LSHX_REQUIRE(capacity > 0 && capacity <= IDX_SMALL_MAX_CAP, "capacity must be in [1, %d]", IDX_SMALL_MAX_CAP);
+  if (nq == 0) return LSHX_OK;
+  LSHX_REQUIRE(X != nullptr && out_ids != nullptr && out_collisions != nullptr && out_count != nullptr, "null buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  std::lock_guard<std::mutex> lk2(h->mu);
+  DeviceGuard g(ix->device);
+  const HashShape& s = h->s;
+  LSHX_REQUIRE(s.num_bands == ix->nb && s.sig_bytes == ix->nb * ix->bpb, "hasher and index shapes differ");
+  LSHX_REQUIRE(nq <= h->small_rows, "the hasher's latency path takes at most %d rows of this dimension", h->small_rows);
+  LSHX_REQUIRE(h->kernel_pref == LSHX_KERNEL_AUTO, "a hasher pinned to one kernel does not take the latency path");
+  if (!ix->pin_res) {
+    const size_t bytes = (size_t)IDX_SMALL_MAX_Q * IDX_SMALL_MAX_CAP * 12 + IDX_SMALL_MAX_Q * 8;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ix->pin_res), bytes, cudaHostAllocMapped) != cudaSuccess) {
+      (void)cudaGetLastError();
+      ix->pin_res = nullptr;
+      set_error("cannot allocate the pinned result block of the latency path");
+      return LSHX_ERR_OOM;
+    }
+  }
+  int rc = index_make_sorted(ix);
+  if (rc != LSHX_OK) return rc;
+  ix->last_nq = -1;
+  cudaStream_t st = ix->stream;
+  // result block: ids [nq][capacity] | collisions [nq][capacity] | count [nq] | zero flag [nq]
+  uint8_t* res = ix->pin_res;
+  int64_t* h_ids = reinterpret_cast<int64_t*>(res);
+  int32_t* h_coll = reinterpret_cast<int32_t*>(res + (size_t)nq * capacity * 8);
+  int32_t* h_count = h_coll + (size_t)nq * capacity;
+  uint8_t* h_flag = reinterpret_cast<uint8_t*>(h_count + nq);
+  uint8_t* d_res = nullptr;
+  LSHX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_res), res, 0));
+  const size_t off_coll = (size_t)nq * capacity * 8, off_count = off_coll + (size_t)nq * capacity * 4,
+               off_flag = off_count + (size_t)nq * 4;
+  if (ix->n == 0) {   // nothing indexed: only the zero-vector test has work to do
+    for (int q = 0; q < nq; ++q) {
+      out_count[q] = 0;
+      if (zero_flag) {
+        bool viol = false;
+        for (int k = 0; k < s.dim; ++k) viol |= !(std::fabs(X[(size_t)q * s.dim + k]) <= 1e-8f);
+        zero_flag[q] = viol ? 0 : 1;
+      }
+    }
+    return LSHX_OK;
+  }
+  if ((rc = ix->q_sig.reserve((size_t)IDX_SMALL_MAX_Q * s.sig_bytes)) != LSHX_OK) return rc;
+  const size_t xb = (size_t)nq * s.dim * sizeof(float);
+  std::memcpy(h->pin_x, X, xb);
+  LSHX_CUDA(cudaMemcpyAsync(h->d_small_x, h->pin_x, xb, cudaMemcpyHostToDevice, st));
+  h->last_kernel = LSHX_KERNEL_SMALL;
+  rc = launch_hash_small(s, h->d_small_x, nq, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p),
+                         zero_flag ? d_res + off_flag : nullptr, st);
+  if (rc != LSHX_OK) return rc;
+  rc = index_query_small(static_cast<const uint8_t*>(ix->q_sig.p), nq, ix->nb, ix->bpb, ix->keys[ix->cur],
+                         ix->ids[ix->cur], ix->n, ix->cap, capacity, reinterpret_cast<int64_t*>(d_res),
+                         reinterpret_cast<int*>(d_res + off_coll), reinterpret_cast<int*>(d_res + off_count), st);
+  if (rc != LSHX_OK) return rc;
+  LSHX_CUDA(cudaStreamSynchronize(st));
+  for (int q = 0; q < nq; ++q) {
+    const int c = h_count[q];
+    out_count[q] = c;
+    const int take = c < capacity ? (c > 0 ? c : 0) : capacity;
+    std::memcpy(out_ids + (size_t)q * capacity, h_ids + (size_t)q * capacity, (size_t)take * 8);
+    std::memcpy(out_collisions + (size_t)q * capacity, h_coll + (size_t)q * capacity, (size_t)take * 4);
+  }
+  if (zero_flag) std::memcpy(zero_flag, h_flag, (size_t)nq);
   return LSHX_OK;
 }
 

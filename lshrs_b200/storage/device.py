@@ -127,6 +127,26 @@ class DeviceIndex:
         self._nq, self._total = nq, int(total.value)
         return self._total, int(maxc.value)
 
+    SMALL_MAX_QUERIES, SMALL_MAX_CAPACITY = 32, 4096
+
+    def query_vectors(self, hasher, vectors: np.ndarray, capacity: int):
+        """Latency path (``lshx_index_query_vectors``): hash up to 32 host vectors with ``hasher`` and join them in
+        two launches and one synchronisation.  Returns ``(ids int64[nq, capacity], collisions int32[nq, capacity],
+        counts int32[nq], zero uint8[nq])``; ``counts[i]`` is the FULL list length (the arrays hold its first
+        ``capacity`` entries) or -1 when query i matches too many bucket entries for this path."""
+        x = np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, hasher.dim)
+        nq, cap = x.shape[0], int(capacity)
+        ids = np.empty((nq, cap), dtype=np.int64)
+        coll = np.empty((nq, cap), dtype=np.int32)
+        counts = np.zeros(nq, dtype=np.int32)
+        zero = np.zeros(nq, dtype=np.uint8)
+        if nq:
+            with self.lock:
+                _native.check(_native.lib().lshx_index_query_vectors(
+                    self._handle, hasher._ensure_handle(), x.ctypes.data, nq, cap, ids.ctypes.data, coll.ctypes.data,
+                    counts.ctypes.data, zero.ctypes.data))
+        return ids, coll, counts, zero
+
     def query_one(self, signature: np.ndarray):
         """``(ids int64[c], collisions int32[c])`` of ONE query, ordered by (-collisions, id)."""
         with self.lock:

@@ -294,6 +294,37 @@ def _index_methods():
         self.launches += 2
         return 0
 
+    def lshx_index_query_vectors(self, h, hh, X_ptr, nq, cap, ids_ptr, coll_ptr, count_ptr, flag_ptr):
+        ix, hs = self._get(h), self._get(hh)
+        if nq > 32 or not 0 < cap <= 4096:
+            self._err = b"latency path limits"
+            return -1
+        X = _arr(X_ptr, (nq, hs.dim), np.float32)
+        sig = oracle.hash_batch_packed(hs.projs, X).reshape(nq, ix.nb, ix.bpb)
+        ids, coll = _arr(ids_ptr, (nq, cap), np.int64), _arr(coll_ptr, (nq, cap), np.int32)
+        cnt = _arr(count_ptr, (nq,), np.int32)
+        for q in range(nq):
+            counts: dict[int, int] = {}
+            slots = 0
+            for b in range(ix.nb):
+                members = ix.buckets[b].get(sig[q, b].tobytes(), ())
+                slots += len(members)
+                for m in members:
+                    counts[m] = counts.get(m, 0) + 1
+            if slots > 4096:
+                cnt[q] = -1
+                continue
+            order = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))
+            cnt[q] = len(order)
+            take = order[:cap]
+            ids[q, :len(take)] = [i for i, _ in take]
+            coll[q, :len(take)] = [c for _, c in take]
+        if not _null(flag_ptr):
+            _arr(flag_ptr, (nq,), np.uint8)[...] = [1 if oracle.is_zero_vector(x) else 0 for x in X]
+        ix.result = None
+        self.launches += 2
+        return 0
+
     def lshx_index_export(self, h, keys_ptr, ids_ptr, cap, n_ref):
         ix = self._get(h)
         rows = [[(k, i) for k, members in sorted(band.items()) for i in sorted(members)] for band in ix.buckets]

@@ -233,3 +233,46 @@ def test_device_mirror_tracks_ingest_delete_clear(indexed_50k):
     lsh.clear()
     a, b = same(top_k=5)
     assert a == b == [[] for _ in range(len(probes))]
+
+
+@pytest.mark.parametrize("dim, nb, r", [(768, 16, 16), (128, 16, 4), (64, 5, 20), (33, 3, 64)])
+def test_latency_path_equals_hash_plus_batched_join(dim, nb, r):
+    """lshx_index_query_vectors (hash_small + one lookup/join/emit launch into mapped memory) returns what
+    hash_batch_packed + lshx_index_query + lshx_index_fetch return, for 1 .. 32 vectors and any capacity; queries
+    with more than 4096 bucket entries report -1."""
+    import lshrs_b200
+    from lshrs_b200.storage.device import DeviceIndex
+
+    rng = np.random.default_rng(dim + nb)
+    n = 3000
+    centers = rng.standard_normal((n // 6, dim)).astype(np.float32)
+    X = (np.repeat(centers, 6, axis=0) + 0.2 * rng.standard_normal((n, dim))).astype(np.float32)
+    h = lshrs_b200.LSHHasher(nb, r, dim, seed=7, device=0)
+    ix = DeviceIndex(nb, h.bytes_per_band, device=0)
+    Q = (X[rng.integers(0, n, 32)] + 0.05 * rng.standard_normal((32, dim))).astype(np.float32)
+    Q[5] = 0                                                        # zero vector: flagged, still answered
+    ids0, coll0, counts0, zero0 = ix.query_vectors(h, Q[:3], 8)     # empty index
+    assert counts0.tolist() == [0, 0, 0]
+    ix.add(h.hash_batch_packed(X), np.arange(n, dtype=np.int64) * 3 + 1)
+    for nq, cap in ((1, 10), (1, 4096), (7, 3), (32, 64), (32, 1)):
+        ids, coll, counts, zero = ix.query_vectors(h, Q[:nq], cap)
+        want = _lists(ix, h.hash_batch_packed(Q[:nq]))
+        assert zero.tolist() == [1 if i == 5 else 0 for i in range(nq)]
+        for q in range(nq):
+            assert counts[q] == len(want[q])
+            take = min(cap, len(want[q]))
+            assert list(zip(ids[q, :take].tolist(), coll[q, :take].tolist())) == want[q][:take]
+    # one bucket with 5000 members: beyond the shared-memory sort of the latency path
+    big = np.repeat(h.hash_batch_packed(Q[:1]), 5000, axis=0)
+    ix.add(big, np.arange(10_000_000, 10_005_000, dtype=np.int64))
+    ids, coll, counts, zero = ix.query_vectors(h, Q[:2], 16)
+    assert counts[0] == -1 and counts[1] == len(_lists(ix, h.hash_batch_packed(Q[1:2]))[0])
+    with pytest.raises(lshrs_b200.LshxError):
+        ix.query_vectors(h, np.zeros((33, dim), np.float32), 8)
+    with pytest.raises(lshrs_b200.LshxError):
+        ix.query_vectors(h, Q[:1], 5000)
+    h.set_kernel("ffma")
+    with pytest.raises(lshrs_b200.LshxError, match="pinned"):
+        ix.query_vectors(h, Q[:1], 8)
+    ix.close()
+    h.close()
