@@ -958,7 +958,7 @@ def run_api(args, dev, shape: Shape) -> dict:
 
     dst = LSHRS(dim=shape.dim, num_perm=shape.num_perm, storage=DeviceBucketStorage(), vector_fetch_fn=lambda ids: allvec[ids],
                 device=dev.index)
-    dst.index(ids[:4096], Xh[:4096])        # first call sizes the segments and staging buffers: off the clock
+    dst.index(ids, Xh)                      # first call sizes the segments and staging buffers: off the clock
     dst.clear()
     t0 = time.perf_counter()
     dst.index(ids, Xh)
@@ -967,7 +967,7 @@ def run_api(args, dev, shape: Shape) -> dict:
     rep = -(-n_more // n_index)
     Xbig = np.tile(Xh, (rep, 1))[:n_more]
     big = LSHRS(dim=shape.dim, num_perm=shape.num_perm, storage=DeviceBucketStorage(), device=dev.index)
-    big.index(ids[:4096], Xh[:4096])
+    big.index(np.arange(n_more), Xbig)
     big.clear()
     t0 = time.perf_counter()
     big.index(np.arange(n_more), Xbig)

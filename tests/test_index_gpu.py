@@ -254,7 +254,8 @@ def test_latency_path_equals_hash_plus_batched_join(dim, nb, r):
     ids0, coll0, counts0, zero0 = ix.query_vectors(h, Q[:3], 8)     # empty index
     assert counts0.tolist() == [0, 0, 0]
     ix.add(h.hash_batch_packed(X), np.arange(n, dtype=np.int64) * 3 + 1)
-    for nq, cap in ((1, 10), (1, 4096), (7, 3), (32, 64), (32, 1)):
+    most = min(32, 65536 // (4 * dim))                              # rows the hasher's latency path takes
+    for nq, cap in ((1, 10), (1, 4096), (7, 3), (most, 64), (most, 1)):
         ids, coll, counts, zero = ix.query_vectors(h, Q[:nq], cap)
         want = _lists(ix, h.hash_batch_packed(Q[:nq]))
         assert zero.tolist() == [1 if i == 5 else 0 for i in range(nq)]
