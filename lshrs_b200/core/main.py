@@ -234,6 +234,8 @@ class LSHRS:
             return
         if vectors is None:
             vectors = self._require_vector_fetch_fn()(indices)
+        if self._store_on_device and getattr(vectors, "is_cuda", False):
+            return self._index_resident(indices, vectors)
         if isinstance(vectors, np.ndarray) and vectors.dtype in self._hasher._TYPED and vectors.ndim == 2:
             arr = vectors   # float16 / int8 / uint8 batches are cast on the device (exact), not here
         else:
@@ -283,6 +285,32 @@ class LSHRS:
             raise
         queue_mirror(len(indices))
         self.flush()
+
+    def _index_resident(self, indices, vectors) -> None:
+        """``index()`` of vectors that are already in HBM (a CUDA float32 tensor) into the store in HBM: hash and
+        append without anything crossing PCIe but one validity flag.  ``indices``: a sequence or an int64 tensor."""
+        import torch
+
+        if vectors.dim() != 2 or vectors.shape[1] != self._dim:
+            raise ValueError(f"Vectors must have shape (n, {self._dim}); received {tuple(vectors.shape)}")
+        n = int(vectors.shape[0])
+        if n != len(indices):
+            raise ValueError(
+                "Number of vectors does not match number of indices "
+                f"(received {n} vectors for {len(indices)} indices)"
+            )
+        dev = vectors.device
+        if isinstance(indices, torch.Tensor):
+            ids_dev = indices.to(device=dev, dtype=torch.int64).contiguous()
+        else:
+            ids_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(indices, dtype=np.int64))).to(dev)
+        flag = torch.zeros(n, dtype=torch.uint8, device=dev)
+        packed = self._hasher.hash_device(vectors.to(torch.float32), zero_flag=flag)
+        if bool(((ids_dev < 0) | (flag != 0)).any()):
+            # an invalid row: the per-row semantics (what is flushed, what stays buffered) live on the host path
+            return self._index_packed(ids_dev.cpu().numpy(), packed.cpu().numpy(), flag.cpu().numpy())
+        self.flush()
+        self._dindex.add_device(packed, ids_dev, torch.cuda.current_stream(dev).cuda_stream)
 
     def _index_packed(self, indices: Sequence[int], packed: np.ndarray, zero_flag: np.ndarray) -> None:
         """``index()`` on a store that takes packed signatures (``DeviceBucketStorage.add_packed``).

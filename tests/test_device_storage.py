@@ -215,3 +215,36 @@ def test_failed_packed_add_keeps_the_operations(lib):
     assert len(lsh._buffer) == 0
     got = lsh.query_batch(X, top_k=None)
     assert all(i in got[i] for i in range(12)) and 99 in got[0]
+
+
+@pytest.mark.gpu
+def test_index_of_resident_vectors_equals_the_host_path():
+    """index(ids, <CUDA tensor>) on the device store: hash + append in HBM; same store contents as from host arrays,
+    same per-row semantics when a row is invalid."""
+    import torch
+
+    X = _clustered(5000, 64, seed=9)
+    made: list = []
+    a, b = _pair(made, X, dim=64, num_perm=32, num_bands=8, rows_per_band=4, buffer_size=100)
+    b.ingest(7000, X[0])
+    a.ingest(7000, X[0])
+    a.index(list(range(5000)), X)
+    xd = torch.from_numpy(X).cuda()
+    b.index(torch.arange(3000, dtype=torch.int64), xd[:3000])          # tensor ids
+    b.index(list(range(3000, 5000)), xd[3000:])                        # sequence ids
+    Q = X[::50] + 0.01
+    assert a.query_batch(Q, top_k=None) == b.query_batch(Q, top_k=None)
+    assert a.query_batch(Q, top_k=7) == b.query_batch(Q, top_k=7, corpus=None)
+    bad = xd[:40].clone()
+    bad[17] = 0
+    for lsh, v in ((a, bad.cpu().numpy()), (b, bad)):
+        with pytest.raises(ValueError, match="zero vector"):
+            lsh.index(list(range(9000, 9040)), v)
+    assert a._buffer == b._buffer
+    for lsh in (a, b):
+        lsh.flush()
+    assert a.query_batch(Q, top_k=None) == b.query_batch(Q, top_k=None)
+    with pytest.raises(ValueError, match="shape"):
+        b.index([1, 2], xd[:2, :10])
+    with pytest.raises(ValueError, match="does not match"):
+        b.index([1, 2, 3], xd[:2])
