@@ -1000,7 +1000,14 @@ def run_api(args, dev, shape: Shape) -> dict:
     t0 = time.perf_counter()
     d_got_p = [dst.get_above_p(Q[i], p=0.2) for i in range(n_single)]
     d_above_qps = n_single / (time.perf_counter() - t0)
-    same_store = (d_got_k == got_k and [[i for i, _ in r] for r in d_got_p] == [[i for i, _ in r] for r in got_p]
+    dst.set_corpus(corpus_dev)               # candidate vectors gathered from HBM by id instead of vector_fetch_fn
+    dst.get_above_p(Q[-1], p=0.2)
+    t0 = time.perf_counter()
+    d_got_pc = [dst.get_above_p(Q[i], p=0.2) for i in range(n_single)]
+    d_above_corpus_qps = n_single / (time.perf_counter() - t0)
+    dst.set_corpus(None)
+    same_store = (d_got_k == got_k and [[i for i, _ in r] for r in d_got_pc] == [[i for i, _ in r] for r in got_p]
+                  and [[i for i, _ in r] for r in d_got_p] == [[i for i, _ in r] for r in got_p]
                   and dst.query_batch(Q, top_k=10, top_p=0.2, corpus=corpus_dev) == dev_batch)
     dst.query_batch(Qbig, as_arrays=True, **kw)
     d_arrays_qps = rate(lambda: dst.query_batch(Qbig, as_arrays=True, **kw))
@@ -1031,6 +1038,8 @@ def run_api(args, dev, shape: Shape) -> dict:
             "ingest": {"value": d_ingest_cps, "unit": "calls/s", "calls": n_single},
             "get_top_k": {"value": d_topk_qps, "unit": "queries/s", "calls": n_single},
             "get_above_p": {"value": d_above_qps, "unit": "queries/s", "calls": n_single},
+            "get_above_p_resident_corpus": {"value": d_above_corpus_qps, "unit": "queries/s", "calls": n_single,
+                                            "note": "LSHRS.set_corpus(<CUDA tensor>): no vector_fetch_fn round trip"},
             "query_batch": {"value": d_arrays_qps, "unit": "queries/s", "queries_per_call": nbig},
             "equals_dict_store": bool(same_store)},
         "reference_survey_values": {"index": 2.2e3, "get_top_k": 3.9e3, "get_above_p": 2.7e3,

@@ -79,6 +79,7 @@ class LSHRS:
         seed: int = 42,
         device: Optional[int] = None,
         device_index: bool = False,
+        corpus=None,
     ) -> None:
         if dim <= 0:
             raise ValueError("Vector dimensionality must be greater than zero")
@@ -95,6 +96,11 @@ class LSHRS:
         self._dim = dim
         self._buffer_size = buffer_size
         self._vector_fetch_fn = vector_fetch_fn
+        # optional: the indexed vectors resident in HBM (CUDA float32 tensor (N, dim), candidate id = row) -- the
+        # device-side stand-in for vector_fetch_fn: reranks gather from it instead of fetching to the host
+        self._corpus = None
+        if corpus is not None:
+            self.set_corpus(corpus)
         self._hasher = LSHHasher(num_bands=num_bands, rows_per_band=rows_per_band, dim=dim, seed=seed, device=device)
         if storage is None:
             storage = self._make_redis_storage(
@@ -140,6 +146,15 @@ class LSHRS:
                     "reference package lshrs.storage.redis, which is not importable here)"
                 ) from exc
         return cls(**kwargs)
+
+    def set_corpus(self, corpus) -> None:
+        """Rerank against ``corpus`` (contiguous CUDA float32 tensor ``(N, dim)``, candidate id = row) instead of
+        calling ``vector_fetch_fn``; ``None`` goes back to the callback."""
+        if corpus is not None:
+            if not getattr(corpus, "is_cuda", False) or corpus.dim() != 2 or corpus.shape[1] != self._dim \
+                    or not corpus.is_contiguous() or str(corpus.dtype) != "torch.float32":
+                raise ValueError(f"corpus must be a contiguous float32 CUDA tensor of shape (n, {self._dim})")
+        self._corpus = corpus
 
     # ------------------------------------------------------------------ lifecycle
     def close(self) -> None:
@@ -378,24 +393,34 @@ class LSHRS:
         if not 0 < top_p <= 1:
             raise ValueError("top_p must be within the range (0, 1]")
         candidate_indices = [idx for idx, _ in ordered]
-        fetched = self._require_vector_fetch_fn()(candidate_indices)
-        arr = np.ascontiguousarray(np.asarray(fetched, dtype=np.float32))
-        if arr.ndim != 2 or arr.shape[1] != self._dim:
-            raise ValueError(f"Fetched vectors must have shape (n, {self._dim}); received {arr.shape}")
-        if arr.shape[0] != len(candidate_indices):
-            raise ValueError(
-                "vector_fetch_fn returned mismatched batch size "
-                f"(expected {len(candidate_indices)}, received {arr.shape[0]})"
-            )
         if top_k is not None and top_k <= 0:
             raise ValueError("top_k must be greater than zero when provided")
         n = len(candidate_indices)
-        # The reference sorts ALL n candidates (top_k_cosine(k=n)) and slices
-        # max(1, ceil(n * top_p)) [then min(., top_k)]; the kernel applies the same
-        # cut and only the kept rows come back over PCIe.
         rer = _get_reranker(self._dim, self._hasher.device)
-        pos, score, count, zero = rer.topk(q, arr, np.array([0, n], dtype=np.int64),
-                                           k=int(top_k) if top_k is not None else 0, p=float(top_p))
+        if self._corpus is not None:
+            # the candidates' vectors are gathered from HBM by id; nothing but ids and the kept scores move
+            ids_arr = np.asarray(candidate_indices, dtype=np.int64)
+            if ids_arr.max() >= self._corpus.shape[0]:
+                raise ValueError(f"candidate id {int(ids_arr.max())} is not a row of the corpus "
+                                 f"({self._corpus.shape[0]} rows)")
+            pos, score, count, zero = rer.topk(q, self._corpus, np.array([0, n], dtype=np.int64), ids_arr,
+                                               k=int(top_k) if top_k is not None else 0, p=float(top_p),
+                                               vectors_on_device=True)
+        else:
+            fetched = self._require_vector_fetch_fn()(candidate_indices)
+            arr = np.ascontiguousarray(np.asarray(fetched, dtype=np.float32))
+            if arr.ndim != 2 or arr.shape[1] != self._dim:
+                raise ValueError(f"Fetched vectors must have shape (n, {self._dim}); received {arr.shape}")
+            if arr.shape[0] != len(candidate_indices):
+                raise ValueError(
+                    "vector_fetch_fn returned mismatched batch size "
+                    f"(expected {len(candidate_indices)}, received {arr.shape[0]})"
+                )
+            # The reference sorts ALL n candidates (top_k_cosine(k=n)) and slices
+            # max(1, ceil(n * top_p)) [then min(., top_k)]; the kernel applies the same
+            # cut and only the kept rows come back over PCIe.
+            pos, score, count, zero = rer.topk(q, arr, np.array([0, n], dtype=np.int64),
+                                               k=int(top_k) if top_k is not None else 0, p=float(top_p))
         if zero.any():
             raise ValueError("Cannot normalize zero vector")
         return [(candidate_indices[int(pos[0, i])], float(score[0, i])) for i in range(int(count[0]))]
@@ -426,6 +451,8 @@ class LSHRS:
         if arr.ndim != 2 or arr.shape[1] != self._dim:
             raise ValueError(f"Vectors must have shape (n, {self._dim}); received {arr.shape}")
         nq = arr.shape[0]
+        if corpus is None:
+            corpus = self._corpus
         if device_index is None:
             device_index = self._store_on_device
         if as_arrays and not device_index:

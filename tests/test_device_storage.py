@@ -248,3 +248,43 @@ def test_index_of_resident_vectors_equals_the_host_path():
         b.index([1, 2], xd[:2, :10])
     with pytest.raises(ValueError, match="does not match"):
         b.index([1, 2, 3], xd[:2])
+
+
+@pytest.mark.gpu
+def test_single_queries_rerank_against_a_resident_corpus():
+    """LSHRS(corpus=<CUDA tensor>): get_above_p / query(top_p=) gather candidate vectors from HBM by id -- same ids,
+    scores within 1e-6 of the vector_fetch_fn path; works with either store; query_batch picks the corpus up."""
+    import torch
+
+    X = _clustered(4000, 96, seed=11)
+    xd = torch.from_numpy(X).cuda()
+    fetch = lambda ids: X[np.asarray(ids, dtype=np.int64)]   # noqa: E731
+    kw = dict(dim=96, num_perm=64, num_bands=16, rows_per_band=4)
+    host = LSHRS(storage=InMemoryStorage(), vector_fetch_fn=fetch, **kw)
+    res = LSHRS(storage=DeviceBucketStorage(), corpus=xd, **kw)
+    mem = LSHRS(storage=InMemoryStorage(), corpus=xd, **kw)
+    for lsh in (host, res, mem):
+        lsh.index(list(range(4000)), X)
+    Q = X[::97] + 0.02
+    for q in Q:
+        for call in (lambda l: l.get_above_p(q, p=0.3), lambda l: l.query(q, top_k=5, top_p=0.9),
+                     lambda l: l.query(q, top_k=None, top_p=1.0)):
+            want = call(host)
+            for lsh in (res, mem):
+                got = call(lsh)
+                assert [i for i, _ in got] == [i for i, _ in want]
+                np.testing.assert_allclose([s for _, s in got], [s for _, s in want], atol=1e-6)
+    want = host.query_batch(Q, top_k=4, top_p=0.5)
+    for lsh in (res, mem):
+        got = lsh.query_batch(Q, top_k=4, top_p=0.5)                 # corpus= defaults to the instance's
+        assert [[i for i, _ in r] for r in got] == [[i for i, _ in r] for r in want]
+    res.index([4500], X[:1])                                          # an id beyond the corpus
+    with pytest.raises(ValueError, match="not a row of the corpus"):
+        res.get_above_p(X[0], p=1.0)
+    with pytest.raises(ValueError, match="corpus must be"):
+        LSHRS(storage=InMemoryStorage(), corpus=torch.zeros(4, 95, device="cuda"), **kw)
+    with pytest.raises(ValueError, match="corpus must be"):
+        LSHRS(storage=InMemoryStorage(), corpus=X, **kw)
+    res.set_corpus(None)
+    with pytest.raises(RuntimeError, match="vector_fetch_fn"):
+        res.get_above_p(X[1], p=0.5)
