@@ -334,6 +334,22 @@ int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const float* X, int
                              int64_t* out_ids, int32_t* out_collisions, int32_t* out_count,
                              uint8_t* zero_flag);
 /*
+ * The same latency path with the rerank fused in (LSHRS.query(top_p=...) /
+ * get_above_p, main.py:625-658, when the indexed vectors are resident in HBM):
+ * hash -> lookup/join -> cosine rerank against corpus_device (candidate id = row)
+ * -> ids, four launches and one synchronisation, results stored straight into
+ * mapped pinned memory.  Query i keeps min(k, max(1, ceil(n_i * p))) of its n_i
+ * candidates (k <= 0: no k; p <= 0: no p), at most out_stride (<= 1024):
+ * out_ids / out_score[i * out_stride ..], out_count[i].  out_candidates[i] = n_i, or
+ * -1 when the query matches more than 1024 bucket entries (nothing is ranked then:
+ * take lshx_index_query + lshx_index_rerank).  out_zero (optional): zero-norm or
+ * out-of-range candidate vectors met; zero_flag (optional) as in lshx_hash_batch.
+ */
+int lshx_index_query_rerank_vectors(lshx_index* ix, lshx_hasher* h, lshx_reranker* r, const float* X, int nq,
+                                    const float* corpus_device, int64_t n_vectors, int k, double p,
+                                    int out_stride, int64_t* out_ids, float* out_score, int32_t* out_count,
+                                    int32_t* out_zero, int32_t* out_candidates, uint8_t* zero_flag);
+/*
  * RedisStorage.get_bucket (SMEMBERS, reference lshrs/storage/redis.py:264-301) for m
  * buckets at once -- what makes the index usable as the bucket STORE, not only as
  * a mirror: bucket t = (band_ids[t], keys[t * bytes_per_band ..]); its members (live

@@ -380,6 +380,11 @@ class LSHRS:
         q = self._prepare_vector(vector)
         if self._store_on_device and top_p is None and top_k is not None and top_k > 0:
             return self._device_candidates(q, top_k)[0].tolist()     # only the slice crosses PCIe
+        if (self._store_on_device and self._corpus is not None and top_p is not None and 0 < top_p <= 1
+                and (top_k is None or top_k > 0)):
+            ranked = self._device_rerank(q, top_k, float(top_p))
+            if ranked is not None:
+                return ranked
         counts = self._candidate_counts(q)
         if not counts:
             return []
@@ -671,6 +676,27 @@ class LSHRS:
                 return ids[0, :take], coll[0, :take]
         ids, coll = ix.query_one(hasher.hash_batch_packed(vec))   # lists beyond the latency path's sizes
         return (ids, coll) if limit is None else (ids[:limit], coll[:limit])
+
+    def _device_rerank(self, q: np.ndarray, top_k: Optional[int], top_p: float):
+        """``query(top_p=...)`` with store AND vectors in HBM: hash, join, rerank and id gather in four launches and
+        one synchronisation; ``None`` when the query is outside the latency path's sizes or met something the
+        general path reports precisely (a candidate id that is not a corpus row, a zero-norm vector)."""
+        from lshrs_b200 import _native
+
+        ix, hasher = self._dindex, self._hasher
+        if hasher._kernel != _native.KERNEL_AUTO or self._dim * 4 > 65536:
+            return None
+        cap = ix.SMALL_RERANK_CAPACITY
+        stride = max(1, math.ceil(cap * top_p))
+        if top_k is not None:
+            stride = min(stride, int(top_k))
+        rer = _get_reranker(self._dim, hasher.device)
+        ids, scores, counts, zero, cands, _ = ix.query_rerank_vectors(
+            hasher, rer, q.reshape(1, self._dim), self._corpus, k=int(top_k or 0), p=top_p, stride=stride)
+        if cands[0] < 0 or zero[0]:
+            return None
+        c = int(counts[0])
+        return list(zip(ids[0, :c].tolist(), scores[0, :c].tolist()))
 
     def _fetch_buckets(self, keys: list) -> list:
         """Members of many ``(band_id, band_bytes)`` buckets, in order.

@@ -387,8 +387,9 @@ index_join_kernel(JoinArgs a) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(JN_THREADS)
 index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const uint64_t* __restrict__ keys,
-                         const int64_t* __restrict__ ids, int64_t n, int64_t cap, int out_cap,
-                         int64_t* __restrict__ out_ids, int* __restrict__ out_coll, int* __restrict__ out_count) {
+                         const int64_t* __restrict__ ids, int64_t n, int64_t cap, int out_cap, int raw_cap,
+                         int64_t* __restrict__ out_ids, int* __restrict__ out_coll, int* __restrict__ out_count,
+                         int* __restrict__ out_count_clamped, int64_t* __restrict__ out_offs) {
   extern __shared__ __align__(16) uint64_t sm[];
   __shared__ int64_t s_lo[256];
   __shared__ int s_cnt[256];
@@ -419,13 +420,17 @@ index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const
   if (tid == 0) {
     long long acc = 0;
     for (int b = 0; b < nb; ++b) { band_off[b] = (int)(acc > 0x7fffffff ? 0x7fffffff : acc); acc += s_cnt[b]; }
-    n_raw_s = acc > (long long)JN_SMEM_CAP ? -1 : (int)acc;
+    n_raw_s = acc > (long long)raw_cap ? -1 : (int)acc;
     heads = 0;
+    if (out_offs) out_offs[q] = q * (int64_t)out_cap;       // CSR base of this query's slots for the rerank kernel
   }
   __syncthreads();
   const int n_raw = n_raw_s;
   if (n_raw <= 0) {
-    if (tid == 0) out_count[q] = n_raw;     // 0 = no candidate, -1 = too many for this path
+    if (tid == 0) {
+      out_count[q] = n_raw;     // 0 = no candidate, -1 = too many for this path
+      if (out_count_clamped) out_count_clamped[q] = 0;
+    }
     return;
   }
   const unsigned P = pow2_at_least((unsigned)n_raw);
@@ -463,9 +468,12 @@ index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const
   for (int i = tid; i < take; i += JN_THREADS) {
     const uint64_t k2 = buf2[i];
     out_ids[q * out_cap + i] = (int64_t)(k2 & ID_MASK);
-    out_coll[q * out_cap + i] = 255 - (int)(k2 >> ID_BITS);
+    if (out_coll) out_coll[q * out_cap + i] = 255 - (int)(k2 >> ID_BITS);
   }
-  if (tid == 0) out_count[q] = u;
+  if (tid == 0) {
+    out_count[q] = u;
+    if (out_count_clamped) out_count_clamped[q] = take;
+  }
 }
 
 // dense [nq][k] prefix of the candidate lists (get_top_k mode, main.py:616-623)
@@ -635,12 +643,15 @@ int index_join(int64_t nq, int nb, const int64_t* ids, int64_t cap, const int64_
 }
 
 int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint64_t* keys, const int64_t* ids, int64_t n,
-                      int64_t cap, int out_cap, int64_t* out_ids, int* out_coll, int* out_count, cudaStream_t st) {
+                      int64_t cap, int out_cap, int raw_cap, int64_t* out_ids, int* out_coll, int* out_count,
+                      int* out_count_clamped, int64_t* out_offs, cudaStream_t st) {
   if (nq <= 0) return LSHX_OK;
+  if (raw_cap <= 0 || raw_cap > (int)JN_SMEM_CAP) raw_cap = (int)JN_SMEM_CAP;
   const size_t smem = 2 * (size_t)JN_SMEM_CAP * sizeof(uint64_t);
   LSHX_CUDA(cudaFuncSetAttribute(index_query_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  index_query_small_kernel<<<(unsigned)nq, JN_THREADS, smem, st>>>(d_sig, nb, bpb, keys, ids, n, cap, out_cap, out_ids,
-                                                                  out_coll, out_count);
+  index_query_small_kernel<<<(unsigned)nq, JN_THREADS, smem, st>>>(d_sig, nb, bpb, keys, ids, n, cap, out_cap, raw_cap,
+                                                                  out_ids, out_coll, out_count, out_count_clamped,
+                                                                  out_offs);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;

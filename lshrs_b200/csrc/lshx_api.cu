@@ -1412,8 +1412,9 @@ extern "C" int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const fl
                          zero_flag ? d_res + off_flag : nullptr, st);
   if (rc != LSHX_OK) return rc;
   rc = index_query_small(static_cast<const uint8_t*>(ix->q_sig.p), nq, ix->nb, ix->bpb, ix->keys[ix->cur],
-                         ix->ids[ix->cur], ix->n, ix->cap, capacity, reinterpret_cast<int64_t*>(d_res),
-                         reinterpret_cast<int*>(d_res + off_coll), reinterpret_cast<int*>(d_res + off_count), st);
+                         ix->ids[ix->cur], ix->n, ix->cap, capacity, 0, reinterpret_cast<int64_t*>(d_res),
+                         reinterpret_cast<int*>(d_res + off_coll), reinterpret_cast<int*>(d_res + off_count), nullptr,
+                         nullptr, st);
   if (rc != LSHX_OK) return rc;
   LSHX_CUDA(cudaStreamSynchronize(st));
   for (int q = 0; q < nq; ++q) {
@@ -1424,6 +1425,117 @@ extern "C" int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const fl
     std::memcpy(out_collisions + (size_t)q * capacity, h_coll + (size_t)q * capacity, (size_t)take * 4);
   }
   if (zero_flag) std::memcpy(zero_flag, h_flag, (size_t)nq);
+  return LSHX_OK;
+}
+
+constexpr int IDX_SMALL_RERANK_CAP = 1024;   // candidates per query the fused latency path reranks
+
+extern "C" int lshx_index_query_rerank_vectors(lshx_index* ix, lshx_hasher* h, lshx_reranker* r, const float* X,
+                                               int nq, const float* corpus_device, int64_t n_vectors, int k,
+                                               double p, int out_stride, int64_t* out_ids, float* out_score,
+                                               int32_t* out_count, int32_t* out_zero, int32_t* out_candidates,
+                                               uint8_t* zero_flag) {
+  LSHX_REQUIRE(ix != nullptr && h != nullptr && r != nullptr, "null handle");
+  LSHX_REQUIRE(ix->device == h->device && ix->device == r->device, "index, hasher and reranker live on different devices");
+  LSHX_REQUIRE(nq >= 0 && nq <= IDX_SMALL_MAX_Q, "the latency path takes at most %d vectors", IDX_SMALL_MAX_Q);
+  LSHX_REQUIRE(k > 0 || p > 0.0, "k must be > 0");
+  LSHX_REQUIRE(!(p > 1.0), "top_p must be within the range (0, 1]");
+  LSHX_REQUIRE(out_stride > 0 && out_stride <= IDX_SMALL_RERANK_CAP, "out_stride must be in [1, %d]", IDX_SMALL_RERANK_CAP);
+  if (nq == 0) return LSHX_OK;
+  LSHX_REQUIRE(X && corpus_device && n_vectors > 0 && out_ids && out_score && out_count && out_candidates, "null buffer");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  std::lock_guard<std::mutex> lk2(h->mu);
+  std::lock_guard<std::mutex> lk3(r->mu);
+  DeviceGuard g(ix->device);
+  const HashShape& s = h->s;
+  LSHX_REQUIRE(s.num_bands == ix->nb && s.sig_bytes == ix->nb * ix->bpb, "hasher and index shapes differ");
+  LSHX_REQUIRE(s.dim == r->dim, "hasher and reranker dimensions differ");
+  LSHX_REQUIRE(nq <= h->small_rows, "the hasher's latency path takes at most %d rows of this dimension", h->small_rows);
+  LSHX_REQUIRE(h->kernel_pref == LSHX_KERNEL_AUTO, "a hasher pinned to one kernel does not take the latency path");
+  if (!ix->pin_res) {
+    const size_t bytes = (size_t)IDX_SMALL_MAX_Q * IDX_SMALL_MAX_CAP * 12 + IDX_SMALL_MAX_Q * 8;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&ix->pin_res), bytes, cudaHostAllocMapped) != cudaSuccess) {
+      (void)cudaGetLastError();
+      ix->pin_res = nullptr;
+      set_error("cannot allocate the pinned result block of the latency path");
+      return LSHX_ERR_OOM;
+    }
+  }
+  if (ix->n == 0) {
+    for (int q = 0; q < nq; ++q) {
+      out_count[q] = 0;
+      out_candidates[q] = 0;
+      if (out_zero) out_zero[q] = 0;
+      if (zero_flag) {
+        bool viol = false;
+        for (int c = 0; c < s.dim; ++c) viol |= !(std::fabs(X[(size_t)q * s.dim + c]) <= 1e-8f);
+        zero_flag[q] = viol ? 0 : 1;
+      }
+    }
+    return LSHX_OK;
+  }
+  int rc = index_make_sorted(ix);
+  if (rc != LSHX_OK) return rc;
+  ix->last_nq = -1;
+  cudaStream_t st = ix->stream;
+  const int RC = IDX_SMALL_RERANK_CAP;
+  // mapped result block: ids [nq][stride] | score [nq][stride] | count [nq] | zero-norm [nq] | candidates [nq] | flag [nq]
+  uint8_t* res = ix->pin_res;
+  uint8_t* d_res = nullptr;
+  LSHX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_res), res, 0));
+  const size_t off_score = (size_t)nq * out_stride * 8, off_count = off_score + (size_t)nq * out_stride * 4,
+               off_rzero = off_count + (size_t)nq * 4, off_cand = off_rzero + (size_t)nq * 4,
+               off_flag = off_cand + (size_t)nq * 4;
+  if ((rc = ix->q_sig.reserve((size_t)IDX_SMALL_MAX_Q * s.sig_bytes)) != LSHX_OK) return rc;
+  if ((rc = ix->out_ids.reserve((size_t)IDX_SMALL_MAX_Q * RC * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->uniq.reserve((size_t)IDX_SMALL_MAX_Q * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->raw_off.reserve((size_t)(IDX_SMALL_MAX_Q + 1) * 8)) != LSHX_OK) return rc;
+  if ((rc = ix->rr_pos.reserve((size_t)IDX_SMALL_MAX_Q * RC * 4)) != LSHX_OK) return rc;
+  const size_t xb = (size_t)nq * s.dim * sizeof(float);
+  std::memcpy(h->pin_x, X, xb);
+  LSHX_CUDA(cudaMemcpyAsync(h->d_small_x, h->pin_x, xb, cudaMemcpyHostToDevice, st));
+  h->last_kernel = LSHX_KERNEL_SMALL;
+  rc = launch_hash_small(s, h->d_small_x, nq, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p),
+                         zero_flag ? d_res + off_flag : nullptr, st);
+  if (rc != LSHX_OK) return rc;
+  rc = index_query_small(static_cast<const uint8_t*>(ix->q_sig.p), nq, ix->nb, ix->bpb, ix->keys[ix->cur],
+                         ix->ids[ix->cur], ix->n, ix->cap, RC, RC, static_cast<int64_t*>(ix->out_ids.p), nullptr,
+                         reinterpret_cast<int*>(d_res + off_cand), static_cast<int*>(ix->uniq.p),
+                         static_cast<int64_t*>(ix->raw_off.p), st);
+  if (rc != LSHX_OK) return rc;
+  RerankArgs a{};
+  a.Q = h->d_small_x;                       // the query vectors are already in HBM
+  a.nq = nq;
+  a.V = corpus_device;
+  a.n_vectors = n_vectors;
+  a.offs = static_cast<const int64_t*>(ix->raw_off.p);
+  a.ids = static_cast<const int64_t*>(ix->out_ids.p);
+  a.cand_counts = static_cast<const int32_t*>(ix->uniq.p);
+  a.dim = s.dim;
+  a.k = k;
+  a.p = p;
+  a.out_stride = out_stride;
+  a.out_pos = static_cast<int32_t*>(ix->rr_pos.p);
+  a.out_score = reinterpret_cast<float*>(d_res + off_score);
+  a.out_count = reinterpret_cast<int32_t*>(d_res + off_count);
+  a.out_zero = reinterpret_cast<int32_t*>(d_res + off_rzero);
+  a.max_cand = RC;
+  a.select = true;
+  if ((rc = launch_rerank(a, st)) != LSHX_OK) return rc;
+  rc = index_pos_to_id(static_cast<const int64_t*>(ix->out_ids.p), static_cast<const int64_t*>(ix->raw_off.p), a.out_pos,
+                       a.out_count, nq, out_stride, reinterpret_cast<int64_t*>(d_res), st);
+  if (rc != LSHX_OK) return rc;
+  LSHX_CUDA(cudaStreamSynchronize(st));
+  const int32_t* h_count = reinterpret_cast<const int32_t*>(res + off_count);
+  for (int q = 0; q < nq; ++q) {
+    const int c = h_count[q];
+    out_count[q] = c;
+    std::memcpy(out_ids + (size_t)q * out_stride, res + (size_t)q * out_stride * 8, (size_t)(c > 0 ? c : 0) * 8);
+    std::memcpy(out_score + (size_t)q * out_stride, res + off_score + (size_t)q * out_stride * 4, (size_t)(c > 0 ? c : 0) * 4);
+  }
+  std::memcpy(out_candidates, res + off_cand, (size_t)nq * 4);
+  if (out_zero) std::memcpy(out_zero, res + off_rzero, (size_t)nq * 4);
+  if (zero_flag) std::memcpy(zero_flag, res + off_flag, (size_t)nq);
   return LSHX_OK;
 }
 

@@ -135,7 +135,8 @@ int index_lookup_scan(const uint8_t* d_sig, int64_t nq, int nb, int bpb, const u
                       int64_t* d_meta, cudaStream_t st);
 unsigned index_join_smem_cap();
 int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint64_t* keys, const int64_t* ids, int64_t n,
-                      int64_t cap, int out_cap, int64_t* out_ids, int* out_coll, int* out_count, cudaStream_t st);
+                      int64_t cap, int out_cap, int raw_cap, int64_t* out_ids, int* out_coll, int* out_count,
+                      int* out_count_clamped, int64_t* out_offs, cudaStream_t st);
 int index_join(int64_t nq, int nb, const int64_t* ids, int64_t cap, const int64_t* d_lo, const int* d_cnt,
                const int* d_raw_count, const int64_t* d_raw_off, const int64_t* d_ws_off, uint64_t* d_ws,
                int64_t ws_total, int64_t* d_out_ids, int* d_out_coll, int* d_uniq, cudaStream_t st);

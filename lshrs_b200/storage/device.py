@@ -147,6 +147,33 @@ class DeviceIndex:
                     counts.ctypes.data, zero.ctypes.data))
         return ids, coll, counts, zero
 
+    SMALL_RERANK_CAPACITY = 1024
+
+    def query_rerank_vectors(self, hasher, reranker, vectors: np.ndarray, corpus, *, k: int = 0, p: float = 0.0,
+                             stride: int):
+        """Latency path with the rerank fused in (``lshx_index_query_rerank_vectors``): hash, join, cosine rerank
+        against the CUDA tensor ``corpus`` (candidate id = row) and id gather in four launches and one
+        synchronisation.  Returns ``(ids int64[nq, stride], scores float32[nq, stride], counts int32[nq],
+        zero int32[nq], candidates int32[nq], zero_flag uint8[nq])``; ``candidates[i]`` is -1 when query i matches
+        more than 1024 bucket entries (nothing was ranked: take ``query`` + ``rerank``)."""
+        x = np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, hasher.dim)
+        nq, stride = x.shape[0], int(stride)
+        ids = np.full((nq, stride), -1, dtype=np.int64)
+        scores = np.zeros((nq, stride), dtype=np.float32)
+        counts = np.zeros(nq, dtype=np.int32)
+        zero = np.zeros(nq, dtype=np.int32)
+        cands = np.zeros(nq, dtype=np.int32)
+        flag = np.zeros(nq, dtype=np.uint8)
+        if nq:
+            if corpus.dim() != 2 or corpus.shape[1] != hasher.dim or not corpus.is_contiguous():
+                raise ValueError(f"corpus must be a contiguous (n, {hasher.dim}) float32 CUDA tensor")
+            with self.lock:
+                _native.check(_native.lib().lshx_index_query_rerank_vectors(
+                    self._handle, hasher._ensure_handle(), reranker._handle, x.ctypes.data, nq, int(corpus.data_ptr()),
+                    int(corpus.shape[0]), int(k), float(p), stride, ids.ctypes.data, scores.ctypes.data,
+                    counts.ctypes.data, zero.ctypes.data, cands.ctypes.data, flag.ctypes.data))
+        return ids, scores, counts, zero, cands, flag
+
     def query_one(self, signature: np.ndarray):
         """``(ids int64[c], collisions int32[c])`` of ONE query, ordered by (-collisions, id)."""
         with self.lock:

@@ -325,6 +325,57 @@ def _index_methods():
         self.launches += 2
         return 0
 
+    def lshx_index_query_rerank_vectors(self, h, hh, rh, X_ptr, nq, V_ptr, nvec, k, p, stride, ids_ptr, score_ptr,
+                                        count_ptr, zero_ptr, cand_ptr, flag_ptr):
+        ix, hs = self._get(h), self._get(hh)
+        dim = hs.dim
+        X = _arr(X_ptr, (nq, dim), np.float32)
+        V = _arr(V_ptr, (nvec, dim), np.float32)
+        sig = oracle.hash_batch_packed(hs.projs, X).reshape(nq, ix.nb, ix.bpb)
+        out_ids, out_sc = _arr(ids_ptr, (nq, stride), np.int64), _arr(score_ptr, (nq, stride), np.float32)
+        cnt, cands = _arr(count_ptr, (nq,), np.int32), _arr(cand_ptr, (nq,), np.int32)
+        zero_all = np.zeros(nq, np.int32)
+        for q in range(nq):
+            counts: dict[int, int] = {}
+            slots = 0
+            for b in range(ix.nb):
+                members = ix.buckets[b].get(sig[q, b].tobytes(), ())
+                slots += len(members)
+                for m in members:
+                    counts[m] = counts.get(m, 0) + 1
+            cnt[q] = 0
+            if slots > 1024:
+                cands[q] = -1
+                continue
+            order = [i for i, _ in sorted(counts.items(), key=lambda kv: (-kv[1], kv[0]))]
+            n = len(order)
+            cands[q] = n
+            if not n:
+                continue
+            flat = np.array(order, dtype=np.int64)
+            zero = np.zeros(1, np.int32)
+            s = self._scores(dim, X[q:q + 1], V, np.array([0, n], dtype=np.int64), flat, zero)
+            zero_all[q] = zero[0]
+            limit = n
+            if p > 0:
+                limit = max(1, math.ceil(n * p))
+                if k > 0:
+                    limit = min(limit, k)
+            elif k > 0:
+                limit = min(k, n)
+            limit = min(limit, n, stride)
+            best = np.lexsort((np.arange(n), -np.nan_to_num(s, nan=-np.inf)))[:limit]
+            out_ids[q, :limit] = flat[best]
+            out_sc[q, :limit] = s[best]
+            cnt[q] = limit
+        if not _null(zero_ptr):
+            _arr(zero_ptr, (nq,), np.int32)[...] = zero_all
+        if not _null(flag_ptr):
+            _arr(flag_ptr, (nq,), np.uint8)[...] = [1 if oracle.is_zero_vector(x) else 0 for x in X]
+        ix.result = None
+        self.launches += 4
+        return 0
+
     def lshx_index_export(self, h, keys_ptr, ids_ptr, cap, n_ref):
         ix = self._get(h)
         rows = [[(k, i) for k, members in sorted(band.items()) for i in sorted(members)] for band in ix.buckets]

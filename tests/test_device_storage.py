@@ -259,7 +259,7 @@ def test_single_queries_rerank_against_a_resident_corpus():
     X = _clustered(4000, 96, seed=11)
     xd = torch.from_numpy(X).cuda()
     fetch = lambda ids: X[np.asarray(ids, dtype=np.int64)]   # noqa: E731
-    kw = dict(dim=96, num_perm=64, num_bands=16, rows_per_band=4)
+    kw = dict(dim=96, num_perm=128, num_bands=16, rows_per_band=8)
     host = LSHRS(storage=InMemoryStorage(), vector_fetch_fn=fetch, **kw)
     res = LSHRS(storage=DeviceBucketStorage(), corpus=xd, **kw)
     mem = LSHRS(storage=InMemoryStorage(), corpus=xd, **kw)
@@ -274,6 +274,11 @@ def test_single_queries_rerank_against_a_resident_corpus():
                 got = call(lsh)
                 assert [i for i, _ in got] == [i for i, _ in want]
                 np.testing.assert_allclose([s for _, s in got], [s for _, s in want], atol=1e-6)
+    from lshrs_b200 import _native
+
+    before = _native.launch_count()
+    assert res.get_above_p(Q[3], p=0.3)
+    assert _native.launch_count() - before == 4          # hash, lookup/join, rerank, id gather: the fused path
     want = host.query_batch(Q, top_k=4, top_p=0.5)
     for lsh in (res, mem):
         got = lsh.query_batch(Q, top_k=4, top_p=0.5)                 # corpus= defaults to the instance's

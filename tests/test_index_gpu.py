@@ -267,7 +267,11 @@ def test_latency_path_equals_hash_plus_batched_join(dim, nb, r):
     big = np.repeat(h.hash_batch_packed(Q[:1]), 5000, axis=0)
     ix.add(big, np.arange(10_000_000, 10_005_000, dtype=np.int64))
     ids, coll, counts, zero = ix.query_vectors(h, Q[:2], 16)
-    assert counts[0] == -1 and counts[1] == len(_lists(ix, h.hash_batch_packed(Q[1:2]))[0])
+    ix.query(h.hash_batch_packed(Q[:2]))
+    offs = ix.fetch()[0]
+    slots1 = int(offs[2] - offs[1])                                 # bucket entries query 1 matches
+    want1 = len(_lists(ix, h.hash_batch_packed(Q[1:2]))[0])
+    assert counts[0] == -1 and counts[1] == (want1 if slots1 <= 4096 else -1)
     with pytest.raises(lshrs_b200.LshxError):
         ix.query_vectors(h, np.zeros((33, dim), np.float32), 8)
     with pytest.raises(lshrs_b200.LshxError):
