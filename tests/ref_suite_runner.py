@@ -6,6 +6,8 @@ three arrangements of ``import lshrs`` and print one JSON line with the outcome.
     python tests/ref_suite_runner.py --variant two_import           # reference LSHRS, B200 hasher + rerank
     python tests/ref_suite_runner.py --variant dropin               # lshrs_b200.compat: B200 everything on the path
     python tests/ref_suite_runner.py --variant dropin --cpu-double  # host logic only, oracle-backed C-ABI double
+    python tests/ref_suite_runner.py --variant dropin --device-store   # ... and the suite's MockStorage fixture is
+                                                                       # the bucket store in HBM (DeviceBucketStorage)
 
 Used by tests/test_reference_suite.py (subprocess).  ``--cpu-double`` swaps liblshx for tests/fake_lshx.py
 so the host layer can be checked without a GPU; without it the real library runs and a run that launched
@@ -44,10 +46,75 @@ class _Tally:
             self.skipped += 1
 
 
+class _DeviceStoreFixture:
+    """Swaps the suite's ``MockStorage`` (reference tests/conftest.py:15-78, a dict of sets that records what it is
+    sent) for the same recorder on top of ``lshrs_b200.DeviceBucketStorage``: every test that builds its LSHRS on
+    the fixture then runs with the bucket store in HBM -- packed ``index()``, device joins for the queries."""
+
+    def pytest_collection_finish(self, session):
+        import numpy as np
+
+        from lshrs_b200 import DeviceBucketStorage
+
+        class MockStorage(DeviceBucketStorage):
+            def __init__(self, *, fail_on_flush: bool = False) -> None:
+                super().__init__()
+                self.batches, self.all_operations, self.removed_indices = [], [], []
+                self.batch_add_call_count = 0
+                self.close_called = self.clear_called = False
+                self._fail_on_flush = fail_on_flush
+
+            def _record(self, operations) -> None:
+                self.batch_add_call_count += 1
+                self.batches.append(list(operations))
+                self.all_operations.extend(operations)
+
+            def batch_add(self, operations) -> None:
+                if self._fail_on_flush:
+                    raise ConnectionError("Simulated Redis failure")
+                self._record(operations)
+                super().batch_add(operations)
+
+            def add_packed(self, signatures, ids) -> None:
+                if self._fail_on_flush:
+                    raise ConnectionError("Simulated Redis failure")
+                sig = np.asarray(signatures)
+                self._record([(b, sig[i, b].tobytes(), int(ids[i])) for i in range(sig.shape[0])
+                              for b in range(sig.shape[1])])
+                super().add_packed(signatures, ids)
+
+            def remove_indices(self, indices) -> None:
+                self.removed_indices.append(list(indices))
+                super().remove_indices(indices)
+
+            def clear(self) -> None:
+                self.clear_called = True
+                super().clear()
+
+            def close(self) -> None:
+                self.close_called = True
+
+            @property
+            def total_operations(self) -> int:
+                return len(self.all_operations)
+
+            @property
+            def unique_indices(self) -> set:
+                return {idx for _, _, idx in self.all_operations}
+
+        patched = 0
+        for name, mod in list(sys.modules.items()):
+            if name.endswith("conftest") and hasattr(mod, "MockStorage") and hasattr(mod, "make_lsh"):
+                mod.MockStorage = MockStorage
+                patched += 1
+        self.patched = patched
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--variant", choices=("reference", "two_import", "dropin"), required=True)
     ap.add_argument("--cpu-double", action="store_true")
+    ap.add_argument("--device-store", action="store_true")
     ap.add_argument("-k", default=None)
     args = ap.parse_args()
     if not (REF / "suite" / "tests").is_dir():
@@ -74,7 +141,8 @@ def main() -> int:
             "-o", "addopts=", "-W", "ignore"]
     if args.k:
         argv += ["-k", args.k]
-    rc = pytest.main(argv, plugins=[tally])
+    store = _DeviceStoreFixture() if args.device_store else None
+    rc = pytest.main(argv, plugins=[tally] + ([store] if store else []))
     import lshrs
 
     launches = None
@@ -83,7 +151,7 @@ def main() -> int:
 
         launches = fake.launches if fake is not None else (_native.launch_count() if _native._lib is not None else 0)
     print(json.dumps({"staged": True, "variant": args.variant, "cpu_double": bool(args.cpu_double), "rc": int(rc),
-                      "passed": tally.passed, "failed": tally.failed, "errors": tally.errors,
+                      "device_store": bool(store and getattr(store, "patched", 0)), "passed": tally.passed, "failed": tally.failed, "errors": tally.errors,
                       "skipped": tally.skipped, "failures": tally.failures[:20], "lshrs": str(lshrs.__file__),
                       "lshrs_LSHRS_module": lshrs.LSHRS.__module__, "kernel_launches": launches}))
     return 0 if rc == 0 else 1

@@ -33,10 +33,12 @@ needs_staged = pytest.mark.skipif(not STAGED, reason="oracle/_ref is not staged 
                                                       "/root/reference exists)")
 
 
-def _run(variant: str, cpu_double: bool) -> dict:
+def _run(variant: str, cpu_double: bool, device_store: bool = False) -> dict:
     cmd = [sys.executable, str(REPO / "tests" / "ref_suite_runner.py"), "--variant", variant]
     if cpu_double:
         cmd.append("--cpu-double")
+    if device_store:
+        cmd.append("--device-store")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(REPO))
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert lines, f"runner printed no summary (rc {res.returncode}):\n{res.stdout[-3000:]}\n{res.stderr[-3000:]}"
@@ -93,3 +95,20 @@ def test_reference_suite_on_b200(variant):
     if variant == "dropin":
         assert out["lshrs_LSHRS_module"] == "lshrs_b200.core.main" and "lshrs_b200/compat" in out["lshrs"]
     assert out["kernel_launches"] and out["kernel_launches"] > 100, out   # liblshx really ran
+
+
+@needs_staged
+def test_reference_suite_on_the_device_store_host_logic_on_cpu():
+    """The suite's MockStorage fixture replaced by the same recorder on DeviceBucketStorage (the bucket store in
+    HBM): packed index(), device joins, latency-path queries -- all 71 tests still pass."""
+    out = _run("dropin", cpu_double=True, device_store=True)
+    _assert_all_passed(out)
+    assert out["device_store"] and out["lshrs_LSHRS_module"] == "lshrs_b200.core.main"
+
+
+@needs_staged
+@pytest.mark.gpu
+def test_reference_suite_on_the_device_store_on_the_gpu():
+    out = _run("dropin", cpu_double=False, device_store=True)
+    _assert_all_passed(out)
+    assert out["device_store"] and out["kernel_launches"] > 0
