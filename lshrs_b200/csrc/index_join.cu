@@ -196,39 +196,45 @@ __global__ void index_tombstone_kernel(int64_t* __restrict__ ids, int64_t n, int
 // ---------------------------------------------------------------------------------------------------
 // query
 // ---------------------------------------------------------------------------------------------------
+// Runs: the main run [0, main_n) and, when main_n < n, the delta run [main_n, n) of every band segment are each in
+// (key, id) order (a small add is sorted on its own instead of re-sorting the whole segment).  A query searches both:
+// slot v = run * nb + band of query q -> lo (absolute entry index), cnt.
+__device__ __forceinline__ void search_run(const uint64_t* __restrict__ k, int64_t begin, int64_t end, uint64_t key,
+                                           int64_t& lo_out, int64_t& cnt_out) {
+  int64_t lo = begin, hi = end;
+  while (lo < hi) {                       // first entry with k >= key
+    const int64_t mid = (lo + hi) >> 1;
+    if (__ldg(k + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  int64_t lo2 = lo, hi2 = end;
+  while (lo2 < hi2) {                     // first entry with k > key
+    const int64_t mid = (lo2 + hi2) >> 1;
+    if (__ldg(k + mid) <= key) lo2 = mid + 1; else hi2 = mid;
+  }
+  lo_out = lo;
+  cnt_out = lo2 - lo;
+}
+
 __global__ void index_lookup_kernel(const uint8_t* __restrict__ sig, int64_t nq, int nb, int bpb,
-                                    const uint64_t* __restrict__ keys, int64_t n, int64_t cap,
+                                    const uint64_t* __restrict__ keys, int64_t main_n, int64_t n, int64_t cap,
                                     int64_t* __restrict__ lo_out, int* __restrict__ cnt_out,
                                     int* __restrict__ raw_count) {
-  const int64_t total = nq * nb;
+  const int nruns = n > main_n ? 2 : 1;
+  const int nv = nb * nruns;
+  const int64_t total = nq * nv;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = t / nb;
-    const int b = (int)(t % nb);
+    const int64_t q = t / nv;
+    const int v = (int)(t % nv);
+    const int b = v % nb, run = v / nb;
     const uint8_t* src = sig + (q * nb + b) * (int64_t)bpb;
     uint64_t key = 0;
     for (int j = 0; j < bpb; ++j) key |= (uint64_t)src[j] << (8 * j);
-    const uint64_t* k = keys + b * cap;
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {                       // first entry with k >= key
-      const int64_t mid = (lo + hi) >> 1;
-      if (__ldg(k + mid) < key) lo = mid + 1; else hi = mid;
-    }
-    int64_t lo2 = lo, hi2 = n;
-    while (lo2 < hi2) {                     // first entry with k > key
-      const int64_t mid = (lo2 + hi2) >> 1;
-      if (__ldg(k + mid) <= key) lo2 = mid + 1; else hi2 = mid;
-    }
-    const int64_t c = lo2 - lo;
+    int64_t lo, c;
+    search_run(keys + b * cap, run ? main_n : 0, run ? n : main_n, key, lo, c);
     lo_out[t] = lo;
     cnt_out[t] = (int)(c > 0x7fffffff ? 0x7fffffff : c);
     if (c) atomicAdd(raw_count + q, (int)c);
   }
-}
-
-__device__ __forceinline__ unsigned pow2_at_least(unsigned v) {
-  unsigned p = 2;
-  while (p < v) p <<= 1;
-  return p;
 }
 
 // exclusive scans of raw_count (candidate slots) and of pow2(raw_count) (sort workspace slots);
@@ -300,7 +306,8 @@ __device__ __forceinline__ void bitonic_asc(uint64_t* a, unsigned P, int tid) {
 
 struct JoinArgs {
   int64_t nq;
-  int nb;
+  int nb;                  // bands
+  int nv;                  // slots per query: nb (one run) or 2 * nb (main + delta run)
   const int64_t* ids;      // [nb][cap]
   int64_t cap;
   const int64_t* lo;       // [nq][nb]
@@ -319,7 +326,7 @@ template <bool SMEM>
 __global__ void __launch_bounds__(JN_THREADS)
 index_join_kernel(JoinArgs a) {
   extern __shared__ __align__(16) uint64_t sm[];
-  __shared__ int band_off[256];
+  __shared__ int band_off[512];
   __shared__ int heads;
   const int tid = threadIdx.x;
   for (int64_t q = blockIdx.x; q < a.nq; q += gridDim.x) {
@@ -333,33 +340,34 @@ index_join_kernel(JoinArgs a) {
     uint64_t* buf2 = SMEM ? sm + JN_SMEM_CAP : a.ws + a.ws_total + a.ws_off[q];
     if (tid == 0) {
       int acc = 0;
-      for (int b = 0; b < a.nb; ++b) { band_off[b] = acc; acc += a.cnt[q * a.nb + b]; }
+      for (int v = 0; v < a.nv; ++v) { band_off[v] = acc; acc += a.cnt[q * a.nv + v]; }
       heads = 0;
     }
     __syncthreads();
-    // gather: the ids of every matching bucket; an id repeated inside one bucket (indexed twice with the
-    // same band key) counts once like a Redis SET member, a tombstone not at all
-    for (int b = 0; b < a.nb; ++b) {
-      const int c = a.cnt[q * a.nb + b];
-      const int64_t* src = a.ids + b * a.cap + a.lo[q * a.nb + b];
+    // gather (id, band) pairs of every matching bucket: after the sort an id repeated inside one bucket (indexed
+    // twice with the same band key -- in one run or once in each) is a repeated PAIR and counts once, like a
+    // Redis SET member; a tombstone not at all
+    for (int v = 0; v < a.nv; ++v) {
+      const int b = v % a.nb;
+      const int c = a.cnt[q * a.nv + v];
+      const int64_t* src = a.ids + b * a.cap + a.lo[q * a.nv + v];
       for (int i = tid; i < c; i += JN_THREADS) {
         const int64_t id = src[i];
-        const bool dup = (i > 0 && src[i - 1] == id);
-        buf[band_off[b] + i] = (id < 0 || dup) ? EMPTY : (uint64_t)id;
+        buf[band_off[v] + i] = id < 0 ? EMPTY : (((uint64_t)id << 8) | (uint64_t)b);
       }
     }
     for (unsigned i = n_raw + tid; i < P; i += JN_THREADS) buf[i] = EMPTY;
     __syncthreads();
     bitonic_asc(buf, P, tid);
-    // run lengths = collisions; order key = (255 - collisions) << 56 | id  (ascending = (-collisions, id))
+    // distinct bands per id = collisions; order key = (255 - collisions) << 56 | id  (ascending = (-collisions, id))
     int mine = 0;
     for (unsigned i = tid; i < P; i += JN_THREADS) {
       const uint64_t v = buf[i];
       uint64_t key2 = EMPTY;
-      if (v != EMPTY && (i == 0 || buf[i - 1] != v)) {
-        unsigned run = 1;
-        while (i + run < P && buf[i + run] == v) ++run;
-        key2 = ((uint64_t)(255u - run) << ID_BITS) | v;
+      if (v != EMPTY && (i == 0 || (buf[i - 1] >> 8) != (v >> 8))) {
+        unsigned coll = 1;
+        for (unsigned j = i + 1; j < P && (buf[j] >> 8) == (v >> 8); ++j) coll += (buf[j] != buf[j - 1]) ? 1u : 0u;
+        key2 = ((uint64_t)(255u - coll) << ID_BITS) | (v >> 8);
         ++mine;
       }
       buf2[i] = key2;
@@ -387,39 +395,32 @@ index_join_kernel(JoinArgs a) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(JN_THREADS)
 index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const uint64_t* __restrict__ keys,
-                         const int64_t* __restrict__ ids, int64_t n, int64_t cap, int out_cap, int raw_cap,
-                         int64_t* __restrict__ out_ids, int* __restrict__ out_coll, int* __restrict__ out_count,
-                         int* __restrict__ out_count_clamped, int64_t* __restrict__ out_offs) {
+                         const int64_t* __restrict__ ids, int64_t main_n, int64_t n, int64_t cap, int out_cap,
+                         int raw_cap, int64_t* __restrict__ out_ids, int* __restrict__ out_coll,
+                         int* __restrict__ out_count, int* __restrict__ out_count_clamped,
+                         int64_t* __restrict__ out_offs) {
   extern __shared__ __align__(16) uint64_t sm[];
-  __shared__ int64_t s_lo[256];
-  __shared__ int s_cnt[256];
-  __shared__ int band_off[256];
+  __shared__ int64_t s_lo[512];
+  __shared__ int s_cnt[512];
+  __shared__ int band_off[512];
   __shared__ int heads, n_raw_s;
   const int tid = threadIdx.x;
   const int64_t q = blockIdx.x;
-  if (tid < nb) {
-    const uint8_t* src = sig + (q * nb + tid) * (int64_t)bpb;
+  const int nv = nb * (n > main_n ? 2 : 1);
+  for (int v = tid; v < nv; v += JN_THREADS) {
+    const int b = v % nb, run = v / nb;
+    const uint8_t* src = sig + (q * nb + b) * (int64_t)bpb;
     uint64_t key = 0;
     for (int j = 0; j < bpb; ++j) key |= (uint64_t)src[j] << (8 * j);
-    const uint64_t* k = keys + tid * cap;
-    int64_t lo = 0, hi = n;
-    while (lo < hi) {
-      const int64_t mid = (lo + hi) >> 1;
-      if (__ldg(k + mid) < key) lo = mid + 1; else hi = mid;
-    }
-    int64_t lo2 = lo, hi2 = n;
-    while (lo2 < hi2) {
-      const int64_t mid = (lo2 + hi2) >> 1;
-      if (__ldg(k + mid) <= key) lo2 = mid + 1; else hi2 = mid;
-    }
-    s_lo[tid] = lo;
-    const int64_t c = lo2 - lo;
-    s_cnt[tid] = (int)(c > 0x7fffffff ? 0x7fffffff : c);
+    int64_t lo, c;
+    search_run(keys + b * cap, run ? main_n : 0, run ? n : main_n, key, lo, c);
+    s_lo[v] = lo;
+    s_cnt[v] = (int)(c > 0x7fffffff ? 0x7fffffff : c);
   }
   __syncthreads();
   if (tid == 0) {
     long long acc = 0;
-    for (int b = 0; b < nb; ++b) { band_off[b] = (int)(acc > 0x7fffffff ? 0x7fffffff : acc); acc += s_cnt[b]; }
+    for (int v = 0; v < nv; ++v) { band_off[v] = (int)(acc > 0x7fffffff ? 0x7fffffff : acc); acc += s_cnt[v]; }
     n_raw_s = acc > (long long)raw_cap ? -1 : (int)acc;
     heads = 0;
     if (out_offs) out_offs[q] = q * (int64_t)out_cap;       // CSR base of this query's slots for the rerank kernel
@@ -436,13 +437,13 @@ index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const
   const unsigned P = pow2_at_least((unsigned)n_raw);
   uint64_t* buf = sm;
   uint64_t* buf2 = sm + JN_SMEM_CAP;
-  for (int b = 0; b < nb; ++b) {
-    const int c = s_cnt[b];
-    const int64_t* src = ids + b * cap + s_lo[b];
+  for (int v = 0; v < nv; ++v) {
+    const int b = v % nb;
+    const int c = s_cnt[v];
+    const int64_t* src = ids + b * cap + s_lo[v];
     for (int i = tid; i < c; i += JN_THREADS) {
       const int64_t id = src[i];
-      const bool dup = (i > 0 && src[i - 1] == id);
-      buf[band_off[b] + i] = (id < 0 || dup) ? EMPTY : (uint64_t)id;
+      buf[band_off[v] + i] = id < 0 ? EMPTY : (((uint64_t)id << 8) | (uint64_t)b);   // (id, band), as in the join
     }
   }
   for (unsigned i = n_raw + tid; i < P; i += JN_THREADS) buf[i] = EMPTY;
@@ -452,10 +453,10 @@ index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const
   for (unsigned i = tid; i < P; i += JN_THREADS) {
     const uint64_t v = buf[i];
     uint64_t key2 = EMPTY;
-    if (v != EMPTY && (i == 0 || buf[i - 1] != v)) {
-      unsigned run = 1;
-      while (i + run < P && buf[i + run] == v) ++run;
-      key2 = ((uint64_t)(255u - run) << ID_BITS) | v;
+    if (v != EMPTY && (i == 0 || (buf[i - 1] >> 8) != (v >> 8))) {
+      unsigned coll = 1;
+      for (unsigned j = i + 1; j < P && (buf[j] >> 8) == (v >> 8); ++j) coll += (buf[j] != buf[j - 1]) ? 1u : 0u;
+      key2 = ((uint64_t)(255u - coll) << ID_BITS) | (v >> 8);
       ++mine;
     }
     buf2[i] = key2;
@@ -558,9 +559,13 @@ int index_append(const uint8_t* d_sig, const int64_t* d_ids, int64_t n, int nb, 
   return LSHX_OK;
 }
 
-int index_sort(uint64_t* keys[2], int64_t* ids[2], int* cur, int64_t n, int64_t cap, int nb, int key_bytes,
-               int id_bytes, unsigned* d_hist, size_t hist_entries, cudaStream_t st) {
+// Sorts entries [first, first + n) of every band segment by (key, id); *cur names the buffer that holds them and is
+// flipped once per pass -- the caller moves the range back when it must stay beside entries that were not sorted.
+int index_sort(uint64_t* keys_in[2], int64_t* ids_in[2], int* cur, int64_t first, int64_t n, int64_t cap, int nb,
+               int key_bytes, int id_bytes, unsigned* d_hist, size_t hist_entries, cudaStream_t st) {
   if (n <= 1) return LSHX_OK;
+  uint64_t* keys[2] = {keys_in[0] + first, keys_in[1] + first};
+  int64_t* ids[2] = {ids_in[0] + first, ids_in[1] + first};
   const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
   LSHX_REQUIRE((size_t)nb * 256 * ntiles <= hist_entries, "radix histogram scratch too small");
   LSHX_REQUIRE(n < (1ll << 32), "more than 2^32 entries per band are not supported");
@@ -591,11 +596,12 @@ int index_tombstone(int64_t* ids, int64_t n, int64_t cap, int nb, const int64_t*
   return LSHX_OK;
 }
 
-int index_lookup_scan(const uint8_t* d_sig, int64_t nq, int nb, int bpb, const uint64_t* keys, int64_t n, int64_t cap,
-                      int64_t* d_lo, int* d_cnt, int* d_raw_count, int64_t* d_raw_off, int64_t* d_ws_off,
+int index_lookup_scan(const uint8_t* d_sig, int64_t nq, int nb, int bpb, const uint64_t* keys, int64_t main_n, int64_t n,
+                      int64_t cap, int64_t* d_lo, int* d_cnt, int* d_raw_count, int64_t* d_raw_off, int64_t* d_ws_off,
                       int64_t* d_meta, cudaStream_t st) {
   LSHX_CUDA(cudaMemsetAsync(d_raw_count, 0, (size_t)nq * sizeof(int), st));
-  index_lookup_kernel<<<grid_for(nq * nb, 256), 256, 0, st>>>(d_sig, nq, nb, bpb, keys, n, cap, d_lo, d_cnt, d_raw_count);
+  index_lookup_kernel<<<grid_for(nq * nb * (n > main_n ? 2 : 1), 256), 256, 0, st>>>(d_sig, nq, nb, bpb, keys, main_n, n,
+                                                                                       cap, d_lo, d_cnt, d_raw_count);
   index_scan_kernel<<<1, 1024, 0, st>>>(d_raw_count, nq, d_raw_off, d_ws_off, d_meta);
   count_launch(2);
   LSHX_CUDA(cudaGetLastError());
@@ -623,11 +629,11 @@ int index_bucket_gather(const int* d_band_ids, const int64_t* d_lo, const int64_
 
 unsigned index_join_smem_cap() { return JN_SMEM_CAP; }
 
-int index_join(int64_t nq, int nb, const int64_t* ids, int64_t cap, const int64_t* d_lo, const int* d_cnt,
+int index_join(int64_t nq, int nb, int nruns, const int64_t* ids, int64_t cap, const int64_t* d_lo, const int* d_cnt,
                const int* d_raw_count, const int64_t* d_raw_off, const int64_t* d_ws_off, uint64_t* d_ws,
                int64_t ws_total, int64_t* d_out_ids, int* d_out_coll, int* d_uniq, cudaStream_t st) {
   if (nq <= 0) return LSHX_OK;
-  JoinArgs a{nq, nb, ids, cap, d_lo, d_cnt, d_raw_count, d_raw_off, d_ws_off, d_ws, ws_total, d_out_ids, d_out_coll,
+  JoinArgs a{nq, nb, nb * nruns, ids, cap, d_lo, d_cnt, d_raw_count, d_raw_off, d_ws_off, d_ws, ws_total, d_out_ids, d_out_coll,
              d_uniq};
   const unsigned grid = (unsigned)(nq < 148 * 8 ? nq : 148 * 8);
   if (d_ws == nullptr) {
@@ -642,15 +648,15 @@ int index_join(int64_t nq, int nb, const int64_t* ids, int64_t cap, const int64_
   return LSHX_OK;
 }
 
-int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint64_t* keys, const int64_t* ids, int64_t n,
-                      int64_t cap, int out_cap, int raw_cap, int64_t* out_ids, int* out_coll, int* out_count,
+int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint64_t* keys, const int64_t* ids,
+                      int64_t main_n, int64_t n, int64_t cap, int out_cap, int raw_cap, int64_t* out_ids, int* out_coll, int* out_count,
                       int* out_count_clamped, int64_t* out_offs, cudaStream_t st) {
   if (nq <= 0) return LSHX_OK;
   if (raw_cap <= 0 || raw_cap > (int)JN_SMEM_CAP) raw_cap = (int)JN_SMEM_CAP;
   const size_t smem = 2 * (size_t)JN_SMEM_CAP * sizeof(uint64_t);
   LSHX_CUDA(cudaFuncSetAttribute(index_query_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  index_query_small_kernel<<<(unsigned)nq, JN_THREADS, smem, st>>>(d_sig, nb, bpb, keys, ids, n, cap, out_cap, raw_cap,
-                                                                  out_ids, out_coll, out_count, out_count_clamped,
+  index_query_small_kernel<<<(unsigned)nq, JN_THREADS, smem, st>>>(d_sig, nb, bpb, keys, ids, main_n, n, cap, out_cap,
+                                                                  raw_cap, out_ids, out_coll, out_count, out_count_clamped,
                                                                   out_offs);
   count_launch();
   LSHX_CUDA(cudaGetLastError());

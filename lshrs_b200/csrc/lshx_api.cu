@@ -975,7 +975,10 @@ struct lshx_index {
   int device = 0;
   int nb = 0, bpb = 0;
   int64_t n = 0;         // entries per band (tombstones included)
-  int64_t sorted_n = 0;  // leading entries of every segment that are in (key, id) order
+  // Two sorted runs per band segment: the main run [0, main_n) and the delta run [main_n, delta_n); entries
+  // [delta_n, n) were appended since the last query.  A small add is sorted into the delta run on its own; the
+  // segment is re-sorted as a whole only when the delta outgrows a quarter of the main run.
+  int64_t main_n = 0, delta_n = 0;
   int64_t cap = 0;       // entries each band segment can hold
   uint64_t* keys[2] = {nullptr, nullptr};
   int64_t* ids[2] = {nullptr, nullptr};
@@ -1140,7 +1143,7 @@ extern "C" int lshx_index_clear(lshx_index* ix) {
   std::lock_guard<std::mutex> lk(ix->mu);
   DeviceGuard g(ix->device);
   LSHX_CUDA(cudaStreamSynchronize(ix->stream));
-  ix->n = ix->sorted_n = 0;
+  ix->n = ix->main_n = ix->delta_n = 0;
   ix->last_nq = -1;
   LSHX_CUDA(cudaMemset(ix->d_max_id, 0, 8));
   return LSHX_OK;
@@ -1165,9 +1168,14 @@ extern "C" int lshx_index_remove(lshx_index* ix, const int64_t* ids_host, int64_
   return LSHX_OK;
 }
 
-// sort what add() appended since the last query
-static int index_make_sorted(lshx_index* ix) {
-  if (ix->sorted_n == ix->n) return LSHX_OK;
+// sort what add() appended since the last query: into the delta run when that is small beside the main run,
+// else the whole segment (which folds the delta into the main run).  force_full: a caller that reads ranges of
+// ONE run (get_buckets, export).
+constexpr int64_t IDX_MIN_MAIN = 32768;   // below this a full sort is as cheap as bookkeeping
+
+static int index_make_sorted(lshx_index* ix, bool force_full = false) {
+  if (ix->main_n == ix->n) return LSHX_OK;
+  if (!force_full && ix->delta_n == ix->n) return LSHX_OK;
   unsigned long long max_id = 0;
   LSHX_CUDA(cudaMemcpyAsync(&max_id, ix->d_max_id, 8, cudaMemcpyDeviceToHost, ix->stream));
   LSHX_CUDA(cudaStreamSynchronize(ix->stream));
@@ -1175,13 +1183,29 @@ static int index_make_sorted(lshx_index* ix) {
   // tombstones sort after every live id of their bucket
   int id_bytes = 1;
   while (id_bytes < 8 && ((max_id + 1) >> (8 * id_bytes)) != 0) ++id_bytes;
-  const size_t hist_entries = index_sort_hist_entries(ix->n, ix->nb);
+  const int64_t tail = ix->n - ix->main_n;
+  const bool full = force_full || ix->main_n < IDX_MIN_MAIN || tail * 4 > ix->main_n;
+  const int64_t first = full ? 0 : ix->main_n, count = full ? ix->n : tail;
+  const size_t hist_entries = index_sort_hist_entries(count, ix->nb);
   int rc = ix->hist.reserve(hist_entries * sizeof(unsigned));
   if (rc != LSHX_OK) return rc;
-  rc = index_sort(ix->keys, ix->ids, &ix->cur, ix->n, ix->cap, ix->nb, ix->bpb, id_bytes,
+  int cur = ix->cur;
+  rc = index_sort(ix->keys, ix->ids, &cur, first, count, ix->cap, ix->nb, ix->bpb, id_bytes,
                   static_cast<unsigned*>(ix->hist.p), hist_entries, ix->stream);
   if (rc != LSHX_OK) return rc;
-  ix->sorted_n = ix->n;
+  if (full) {
+    ix->cur = cur;
+    ix->main_n = ix->delta_n = ix->n;
+    return LSHX_OK;
+  }
+  if (cur != ix->cur) {   // an odd number of passes left the sorted delta in the other buffer: bring it home
+    const size_t pitch = (size_t)ix->cap * 8, width = (size_t)count * 8;
+    LSHX_CUDA(cudaMemcpy2DAsync(ix->keys[ix->cur] + first, pitch, ix->keys[cur] + first, pitch, width, (size_t)ix->nb,
+                                cudaMemcpyDeviceToDevice, ix->stream));
+    LSHX_CUDA(cudaMemcpy2DAsync(ix->ids[ix->cur] + first, pitch, ix->ids[cur] + first, pitch, width, (size_t)ix->nb,
+                                cudaMemcpyDeviceToDevice, ix->stream));
+  }
+  ix->delta_n = ix->n;
   return LSHX_OK;
 }
 
@@ -1211,14 +1235,15 @@ extern "C" int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64
   } else {
     LSHX_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
   }
-  if ((rc = ix->lo.reserve((size_t)nq * ix->nb * 8)) != LSHX_OK) return rc;
-  if ((rc = ix->cnt.reserve((size_t)nq * ix->nb * 4)) != LSHX_OK) return rc;
+  if ((rc = ix->lo.reserve((size_t)nq * ix->nb * 2 * 8)) != LSHX_OK) return rc;    // two runs per band
+  if ((rc = ix->cnt.reserve((size_t)nq * ix->nb * 2 * 4)) != LSHX_OK) return rc;
   if ((rc = ix->raw_count.reserve((size_t)nq * 4)) != LSHX_OK) return rc;
   if ((rc = ix->raw_off.reserve((size_t)(nq + 1) * 8)) != LSHX_OK) return rc;
   if ((rc = ix->ws_off.reserve((size_t)(nq + 1) * 8)) != LSHX_OK) return rc;
   if ((rc = ix->meta.reserve(32)) != LSHX_OK) return rc;
   if ((rc = ix->uniq.reserve((size_t)nq * 4)) != LSHX_OK) return rc;
-  rc = index_lookup_scan(d_sig, nq, ix->nb, ix->bpb, ix->keys[ix->cur], ix->n, ix->cap,
+  const int nruns = ix->n > ix->main_n ? 2 : 1;
+  rc = index_lookup_scan(d_sig, nq, ix->nb, ix->bpb, ix->keys[ix->cur], ix->main_n, ix->n, ix->cap,
                          static_cast<int64_t*>(ix->lo.p), static_cast<int*>(ix->cnt.p),
                          static_cast<int*>(ix->raw_count.p), static_cast<int64_t*>(ix->raw_off.p),
                          static_cast<int64_t*>(ix->ws_off.p), static_cast<int64_t*>(ix->meta.p), ix->stream);
@@ -1235,7 +1260,7 @@ extern "C" int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64
     if ((rc = ix->ws.reserve((size_t)ws_total * 2 * 8)) != LSHX_OK) return rc;
     d_ws = static_cast<uint64_t*>(ix->ws.p);
   }
-  rc = index_join(nq, ix->nb, ix->ids[ix->cur], ix->cap, static_cast<const int64_t*>(ix->lo.p),
+  rc = index_join(nq, ix->nb, nruns, ix->ids[ix->cur], ix->cap, static_cast<const int64_t*>(ix->lo.p),
                   static_cast<const int*>(ix->cnt.p), static_cast<const int*>(ix->raw_count.p),
                   static_cast<const int64_t*>(ix->raw_off.p), static_cast<const int64_t*>(ix->ws_off.p), d_ws,
                   ws_total, static_cast<int64_t*>(ix->out_ids.p), static_cast<int*>(ix->out_coll.p),
@@ -1271,7 +1296,7 @@ extern "C" int lshx_index_get_buckets(lshx_index* ix, const int32_t* band_ids, c
     for (int64_t t = 0; t < m; ++t) offsets[t + 1] = 0;
     return LSHX_OK;
   }
-  int rc = index_make_sorted(ix);
+  int rc = index_make_sorted(ix, /*force_full=*/true);   // a bucket is read as ONE id-ascending range
   if (rc != LSHX_OK) return rc;
   // scratch in the query buffers (their contents die with last_nq below)
   ix->last_nq = -1;
@@ -1339,7 +1364,7 @@ extern "C" int lshx_index_export(lshx_index* ix, uint8_t* keys_out, int64_t* ids
   LSHX_REQUIRE(capacity >= ix->n, "buffers hold %lld entries per band, the index has %lld", (long long)capacity,
                (long long)ix->n);
   if (ix->n == 0) return LSHX_OK;
-  int rc = index_make_sorted(ix);
+  int rc = index_make_sorted(ix, /*force_full=*/true);
   if (rc != LSHX_OK) return rc;
   const int64_t n = ix->n;
   std::vector<uint64_t> k((size_t)ix->nb * n);
@@ -1412,7 +1437,7 @@ extern "C" int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const fl
                          zero_flag ? d_res + off_flag : nullptr, st);
   if (rc != LSHX_OK) return rc;
   rc = index_query_small(static_cast<const uint8_t*>(ix->q_sig.p), nq, ix->nb, ix->bpb, ix->keys[ix->cur],
-                         ix->ids[ix->cur], ix->n, ix->cap, capacity, 0, reinterpret_cast<int64_t*>(d_res),
+                         ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, capacity, 0, reinterpret_cast<int64_t*>(d_res),
                          reinterpret_cast<int*>(d_res + off_coll), reinterpret_cast<int*>(d_res + off_count), nullptr,
                          nullptr, st);
   if (rc != LSHX_OK) return rc;
@@ -1499,7 +1524,7 @@ extern "C" int lshx_index_query_rerank_vectors(lshx_index* ix, lshx_hasher* h, l
                          zero_flag ? d_res + off_flag : nullptr, st);
   if (rc != LSHX_OK) return rc;
   rc = index_query_small(static_cast<const uint8_t*>(ix->q_sig.p), nq, ix->nb, ix->bpb, ix->keys[ix->cur],
-                         ix->ids[ix->cur], ix->n, ix->cap, RC, RC, static_cast<int64_t*>(ix->out_ids.p), nullptr,
+                         ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, RC, RC, static_cast<int64_t*>(ix->out_ids.p), nullptr,
                          reinterpret_cast<int*>(d_res + off_cand), static_cast<int*>(ix->uniq.p),
                          static_cast<int64_t*>(ix->raw_off.p), st);
   if (rc != LSHX_OK) return rc;

@@ -126,18 +126,18 @@ int index_bucket_lookup(const int* d_band_ids, const uint64_t* d_want, int64_t m
 int index_bucket_gather(const int* d_band_ids, const int64_t* d_lo, const int64_t* d_off, int64_t m, const int64_t* ids,
                         int64_t cap, int64_t* d_out, cudaStream_t st);
 size_t index_sort_hist_entries(int64_t n, int nb);
-int index_sort(uint64_t* keys[2], int64_t* ids[2], int* cur, int64_t n, int64_t cap, int nb, int key_bytes,
-               int id_bytes, unsigned* d_hist, size_t hist_entries, cudaStream_t st);
+int index_sort(uint64_t* keys[2], int64_t* ids[2], int* cur, int64_t first, int64_t n, int64_t cap, int nb,
+               int key_bytes, int id_bytes, unsigned* d_hist, size_t hist_entries, cudaStream_t st);
 int index_tombstone(int64_t* ids, int64_t n, int64_t cap, int nb, const int64_t* d_gone_sorted, int64_t ngone,
                     cudaStream_t st);
-int index_lookup_scan(const uint8_t* d_sig, int64_t nq, int nb, int bpb, const uint64_t* keys, int64_t n, int64_t cap,
-                      int64_t* d_lo, int* d_cnt, int* d_raw_count, int64_t* d_raw_off, int64_t* d_ws_off,
+int index_lookup_scan(const uint8_t* d_sig, int64_t nq, int nb, int bpb, const uint64_t* keys, int64_t main_n, int64_t n,
+                      int64_t cap, int64_t* d_lo, int* d_cnt, int* d_raw_count, int64_t* d_raw_off, int64_t* d_ws_off,
                       int64_t* d_meta, cudaStream_t st);
 unsigned index_join_smem_cap();
-int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint64_t* keys, const int64_t* ids, int64_t n,
-                      int64_t cap, int out_cap, int raw_cap, int64_t* out_ids, int* out_coll, int* out_count,
+int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint64_t* keys, const int64_t* ids,
+                      int64_t main_n, int64_t n, int64_t cap, int out_cap, int raw_cap, int64_t* out_ids, int* out_coll, int* out_count,
                       int* out_count_clamped, int64_t* out_offs, cudaStream_t st);
-int index_join(int64_t nq, int nb, const int64_t* ids, int64_t cap, const int64_t* d_lo, const int* d_cnt,
+int index_join(int64_t nq, int nb, int nruns, const int64_t* ids, int64_t cap, const int64_t* d_lo, const int* d_cnt,
                const int* d_raw_count, const int64_t* d_raw_off, const int64_t* d_ws_off, uint64_t* d_ws,
                int64_t ws_total, int64_t* d_out_ids, int* d_out_coll, int* d_uniq, cudaStream_t st);
 int index_topk(const int64_t* d_cand, const int64_t* d_raw_off, const int* d_uniq, int64_t nq, int k, int64_t* d_out,

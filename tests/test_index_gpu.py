@@ -281,3 +281,78 @@ def test_latency_path_equals_hash_plus_batched_join(dim, nb, r):
         ix.query_vectors(h, Q[:1], 8)
     ix.close()
     h.close()
+
+
+def test_small_adds_go_to_a_delta_run_with_identical_results():
+    """Above 32 768 entries a small add is sorted on its own (delta run) instead of re-sorting the segment; queries
+    search both runs.  Same lists as the dict-of-sets model through adds, duplicates of main-run entries, removals
+    that hit both runs, re-adds, the latency path, bucket reads (which fold the runs) and the fold by growth."""
+    import lshrs_b200
+    from lshrs_b200.storage.device import DeviceIndex
+
+    rng = np.random.default_rng(77)
+    dim, nb, r, n0 = 64, 12, 10, 40_000
+    centers = rng.standard_normal((n0 // 8, dim)).astype(np.float32)
+
+    def vectors(n):
+        return (centers[rng.integers(0, centers.shape[0], n)] + 0.25 * rng.standard_normal((n, dim))).astype(np.float32)
+
+    h = lshrs_b200.LSHHasher(nb, r, dim, seed=3, device=0)
+    ix, model = DeviceIndex(nb, h.bytes_per_band, device=0), Model(nb)
+    X0 = vectors(n0)
+    S0 = h.hash_batch_packed(X0)
+    ids0 = rng.permutation(n0).astype(np.int64) * 5 + 2
+    ix.add(S0, ids0)
+    model.add(S0, ids0)
+    Qv = (X0[rng.integers(0, n0, 200)] + 0.05 * rng.standard_normal((200, dim))).astype(np.float32)
+    Q = h.hash_batch_packed(Qv)
+
+    def check(tag):
+        want = model.query(Q)
+        assert _lists(ix, Q) == want, tag
+        ids, coll, counts, _ = ix.query_vectors(h, Qv[:16], 64)            # the latency path sees both runs too
+        for q in range(16):
+            if counts[q] >= 0:
+                take = min(64, len(want[q]))
+                assert counts[q] == len(want[q]) and \
+                    list(zip(ids[q, :take].tolist(), coll[q, :take].tolist())) == want[q][:take], (tag, q)
+
+    check("main run only")
+    next_id = 10_000_000
+    for rnd, m in enumerate((500, 700, 1, 2000)):
+        Xn = vectors(m)
+        Sn = h.hash_batch_packed(Xn)
+        idn = np.arange(next_id, next_id + m, dtype=np.int64)
+        next_id += m
+        ix.add(Sn, idn)
+        model.add(Sn, idn)
+        check(f"delta round {rnd}")
+        if rnd == 0:
+            # entries of the MAIN run again (same ids, same keys): SET semantics across the runs
+            ix.add(S0[:300], ids0[:300])
+            model.add(S0[:300], ids0[:300])
+            check("duplicates of main-run entries in the delta run")
+        if rnd == 1:
+            gone = np.concatenate([ids0[100:400], idn[:50]])               # ids in the main run, in both, in the delta
+            ix.remove(gone)
+            model.remove(gone)
+            check("removal across both runs")
+            ix.add(S0[150:250], ids0[150:250])                             # removed ids come back (delta run)
+            model.add(S0[150:250], ids0[150:250])
+            check("re-add after removal")
+        if rnd == 2:
+            # a bucket read folds the runs (one id-ascending range per bucket) -- and must agree with the model
+            keys = Q[:5].reshape(5 * nb, -1)
+            bands = np.tile(np.arange(nb, dtype=np.int32), 5)
+            offs, flat = ix.get_buckets(bands, keys)
+            for t in range(5 * nb):
+                assert set(flat[offs[t]:offs[t + 1]].tolist()) == model.b[int(bands[t])].get(keys[t].tobytes(), set())
+            check("after the fold by a bucket read")
+    Xn = vectors(15_000)                                                   # more than a quarter of the main run: fold
+    Sn = h.hash_batch_packed(Xn)
+    idn = np.arange(next_id, next_id + 15_000, dtype=np.int64)
+    ix.add(Sn, idn)
+    model.add(Sn, idn)
+    check("fold by growth")
+    ix.close()
+    h.close()
