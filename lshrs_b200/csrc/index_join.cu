@@ -237,6 +237,12 @@ __global__ void index_lookup_kernel(const uint8_t* __restrict__ sig, int64_t nq,
   }
 }
 
+__device__ __forceinline__ unsigned pow2_at_least(unsigned v) {
+  unsigned p = 2;
+  while (p < v) p <<= 1;
+  return p;
+}
+
 // exclusive scans of raw_count (candidate slots) and of pow2(raw_count) (sort workspace slots);
 // meta = {total raw, max raw, total workspace}
 __global__ void __launch_bounds__(1024)
