@@ -215,6 +215,31 @@ __device__ __forceinline__ void search_run(const uint64_t* __restrict__ k, int64
   cnt_out = lo2 - lo;
 }
 
+// The same search by a whole warp (latency path: one query, nothing else in flight to hide a 20-step chain of
+// dependent loads behind): 32 probes per step split the range 33 ways -- 4 steps for a million entries -- and a
+// bucket shorter than 32 entries ends in one more.  LE = false: first entry >= key; true: first entry > key.
+template <bool LE>
+__device__ __forceinline__ int64_t warp_bound(const uint64_t* __restrict__ k, int64_t lo, int64_t hi, uint64_t key,
+                                              int lane) {
+  while (hi > lo) {
+    const int64_t len = hi - lo;
+    const int64_t p = (len <= 32) ? lo + lane : lo + (len * (lane + 1)) / 33;   // ascending in the lane, p < hi
+    bool before = false;
+    if (p < hi) {
+      const uint64_t v = __ldg(k + p);
+      before = LE ? (v <= key) : (v < key);
+    }
+    const int t = __popc(__ballot_sync(0xffffffffu, before));    // sorted: the first t probes are "before"
+    if (len <= 32) return lo + t;
+    const int64_t p_prev = lo + (len * t) / 33;                  // probe t - 1 (for t > 0)
+    const int64_t p_next = lo + (len * (t + 1)) / 33;            // probe t     (for t < 32)
+    const int64_t nlo = t > 0 ? p_prev + 1 : lo;
+    hi = t < 32 ? p_next : hi;
+    lo = nlo;
+  }
+  return lo;
+}
+
 __global__ void index_lookup_kernel(const uint8_t* __restrict__ sig, int64_t nq, int nb, int bpb,
                                     const uint64_t* __restrict__ keys, int64_t main_n, int64_t n, int64_t cap,
                                     int64_t* __restrict__ lo_out, int* __restrict__ cnt_out,
@@ -413,15 +438,23 @@ index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const
   const int tid = threadIdx.x;
   const int64_t q = blockIdx.x;
   const int nv = nb * (n > main_n ? 2 : 1);
-  for (int v = tid; v < nv; v += JN_THREADS) {
-    const int b = v % nb, run = v / nb;
+  for (int v = tid >> 5; v < nv; v += JN_THREADS / 32) {       // one warp per (run, band) slot
+    const int b = v % nb, run = v / nb, lane = tid & 31;
     const uint8_t* src = sig + (q * nb + b) * (int64_t)bpb;
     uint64_t key = 0;
     for (int j = 0; j < bpb; ++j) key |= (uint64_t)src[j] << (8 * j);
-    int64_t lo, c;
-    search_run(keys + b * cap, run ? main_n : 0, run ? n : main_n, key, lo, c);
-    s_lo[v] = lo;
-    s_cnt[v] = (int)(c > 0x7fffffff ? 0x7fffffff : c);
+    const uint64_t* k = keys + b * cap;
+    const int64_t end = run ? n : main_n;
+    const int64_t lo = warp_bound<false>(k, run ? main_n : 0, end, key, lane);
+    // most buckets are short: one probe of the 32 entries behind lo usually finds the end
+    const int64_t near = (end - lo < 32) ? end : lo + 32;
+    int64_t up = warp_bound<true>(k, lo, near, key, lane);
+    if (up == near && near < end) up = warp_bound<true>(k, near, end, key, lane);
+    if (lane == 0) {
+      const int64_t c = up - lo;
+      s_lo[v] = lo;
+      s_cnt[v] = (int)(c > 0x7fffffff ? 0x7fffffff : c);
+    }
   }
   __syncthreads();
   if (tid == 0) {
