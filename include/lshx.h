@@ -322,8 +322,10 @@ int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64_t nq, int 
 /*
  * Latency path of LSHRS.query / get_top_k / get_above_p (reference lshrs/core/main.py:
  * 524-658 hash ONE vector per call and read num_bands buckets): hash nq <= 32 host
- * vectors with `h` (the FP32 small-batch kernel of lshx_hash_batch), look their band
- * keys up and join, all in two launches and one synchronisation.  Query i: its first
+ * vectors with `h` (the FP32 small-batch arithmetic of lshx_hash_batch), look their band
+ * keys up and join, all in ONE launch and one synchronisation: one CTA per signature
+ * byte hashes, reading the vectors from pinned memory in place, and the CTA that
+ * finishes last runs the lookup / join and stores the lists into mapped memory.  Query i: its first
  * min(out_count[i], capacity) candidates, ordered by (-collisions, id), in
  * out_ids / out_collisions[i * capacity ..]; out_count[i] = the full list length, or
  * -1 when the query matches more than 4096 bucket entries (take lshx_index_query +
@@ -337,7 +339,7 @@ int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const float* X, int
  * The same latency path with the rerank fused in (LSHRS.query(top_p=...) /
  * get_above_p, main.py:625-658, when the indexed vectors are resident in HBM):
  * hash -> lookup/join -> cosine rerank against corpus_device (candidate id = row)
- * -> ids, four launches and one synchronisation, results stored straight into
+ * -> ids, three launches and one synchronisation, results stored straight into
  * mapped pinned memory.  Query i keeps min(k, max(1, ceil(n_i * p))) of its n_i
  * candidates (k <= 0: no k; p <= 0: no p), at most out_stride (<= 1024):
  * out_ids / out_score[i * out_stride ..], out_count[i].  out_candidates[i] = n_i, or

@@ -14,6 +14,7 @@
 // BK = 16, double-buffered shared memory with register prefetch.
 
 #include "lshx_common.cuh"
+#include "hash_small.cuh"
 
 namespace lshx {
 namespace {
@@ -204,48 +205,12 @@ hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* _
 // A handful of rows cannot fill a 128-row tile and the call is pure latency, so: one CTA per OUTPUT
 // BYTE, one warp per column (= signature bit), the rows in shared memory, fp32 FMA + shuffle
 // reduction, `> 0`, eight warps -> one byte per row.  Same arithmetic class as the tiled kernel.
-constexpr int SMALL_THREADS = 256;
-
 __global__ void __launch_bounds__(SMALL_THREADS)
 hash_small_kernel(const float* __restrict__ X, int n, int dim, const float* __restrict__ Rp,
                   uint8_t* __restrict__ out, int sig_bytes, uint8_t* __restrict__ zero_flag) {
   extern __shared__ float xs[];          // [n][dim]
   __shared__ unsigned int sbits[32];     // one byte per row, built with atomicOr
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n * dim; i += SMALL_THREADS) xs[i] = X[i];
-  if (tid < 32) sbits[tid] = 0u;
-  __syncthreads();
-
-  const float* rrow = Rp + (int64_t)(blockIdx.x * 8 + warp) * dim;   // column of this warp
-  for (int i0 = 0; i0 < n; i0 += 8) {
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = lane; k < dim; k += 32) {
-      const float rv = __ldg(rrow + k);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (i0 + j < n) acc[j] = fmaf(rv, xs[(i0 + j) * dim + k], acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = acc[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && i0 + j < n && v > 0.f) atomicOr(&sbits[i0 + j], 1u << warp);
-    }
-  }
-  __syncthreads();
-  if (tid < n) out[(int64_t)tid * sig_bytes + blockIdx.x] = (uint8_t)sbits[tid];
-
-  if (zero_flag != nullptr && blockIdx.x == 0) {
-    for (int i = warp; i < n; i += SMALL_THREADS / 32) {
-      bool viol = false;
-      for (int k = lane; k < dim; k += 32) viol |= !(fabsf(xs[i * dim + k]) <= 1e-8f);
-      const unsigned any = __ballot_sync(0xffffffffu, viol);
-      if (lane == 0) zero_flag[i] = any ? 0 : 1;
-    }
-  }
+  hash_small_body(X, n, dim, Rp, out, sig_bytes, zero_flag, xs, sbits);
 }
 
 }  // namespace

@@ -22,6 +22,7 @@
 // storage path's.  HBM / L2-latency bound; nothing here belongs on tensor cores.
 
 #include "lshx_common.cuh"
+#include "hash_small.cuh"
 
 namespace lshx {
 namespace {
@@ -424,25 +425,22 @@ index_join_kernel(JoinArgs a) {
 // host memory (no copy call), count = -1 when the raw candidates do not fit the shared-memory sort (the caller
 // then takes the batched path).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(JN_THREADS)
-index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const uint64_t* __restrict__ keys,
+__device__ __forceinline__ void query_small_body(uint64_t* sm, const int64_t q, const uint8_t* sig, int nb, int bpb, const uint64_t* __restrict__ keys,
                          const int64_t* __restrict__ ids, int64_t main_n, int64_t n, int64_t cap, int out_cap,
                          int raw_cap, int64_t* __restrict__ out_ids, int* __restrict__ out_coll,
                          int* __restrict__ out_count, int* __restrict__ out_count_clamped,
                          int64_t* __restrict__ out_offs) {
-  extern __shared__ __align__(16) uint64_t sm[];
   __shared__ int64_t s_lo[512];
   __shared__ int s_cnt[512];
   __shared__ int band_off[512];
   __shared__ int heads, n_raw_s;
   const int tid = threadIdx.x;
-  const int64_t q = blockIdx.x;
   const int nv = nb * (n > main_n ? 2 : 1);
   for (int v = tid >> 5; v < nv; v += JN_THREADS / 32) {       // one warp per (run, band) slot
     const int b = v % nb, run = v / nb, lane = tid & 31;
     const uint8_t* src = sig + (q * nb + b) * (int64_t)bpb;
     uint64_t key = 0;
-    for (int j = 0; j < bpb; ++j) key |= (uint64_t)src[j] << (8 * j);
+    for (int j = 0; j < bpb; ++j) key |= (uint64_t)__ldcg(src + j) << (8 * j);
     const uint64_t* k = keys + b * cap;
     const int64_t end = run ? n : main_n;
     const int64_t lo = warp_bound<false>(k, run ? main_n : 0, end, key, lane);
@@ -513,6 +511,51 @@ index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const
   if (tid == 0) {
     out_count[q] = u;
     if (out_count_clamped) out_count_clamped[q] = take;
+  }
+}
+
+
+__global__ void __launch_bounds__(JN_THREADS)
+index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const uint64_t* __restrict__ keys,
+                         const int64_t* __restrict__ ids, int64_t main_n, int64_t n, int64_t cap, int out_cap,
+                         int raw_cap, int64_t* __restrict__ out_ids, int* __restrict__ out_coll,
+                         int* __restrict__ out_count, int* __restrict__ out_count_clamped,
+                         int64_t* __restrict__ out_offs) {
+  extern __shared__ __align__(16) uint64_t sm[];
+  query_small_body(sm, blockIdx.x, sig, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap, out_ids, out_coll, out_count,
+                   out_count_clamped, out_offs);
+}
+
+// Hash AND query in one launch: one CTA per signature byte hashes the nq vectors (hash_small_body; X may be mapped
+// pinned host memory, so no copy precedes the launch); the CTA that finishes last -- a ticket counter, no CTA
+// ever waits for another -- reads the finished signatures and runs the lookup / join / emit of every query.
+static_assert(SMALL_THREADS == JN_THREADS, "the fused latency kernel runs both bodies with one block size");
+__global__ void __launch_bounds__(JN_THREADS)
+index_hash_query_small_kernel(const float* __restrict__ X, int nq, int dim, const float* __restrict__ Rp,
+                              uint8_t* __restrict__ sig, int sig_bytes, uint8_t* __restrict__ zero_flag,
+                              unsigned* __restrict__ ticket, int nb, int bpb, const uint64_t* __restrict__ keys,
+                              const int64_t* __restrict__ ids, int64_t main_n, int64_t n, int64_t cap, int out_cap,
+                              int raw_cap, int64_t* __restrict__ out_ids, int* __restrict__ out_coll,
+                              int* __restrict__ out_count, int* __restrict__ out_count_clamped,
+                              int64_t* __restrict__ out_offs) {
+  extern __shared__ __align__(16) uint64_t sm[];
+  __shared__ unsigned int sbits[32];
+  __shared__ int last;
+  hash_small_body(X, nq, dim, Rp, sig, sig_bytes, zero_flag, reinterpret_cast<float*>(sm), sbits);
+  __threadfence();                      // this CTA's signature bytes are visible before its ticket is
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    last = (t == gridDim.x - 1) ? 1 : 0;
+    if (last) *ticket = 0u;             // ready for the next launch (launches on one stream do not overlap)
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  for (int q = 0; q < nq; ++q) {
+    query_small_body(sm, q, sig, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap, out_ids, out_coll, out_count,
+                     out_count_clamped, out_offs);
+    __syncthreads();
   }
 }
 
@@ -697,6 +740,24 @@ int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint6
   index_query_small_kernel<<<(unsigned)nq, JN_THREADS, smem, st>>>(d_sig, nb, bpb, keys, ids, main_n, n, cap, out_cap,
                                                                   raw_cap, out_ids, out_coll, out_count, out_count_clamped,
                                                                   out_offs);
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
+}
+
+int index_hash_query_small(const float* X, int nq, int dim, const float* d_Rp, uint8_t* d_sig, int sig_bytes,
+                           uint8_t* zero_flag, unsigned* d_ticket, int nb, int bpb, const uint64_t* keys,
+                           const int64_t* ids, int64_t main_n, int64_t n, int64_t cap, int out_cap, int raw_cap,
+                           int64_t* out_ids, int* out_coll, int* out_count, int* out_count_clamped, int64_t* out_offs,
+                           cudaStream_t st) {
+  if (nq <= 0) return LSHX_OK;
+  if (raw_cap <= 0 || raw_cap > (int)JN_SMEM_CAP) raw_cap = (int)JN_SMEM_CAP;
+  const size_t smem = 2 * (size_t)JN_SMEM_CAP * sizeof(uint64_t);     // >= nq * dim floats (hash_small_max_rows)
+  LSHX_REQUIRE((size_t)nq * dim * sizeof(float) <= smem, "too many rows for the fused latency kernel");
+  LSHX_CUDA(cudaFuncSetAttribute(index_hash_query_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  index_hash_query_small_kernel<<<(unsigned)sig_bytes, JN_THREADS, smem, st>>>(
+      X, nq, dim, d_Rp, d_sig, sig_bytes, zero_flag, d_ticket, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap,
+      out_ids, out_coll, out_count, out_count_clamped, out_offs);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;

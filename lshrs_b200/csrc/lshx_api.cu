@@ -105,7 +105,7 @@ struct lshx_hasher {
   DevBuf raw_stage[2];         // typed host batches (fp16 / int8 / uint8) before the on-device cast
   // small-batch path (per-vector calls): pinned, device-mapped staging for up to small_rows rows
   int small_rows = 0;
-  float* pin_x = nullptr;      // host, pinned
+  float* pin_x = nullptr;      // host, pinned + mapped (the fused latency kernel of the band index reads it in place)
   uint8_t* pin_out = nullptr;  // host, pinned + mapped: the kernel stores signatures / flags into it
   float* d_small_x = nullptr;
   // pageable host batches: pinned bounce buffers filled by several CPU threads (see hash_pageable)
@@ -205,7 +205,7 @@ extern "C" int lshx_hasher_create(int device, int dim, int num_bands, int rows_p
   if (h->small_rows > 0) {
     const size_t xb = (size_t)h->small_rows * dim * sizeof(float);
     const size_t ob = (size_t)h->small_rows * (s.sig_bytes + 1);
-    if (cudaHostAlloc(&h->pin_x, xb, cudaHostAllocDefault) != cudaSuccess ||
+    if (cudaHostAlloc(&h->pin_x, xb, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
         cudaHostAlloc(&h->pin_out, ob, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
         cudaMalloc(&h->d_small_x, xb) != cudaSuccess) {
       (void)cudaGetLastError();
@@ -991,8 +991,10 @@ struct lshx_index {
   DevBuf q_sig, lo, cnt, raw_count, raw_off, ws_off, meta, ws, out_ids, out_coll, uniq, topk_ids, topk_cnt;
   DevBuf rr_pos, rr_score, rr_count, rr_zero, rr_ids, rr_q;
   int64_t last_nq = -1, last_total = 0, last_max = 0;
-  // latency path (lshx_index_query_vectors): pinned + mapped result block the kernel stores into
+  // latency path (lshx_index_query_vectors): pinned + mapped result block the kernel stores into, and the
+  // ticket counter by which the fused hash + query kernel finds its last CTA
   uint8_t* pin_res = nullptr;
+  unsigned* d_ticket = nullptr;
   std::mutex mu;
 };
 
@@ -1052,7 +1054,9 @@ extern "C" int lshx_index_create(int device, int num_bands, int bytes_per_band, 
   if (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&ix->d_max_id), 8) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&ix->d_bad), 4) != cudaSuccess ||
-      cudaMemset(ix->d_max_id, 0, 8) != cudaSuccess || cudaMemset(ix->d_bad, 0, 4) != cudaSuccess) {
+      cudaMalloc(reinterpret_cast<void**>(&ix->d_ticket), 4) != cudaSuccess ||
+      cudaMemset(ix->d_max_id, 0, 8) != cudaSuccess || cudaMemset(ix->d_bad, 0, 4) != cudaSuccess ||
+      cudaMemset(ix->d_ticket, 0, 4) != cudaSuccess) {
     (void)cudaGetLastError();
     set_error("cannot create the band index on device %d", device);
     lshx_index_destroy(ix);
@@ -1073,6 +1077,7 @@ extern "C" int lshx_index_destroy(lshx_index* ix) {
     }
     if (ix->d_max_id) cudaFree(ix->d_max_id);
     if (ix->d_bad) cudaFree(ix->d_bad);
+    if (ix->d_ticket) cudaFree(ix->d_ticket);
     if (ix->pin_res) cudaFreeHost(ix->pin_res);
     for (DevBuf* b : {&ix->hist, &ix->stage_sig, &ix->stage_ids, &ix->gone, &ix->q_sig, &ix->lo, &ix->cnt,
                       &ix->raw_count, &ix->raw_off, &ix->ws_off, &ix->meta, &ix->ws, &ix->out_ids, &ix->out_coll,
@@ -1431,15 +1436,14 @@ extern "C" int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const fl
   if ((rc = ix->q_sig.reserve((size_t)IDX_SMALL_MAX_Q * s.sig_bytes)) != LSHX_OK) return rc;
   const size_t xb = (size_t)nq * s.dim * sizeof(float);
   std::memcpy(h->pin_x, X, xb);
-  LSHX_CUDA(cudaMemcpyAsync(h->d_small_x, h->pin_x, xb, cudaMemcpyHostToDevice, st));
+  float* d_x_map = nullptr;                  // the kernel reads the vectors from the pinned block in place
+  LSHX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_x_map), h->pin_x, 0));
   h->last_kernel = LSHX_KERNEL_SMALL;
-  rc = launch_hash_small(s, h->d_small_x, nq, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p),
-                         zero_flag ? d_res + off_flag : nullptr, st);
-  if (rc != LSHX_OK) return rc;
-  rc = index_query_small(static_cast<const uint8_t*>(ix->q_sig.p), nq, ix->nb, ix->bpb, ix->keys[ix->cur],
-                         ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, capacity, 0, reinterpret_cast<int64_t*>(d_res),
-                         reinterpret_cast<int*>(d_res + off_coll), reinterpret_cast<int*>(d_res + off_count), nullptr,
-                         nullptr, st);
+  rc = index_hash_query_small(d_x_map, nq, s.dim, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p), s.sig_bytes,
+                              zero_flag ? d_res + off_flag : nullptr, ix->d_ticket, ix->nb, ix->bpb,
+                              ix->keys[ix->cur], ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, capacity, 0,
+                              reinterpret_cast<int64_t*>(d_res), reinterpret_cast<int*>(d_res + off_coll),
+                              reinterpret_cast<int*>(d_res + off_count), nullptr, nullptr, st);
   if (rc != LSHX_OK) return rc;
   LSHX_CUDA(cudaStreamSynchronize(st));
   for (int q = 0; q < nq; ++q) {
@@ -1518,18 +1522,17 @@ extern "C" int lshx_index_query_rerank_vectors(lshx_index* ix, lshx_hasher* h, l
   if ((rc = ix->rr_pos.reserve((size_t)IDX_SMALL_MAX_Q * RC * 4)) != LSHX_OK) return rc;
   const size_t xb = (size_t)nq * s.dim * sizeof(float);
   std::memcpy(h->pin_x, X, xb);
-  LSHX_CUDA(cudaMemcpyAsync(h->d_small_x, h->pin_x, xb, cudaMemcpyHostToDevice, st));
+  float* d_x_map = nullptr;
+  LSHX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_x_map), h->pin_x, 0));
   h->last_kernel = LSHX_KERNEL_SMALL;
-  rc = launch_hash_small(s, h->d_small_x, nq, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p),
-                         zero_flag ? d_res + off_flag : nullptr, st);
-  if (rc != LSHX_OK) return rc;
-  rc = index_query_small(static_cast<const uint8_t*>(ix->q_sig.p), nq, ix->nb, ix->bpb, ix->keys[ix->cur],
-                         ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, RC, RC, static_cast<int64_t*>(ix->out_ids.p), nullptr,
-                         reinterpret_cast<int*>(d_res + off_cand), static_cast<int*>(ix->uniq.p),
-                         static_cast<int64_t*>(ix->raw_off.p), st);
+  rc = index_hash_query_small(d_x_map, nq, s.dim, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p), s.sig_bytes,
+                              zero_flag ? d_res + off_flag : nullptr, ix->d_ticket, ix->nb, ix->bpb,
+                              ix->keys[ix->cur], ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, RC, RC,
+                              static_cast<int64_t*>(ix->out_ids.p), nullptr, reinterpret_cast<int*>(d_res + off_cand),
+                              static_cast<int*>(ix->uniq.p), static_cast<int64_t*>(ix->raw_off.p), st);
   if (rc != LSHX_OK) return rc;
   RerankArgs a{};
-  a.Q = h->d_small_x;                       // the query vectors are already in HBM
+  a.Q = d_x_map;                            // the rerank kernel stages each query in shared memory once
   a.nq = nq;
   a.V = corpus_device;
   a.n_vectors = n_vectors;

@@ -140,6 +140,12 @@ int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint6
 int index_join(int64_t nq, int nb, int nruns, const int64_t* ids, int64_t cap, const int64_t* d_lo, const int* d_cnt,
                const int* d_raw_count, const int64_t* d_raw_off, const int64_t* d_ws_off, uint64_t* d_ws,
                int64_t ws_total, int64_t* d_out_ids, int* d_out_coll, int* d_uniq, cudaStream_t st);
+// hash (small-batch FP32 kernel body) + lookup / join / emit of nq <= hash_small_max_rows vectors in ONE launch
+int index_hash_query_small(const float* X, int nq, int dim, const float* d_Rp, uint8_t* d_sig, int sig_bytes,
+                           uint8_t* zero_flag, unsigned* d_ticket, int nb, int bpb, const uint64_t* keys,
+                           const int64_t* ids, int64_t main_n, int64_t n, int64_t cap, int out_cap, int raw_cap,
+                           int64_t* out_ids, int* out_coll, int* out_count, int* out_count_clamped, int64_t* out_offs,
+                           cudaStream_t st);
 int index_topk(const int64_t* d_cand, const int64_t* d_raw_off, const int* d_uniq, int64_t nq, int k, int64_t* d_out,
                int* d_out_count, cudaStream_t st);
 int index_pos_to_id(const int64_t* d_cand, const int64_t* d_raw_off, const int32_t* d_pos, const int32_t* d_count,

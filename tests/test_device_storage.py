@@ -278,7 +278,7 @@ def test_single_queries_rerank_against_a_resident_corpus():
 
     before = _native.launch_count()
     assert res.get_above_p(Q[3], p=0.3)
-    assert _native.launch_count() - before == 4          # hash, lookup/join, rerank, id gather: the fused path
+    assert _native.launch_count() - before == 3          # hash + lookup/join, rerank, id gather: the fused path
     want = host.query_batch(Q, top_k=4, top_p=0.5)
     for lsh in (res, mem):
         got = lsh.query_batch(Q, top_k=4, top_p=0.5)                 # corpus= defaults to the instance's
