@@ -208,7 +208,7 @@ hash_ffma_kernel(const float* __restrict__ X, int64_t n, int dim, const float* _
 __global__ void __launch_bounds__(SMALL_THREADS)
 hash_small_kernel(const float* __restrict__ X, int n, int dim, const float* __restrict__ Rp,
                   uint8_t* __restrict__ out, int sig_bytes, uint8_t* __restrict__ zero_flag) {
-  extern __shared__ float xs[];          // [n][dim]
+  extern __shared__ __align__(16) float xs[];   // [n][dim]
   __shared__ unsigned int sbits[32];     // one byte per row, built with atomicOr
   hash_small_body(X, n, dim, Rp, out, sig_bytes, zero_flag, xs, sbits);
 }

@@ -14,7 +14,31 @@ __device__ __forceinline__ void hash_small_body(const float* __restrict__ X, int
                                                 const float* __restrict__ Rp, uint8_t* __restrict__ out, int sig_bytes,
                                                 uint8_t* __restrict__ zero_flag, float* xs, unsigned int* sbits) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n * dim; i += SMALL_THREADS) xs[i] = X[i];
+  // the rows -> shared memory.  This is a latency path (one CTA per output byte, nothing else in flight), so
+  // loads are issued in batches before anything consumes them: 16-byte loads when the layout allows (one round
+  // trip for a 768-float row, which matters when X is pinned HOST memory read over PCIe), else four in flight.
+  const int total = n * dim;
+  if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    const float4* X4 = reinterpret_cast<const float4*>(X);
+    float4* xs4 = reinterpret_cast<float4*>(xs);
+    for (int i = tid; i < (total >> 2); i += 2 * SMALL_THREADS) {
+      const int i2 = i + SMALL_THREADS;
+      const float4 a = X4[i];
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i2 < (total >> 2)) b = X4[i2];
+      xs4[i] = a;
+      if (i2 < (total >> 2)) xs4[i2] = b;
+    }
+  } else {
+    for (int i = tid; i < total; i += 4 * SMALL_THREADS) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (i + u * SMALL_THREADS < total) ? X[i + u * SMALL_THREADS] : 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + u * SMALL_THREADS < total) xs[i + u * SMALL_THREADS] = v[u];
+    }
+  }
   if (tid < 32) sbits[tid] = 0u;
   __syncthreads();
 
@@ -23,7 +47,22 @@ __device__ __forceinline__ void hash_small_body(const float* __restrict__ X, int
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    for (int k = lane; k < dim; k += 32) {
+    int k = lane;
+    // eight strided elements of the projection row per batch, loaded before the first FMA needs one (a
+    // dependent chain of 24 L2 round trips was most of this kernel's time); the order of the FMAs -- k
+    // ascending per lane -- is unchanged, so the bits are too
+    for (; k + 7 * 32 < dim; k += 8 * 32) {
+      float rv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) rv[u] = __ldg(rrow + k + u * 32);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (i0 + j < n) acc[j] = fmaf(rv[u], xs[(i0 + j) * dim + k + u * 32], acc[j]);
+      }
+    }
+    for (; k < dim; k += 32) {
       const float rv = __ldg(rrow + k);
 #pragma unroll
       for (int j = 0; j < 8; ++j)
