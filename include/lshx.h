@@ -352,6 +352,14 @@ int lshx_index_query_rerank_vectors(lshx_index* ix, lshx_hasher* h, lshx_reranke
                                     int out_stride, int64_t* out_ids, float* out_score, int32_t* out_count,
                                     int32_t* out_zero, int32_t* out_candidates, uint8_t* zero_flag);
 /*
+ * DIAGNOSTICS (no reference counterpart, not on any product path): with enable != 0 the
+ * fused latency kernel of lshx_index_query_vectors records %globaltimer stamps (ns) of its
+ * phases for query 0 -- last CTA entered, hashed, ticket taken, bands searched, candidates
+ * gathered, first sort, counted + second sort, list stored -- and the number of bucket
+ * entries matched; stamps_out (9 words, may be NULL) receives the last launch's.
+ */
+int lshx_index_debug_timeline(lshx_index* ix, int enable, uint64_t* stamps_out);
+/*
  * RedisStorage.get_bucket (SMEMBERS, reference lshrs/storage/redis.py:264-301) for m
  * buckets at once -- what makes the index usable as the bucket STORE, not only as
  * a mirror: bucket t = (band_ids[t], keys[t * bytes_per_band ..]); its members (live

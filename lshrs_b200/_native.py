@@ -69,6 +69,7 @@ EXPORTED_SYMBOLS = (
     "lshx_index_get_buckets",
     "lshx_index_query_vectors",
     "lshx_index_query_rerank_vectors",
+    "lshx_index_debug_timeline",
     "lshx_index_export",
     "lshx_index_clear",
     "lshx_index_query",
@@ -175,6 +176,8 @@ def _declare(cdll: ctypes.CDLL) -> None:
     cdll.lshx_index_query_rerank_vectors.restype = c_int
     cdll.lshx_index_query_rerank_vectors.argtypes = [vp, vp, vp, vp, c_int, vp, c_int64, c_int, c_double, c_int,
                                                      vp, vp, vp, vp, vp, vp]
+    cdll.lshx_index_debug_timeline.restype = c_int
+    cdll.lshx_index_debug_timeline.argtypes = [vp, c_int, vp]
     cdll.lshx_index_export.restype = c_int
     cdll.lshx_index_export.argtypes = [vp, vp, vp, c_int64, POINTER(c_int64)]
     cdll.lshx_index_remove.restype = c_int

@@ -425,7 +425,14 @@ index_join_kernel(JoinArgs a) {
 // host memory (no copy call), count = -1 when the raw candidates do not fit the shared-memory sort (the caller
 // then takes the batched path).
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void query_small_body(uint64_t* sm, const int64_t q, const uint8_t* sig, int nb, int bpb, const uint64_t* __restrict__ keys,
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// dbg (diagnostics, normally null): nanosecond stamps of the phases of query 0, see lshx_index_debug_timeline
+__device__ __forceinline__ void query_small_body(unsigned long long* dbg, uint64_t* sm, const int64_t q, const uint8_t* sig, int nb, int bpb, const uint64_t* __restrict__ keys,
                          const int64_t* __restrict__ ids, int64_t main_n, int64_t n, int64_t cap, int out_cap,
                          int raw_cap, int64_t* __restrict__ out_ids, int* __restrict__ out_coll,
                          int* __restrict__ out_count, int* __restrict__ out_count_clamped,
@@ -455,6 +462,7 @@ __device__ __forceinline__ void query_small_body(uint64_t* sm, const int64_t q, 
     }
   }
   __syncthreads();
+  if (dbg && tid == 0 && q == 0) dbg[3] = gtime();     // searches done
   if (tid == 0) {
     long long acc = 0;
     for (int v = 0; v < nv; ++v) { band_off[v] = (int)(acc > 0x7fffffff ? 0x7fffffff : acc); acc += s_cnt[v]; }
@@ -485,7 +493,9 @@ __device__ __forceinline__ void query_small_body(uint64_t* sm, const int64_t q, 
   }
   for (unsigned i = n_raw + tid; i < P; i += JN_THREADS) buf[i] = EMPTY;
   __syncthreads();
+  if (dbg && tid == 0 && q == 0) dbg[4] = gtime();     // gathered
   bitonic_asc(buf, P, tid);
+  if (dbg && tid == 0 && q == 0) dbg[5] = gtime();     // first sort
   int mine = 0;
   for (unsigned i = tid; i < P; i += JN_THREADS) {
     const uint64_t v = buf[i];
@@ -501,6 +511,7 @@ __device__ __forceinline__ void query_small_body(uint64_t* sm, const int64_t q, 
   if (mine) atomicAdd(&heads, mine);
   __syncthreads();
   bitonic_asc(buf2, P, tid);
+  if (dbg && tid == 0 && q == 0) dbg[6] = gtime();     // counted + second sort
   const int u = heads;
   const int take = u < out_cap ? u : out_cap;
   for (int i = tid; i < take; i += JN_THREADS) {
@@ -511,6 +522,7 @@ __device__ __forceinline__ void query_small_body(uint64_t* sm, const int64_t q, 
   if (tid == 0) {
     out_count[q] = u;
     if (out_count_clamped) out_count_clamped[q] = take;
+    if (dbg && q == 0) { dbg[7] = gtime(); dbg[8] = (unsigned long long)n_raw; }
   }
 }
 
@@ -522,7 +534,7 @@ index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const
                          int* __restrict__ out_count, int* __restrict__ out_count_clamped,
                          int64_t* __restrict__ out_offs) {
   extern __shared__ __align__(16) uint64_t sm[];
-  query_small_body(sm, blockIdx.x, sig, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap, out_ids, out_coll, out_count,
+  query_small_body(nullptr, sm, blockIdx.x, sig, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap, out_ids, out_coll, out_count,
                    out_count_clamped, out_offs);
 }
 
@@ -537,11 +549,15 @@ index_hash_query_small_kernel(const float* __restrict__ X, int nq, int dim, cons
                               const int64_t* __restrict__ ids, int64_t main_n, int64_t n, int64_t cap, int out_cap,
                               int raw_cap, int64_t* __restrict__ out_ids, int* __restrict__ out_coll,
                               int* __restrict__ out_count, int* __restrict__ out_count_clamped,
-                              int64_t* __restrict__ out_offs) {
+                              int64_t* __restrict__ out_offs, unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(16) uint64_t sm[];
   __shared__ unsigned int sbits[32];
   __shared__ int last;
+  unsigned long long t_in = 0;
+  if (dbg && threadIdx.x == 0) t_in = gtime();
   hash_small_body(X, nq, dim, Rp, sig, sig_bytes, zero_flag, reinterpret_cast<float*>(sm), sbits);
+  unsigned long long t_hashed = 0;
+  if (dbg && threadIdx.x == 0) t_hashed = gtime();
   __threadfence();                      // this CTA's signature bytes are visible before its ticket is
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -552,8 +568,9 @@ index_hash_query_small_kernel(const float* __restrict__ X, int nq, int dim, cons
   __syncthreads();
   if (!last) return;
   __threadfence();
+  if (dbg && threadIdx.x == 0) { dbg[0] = t_in; dbg[1] = t_hashed; dbg[2] = gtime(); }   // last CTA: in, hashed, ticket
   for (int q = 0; q < nq; ++q) {
-    query_small_body(sm, q, sig, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap, out_ids, out_coll, out_count,
+    query_small_body(dbg, sm, q, sig, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap, out_ids, out_coll, out_count,
                      out_count_clamped, out_offs);
     __syncthreads();
   }
@@ -749,7 +766,7 @@ int index_hash_query_small(const float* X, int nq, int dim, const float* d_Rp, u
                            uint8_t* zero_flag, unsigned* d_ticket, int nb, int bpb, const uint64_t* keys,
                            const int64_t* ids, int64_t main_n, int64_t n, int64_t cap, int out_cap, int raw_cap,
                            int64_t* out_ids, int* out_coll, int* out_count, int* out_count_clamped, int64_t* out_offs,
-                           cudaStream_t st) {
+                           unsigned long long* d_dbg, cudaStream_t st) {
   if (nq <= 0) return LSHX_OK;
   if (raw_cap <= 0 || raw_cap > (int)JN_SMEM_CAP) raw_cap = (int)JN_SMEM_CAP;
   const size_t smem = 2 * (size_t)JN_SMEM_CAP * sizeof(uint64_t);     // >= nq * dim floats (hash_small_max_rows)
@@ -757,7 +774,7 @@ int index_hash_query_small(const float* X, int nq, int dim, const float* d_Rp, u
   LSHX_CUDA(cudaFuncSetAttribute(index_hash_query_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   index_hash_query_small_kernel<<<(unsigned)sig_bytes, JN_THREADS, smem, st>>>(
       X, nq, dim, d_Rp, d_sig, sig_bytes, zero_flag, d_ticket, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap,
-      out_ids, out_coll, out_count, out_count_clamped, out_offs);
+      out_ids, out_coll, out_count, out_count_clamped, out_offs, d_dbg);
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;

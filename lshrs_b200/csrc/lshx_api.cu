@@ -995,6 +995,7 @@ struct lshx_index {
   // ticket counter by which the fused hash + query kernel finds its last CTA
   uint8_t* pin_res = nullptr;
   unsigned* d_ticket = nullptr;
+  unsigned long long* d_dbg = nullptr;   // diagnostics: phase stamps of the latency kernel (lshx_index_debug_timeline)
   std::mutex mu;
 };
 
@@ -1078,6 +1079,7 @@ extern "C" int lshx_index_destroy(lshx_index* ix) {
     if (ix->d_max_id) cudaFree(ix->d_max_id);
     if (ix->d_bad) cudaFree(ix->d_bad);
     if (ix->d_ticket) cudaFree(ix->d_ticket);
+    if (ix->d_dbg) cudaFree(ix->d_dbg);
     if (ix->pin_res) cudaFreeHost(ix->pin_res);
     for (DevBuf* b : {&ix->hist, &ix->stage_sig, &ix->stage_ids, &ix->gone, &ix->q_sig, &ix->lo, &ix->cnt,
                       &ix->raw_count, &ix->raw_off, &ix->ws_off, &ix->meta, &ix->ws, &ix->out_ids, &ix->out_coll,
@@ -1443,7 +1445,7 @@ extern "C" int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const fl
                               zero_flag ? d_res + off_flag : nullptr, ix->d_ticket, ix->nb, ix->bpb,
                               ix->keys[ix->cur], ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, capacity, 0,
                               reinterpret_cast<int64_t*>(d_res), reinterpret_cast<int*>(d_res + off_coll),
-                              reinterpret_cast<int*>(d_res + off_count), nullptr, nullptr, st);
+                              reinterpret_cast<int*>(d_res + off_count), nullptr, nullptr, ix->d_dbg, st);
   if (rc != LSHX_OK) return rc;
   LSHX_CUDA(cudaStreamSynchronize(st));
   for (int q = 0; q < nq; ++q) {
@@ -1529,7 +1531,7 @@ extern "C" int lshx_index_query_rerank_vectors(lshx_index* ix, lshx_hasher* h, l
                               zero_flag ? d_res + off_flag : nullptr, ix->d_ticket, ix->nb, ix->bpb,
                               ix->keys[ix->cur], ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, RC, RC,
                               static_cast<int64_t*>(ix->out_ids.p), nullptr, reinterpret_cast<int*>(d_res + off_cand),
-                              static_cast<int*>(ix->uniq.p), static_cast<int64_t*>(ix->raw_off.p), st);
+                              static_cast<int*>(ix->uniq.p), static_cast<int64_t*>(ix->raw_off.p), nullptr, st);
   if (rc != LSHX_OK) return rc;
   RerankArgs a{};
   a.Q = d_x_map;                            // the rerank kernel stages each query in shared memory once
@@ -1564,6 +1566,25 @@ extern "C" int lshx_index_query_rerank_vectors(lshx_index* ix, lshx_hasher* h, l
   std::memcpy(out_candidates, res + off_cand, (size_t)nq * 4);
   if (out_zero) std::memcpy(out_zero, res + off_rzero, (size_t)nq * 4);
   if (zero_flag) std::memcpy(zero_flag, res + off_flag, (size_t)nq);
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_debug_timeline(lshx_index* ix, int enable, uint64_t* stamps_out /* 9 */) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  if (enable && !ix->d_dbg) {
+    LSHX_CUDA(cudaMalloc(reinterpret_cast<void**>(&ix->d_dbg), 9 * 8));
+    LSHX_CUDA(cudaMemset(ix->d_dbg, 0, 9 * 8));
+  }
+  if (stamps_out && ix->d_dbg) {
+    LSHX_CUDA(cudaStreamSynchronize(ix->stream));
+    LSHX_CUDA(cudaMemcpy(stamps_out, ix->d_dbg, 9 * 8, cudaMemcpyDeviceToHost));
+  }
+  if (!enable && ix->d_dbg) {
+    cudaFree(ix->d_dbg);
+    ix->d_dbg = nullptr;
+  }
   return LSHX_OK;
 }
 

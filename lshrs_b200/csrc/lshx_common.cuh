@@ -145,7 +145,7 @@ int index_hash_query_small(const float* X, int nq, int dim, const float* d_Rp, u
                            uint8_t* zero_flag, unsigned* d_ticket, int nb, int bpb, const uint64_t* keys,
                            const int64_t* ids, int64_t main_n, int64_t n, int64_t cap, int out_cap, int raw_cap,
                            int64_t* out_ids, int* out_coll, int* out_count, int* out_count_clamped, int64_t* out_offs,
-                           cudaStream_t st);
+                           unsigned long long* d_dbg, cudaStream_t st);
 int index_topk(const int64_t* d_cand, const int64_t* d_raw_off, const int* d_uniq, int64_t nq, int k, int64_t* d_out,
                int* d_out_count, cudaStream_t st);
 int index_pos_to_id(const int64_t* d_cand, const int64_t* d_raw_off, const int32_t* d_pos, const int32_t* d_count,

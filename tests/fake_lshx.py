@@ -376,6 +376,11 @@ def _index_methods():
         self.launches += 4
         return 0
 
+    def lshx_index_debug_timeline(self, h, enable, out_ptr):
+        if not _null(out_ptr):
+            _arr(out_ptr, (9,), np.uint64)[...] = 0
+        return 0
+
     def lshx_index_export(self, h, keys_ptr, ids_ptr, cap, n_ref):
         ix = self._get(h)
         rows = [[(k, i) for k, members in sorted(band.items()) for i in sorted(members)] for band in ix.buckets]

@@ -40,3 +40,20 @@ print(f"lshx_index_query_vectors   {per_call(lambda i: lib.lshx_index_query_vect
 out = np.empty((1, 32), np.uint8)
 print(f"lshx_hash_batch (1 row)    {per_call(lambda i: lib.lshx_hash_batch(hh, Q[i].ctypes.data, 1, 0, out.ctypes.data, 0, None, None)):7.1f} us")
 print(f"ctypes no-op (abi_version) {per_call(lambda i: lib.lshx_abi_version()):7.1f} us")
+# phase stamps of the fused latency kernel (lshx_index_debug_timeline), median over 200 calls
+stamps = np.zeros(9, np.uint64)
+lib.lshx_index_debug_timeline(ih, 1, None)
+rows, wall = [], []
+for i in range(300):
+    t0 = time.perf_counter_ns()
+    lib.lshx_index_query_vectors(ih, hh, Q[i].ctypes.data, 1, 10, *args)
+    wall.append(time.perf_counter_ns() - t0)
+    lib.lshx_index_debug_timeline(ih, 1, stamps.ctypes.data)
+    rows.append(stamps.astype(np.int64).copy())
+rows = np.array(rows[100:])
+names = ["hash (last CTA)", "ticket", "band searches", "gather", "first sort", "count + second sort", "store"]
+d = np.diff(rows[:, :8], axis=1)
+print("fused kernel phases of the last CTA, median ns:", {n: int(np.median(d[:, i])) for i, n in enumerate(names)},
+      "total", int(np.median(rows[:, 7] - rows[:, 0])), "raw entries", int(np.median(rows[:, 8])),
+      "| C call wall ns (stamps on)", int(np.median(wall[100:])))
+lib.lshx_index_debug_timeline(ih, 0, None)
