@@ -21,6 +21,8 @@
 // Integer work end to end: the candidate lists, their order and the collision counts are EXACTLY the
 // storage path's.  HBM / L2-latency bound; nothing here belongs on tensor cores.
 
+#include <cstring>
+
 #include "lshx_common.cuh"
 #include "hash_small.cuh"
 
@@ -216,26 +218,29 @@ __device__ __forceinline__ void search_run(const uint64_t* __restrict__ k, int64
   cnt_out = lo2 - lo;
 }
 
-// The same search by a whole warp (latency path: one query, nothing else in flight to hide a 20-step chain of
-// dependent loads behind): 32 probes per step split the range 33 ways -- 4 steps for a million entries -- and a
-// bucket shorter than 32 entries ends in one more.  LE = false: first entry >= key; true: first entry > key.
-template <bool LE>
-__device__ __forceinline__ int64_t warp_bound(const uint64_t* __restrict__ k, int64_t lo, int64_t hi, uint64_t key,
-                                              int lane) {
+// The same search by a GROUP of W lanes (latency path: one query, nothing else in flight to hide a 20-step chain
+// of dependent loads behind): W probes per step split the range W + 1 ways -- 5 steps for a million entries with
+// W = 16 -- and a bucket shorter than W entries ends in one more.  Two groups share a warp (each ballots under
+// its own mask), so the 16 slots of a 16-band query are searched in ONE round of the CTA's 8 warps.
+// LE = false: first entry >= key; true: first entry > key.
+template <bool LE, int W>
+__device__ __forceinline__ int64_t group_bound(const uint64_t* __restrict__ k, int64_t lo, int64_t hi, uint64_t key,
+                                               int gl /* lane within the group */, unsigned mask) {
+  const int shift = __ffs(mask) - 1;
   while (hi > lo) {
     const int64_t len = hi - lo;
-    const int64_t p = (len <= 32) ? lo + lane : lo + (len * (lane + 1)) / 33;   // ascending in the lane, p < hi
+    const int64_t p = (len <= W) ? lo + gl : lo + (len * (gl + 1)) / (W + 1);   // ascending in the lane, p < hi
     bool before = false;
     if (p < hi) {
       const uint64_t v = __ldg(k + p);
       before = LE ? (v <= key) : (v < key);
     }
-    const int t = __popc(__ballot_sync(0xffffffffu, before));    // sorted: the first t probes are "before"
-    if (len <= 32) return lo + t;
-    const int64_t p_prev = lo + (len * t) / 33;                  // probe t - 1 (for t > 0)
-    const int64_t p_next = lo + (len * (t + 1)) / 33;            // probe t     (for t < 32)
+    const int t = __popc((__ballot_sync(mask, before) & mask) >> shift);   // sorted: the first t probes are "before"
+    if (len <= W) return lo + t;
+    const int64_t p_prev = lo + (len * t) / (W + 1);                 // probe t - 1 (for t > 0)
+    const int64_t p_next = lo + (len * (t + 1)) / (W + 1);           // probe t     (for t < W)
     const int64_t nlo = t > 0 ? p_prev + 1 : lo;
-    hi = t < 32 ? p_next : hi;
+    hi = t < W ? p_next : hi;
     lo = nlo;
   }
   return lo;
@@ -443,19 +448,22 @@ __device__ __forceinline__ void query_small_body(unsigned long long* dbg, uint64
   __shared__ int heads, n_raw_s;
   const int tid = threadIdx.x;
   const int nv = nb * (n > main_n ? 2 : 1);
-  for (int v = tid >> 5; v < nv; v += JN_THREADS / 32) {       // one warp per (run, band) slot
-    const int b = v % nb, run = v / nb, lane = tid & 31;
+  constexpr int GW = 16;                                        // lanes per search group
+  const int gl = tid & (GW - 1);
+  const unsigned gmask = ((1u << GW) - 1u) << ((tid & 31) & ~(GW - 1));
+  for (int v = tid / GW; v < nv; v += JN_THREADS / GW) {        // one group per (run, band) slot
+    const int b = v % nb, run = v / nb;
     const uint8_t* src = sig + (q * nb + b) * (int64_t)bpb;
     uint64_t key = 0;
     for (int j = 0; j < bpb; ++j) key |= (uint64_t)__ldcg(src + j) << (8 * j);
     const uint64_t* k = keys + b * cap;
     const int64_t end = run ? n : main_n;
-    const int64_t lo = warp_bound<false>(k, run ? main_n : 0, end, key, lane);
-    // most buckets are short: one probe of the 32 entries behind lo usually finds the end
-    const int64_t near = (end - lo < 32) ? end : lo + 32;
-    int64_t up = warp_bound<true>(k, lo, near, key, lane);
-    if (up == near && near < end) up = warp_bound<true>(k, near, end, key, lane);
-    if (lane == 0) {
+    const int64_t lo = group_bound<false, GW>(k, run ? main_n : 0, end, key, gl, gmask);
+    // most buckets are short: one probe of the GW entries behind lo usually finds the end
+    const int64_t near = (end - lo < GW) ? end : lo + GW;
+    int64_t up = group_bound<true, GW>(k, lo, near, key, gl, gmask);
+    if (up == near && near < end) up = group_bound<true, GW>(k, near, end, key, gl, gmask);
+    if (gl == 0) {
       const int64_t c = up - lo;
       s_lo[v] = lo;
       s_cnt[v] = (int)(c > 0x7fffffff ? 0x7fffffff : c);
@@ -482,14 +490,17 @@ __device__ __forceinline__ void query_small_body(unsigned long long* dbg, uint64
   const unsigned P = pow2_at_least((unsigned)n_raw);
   uint64_t* buf = sm;
   uint64_t* buf2 = sm + JN_SMEM_CAP;
-  for (int v = 0; v < nv; ++v) {
-    const int b = v % nb;
-    const int c = s_cnt[v];
-    const int64_t* src = ids + b * cap + s_lo[v];
-    for (int i = tid; i < c; i += JN_THREADS) {
-      const int64_t id = src[i];
-      buf[band_off[v] + i] = id < 0 ? EMPTY : (((uint64_t)id << 8) | (uint64_t)b);   // (id, band), as in the join
+  // gather, flattened over the matched entries: every load is in flight at once (a loop over the slots costs one
+  // memory round trip per slot -- 6.5 us of a 27 us kernel, lshx_index_debug_timeline)
+  for (int e = tid; e < n_raw; e += JN_THREADS) {
+    int lo_v = 0, hi_v = nv - 1;          // last slot whose first entry is <= e (empty slots share an offset)
+    while (lo_v < hi_v) {
+      const int mid = (lo_v + hi_v + 1) >> 1;
+      if (band_off[mid] <= e) lo_v = mid; else hi_v = mid - 1;
     }
+    const int b = lo_v % nb;
+    const int64_t id = ids[b * cap + s_lo[lo_v] + (e - band_off[lo_v])];
+    buf[e] = id < 0 ? EMPTY : (((uint64_t)id << 8) | (uint64_t)b);   // (id, band), as in the join
   }
   for (unsigned i = n_raw + tid; i < P; i += JN_THREADS) buf[i] = EMPTY;
   __syncthreads();
@@ -542,38 +553,67 @@ index_query_small_kernel(const uint8_t* __restrict__ sig, int nb, int bpb, const
 // pinned host memory, so no copy precedes the launch); the CTA that finishes last -- a ticket counter, no CTA
 // ever waits for another -- reads the finished signatures and runs the lookup / join / emit of every query.
 static_assert(SMALL_THREADS == JN_THREADS, "the fused latency kernel runs both bodies with one block size");
-__global__ void __launch_bounds__(JN_THREADS)
-index_hash_query_small_kernel(const float* __restrict__ X, int nq, int dim, const float* __restrict__ Rp,
-                              uint8_t* __restrict__ sig, int sig_bytes, uint8_t* __restrict__ zero_flag,
-                              unsigned* __restrict__ ticket, int nb, int bpb, const uint64_t* __restrict__ keys,
-                              const int64_t* __restrict__ ids, int64_t main_n, int64_t n, int64_t cap, int out_cap,
-                              int raw_cap, int64_t* __restrict__ out_ids, int* __restrict__ out_coll,
-                              int* __restrict__ out_count, int* __restrict__ out_count_clamped,
-                              int64_t* __restrict__ out_offs, unsigned long long* __restrict__ dbg) {
-  extern __shared__ __align__(16) uint64_t sm[];
+
+struct HashQueryArgs {
+  int nq, dim;
+  const float* Rp;
+  uint8_t* sig;
+  int sig_bytes;
+  uint8_t* zero_flag;
+  unsigned* ticket;
+  int nb, bpb;
+  const uint64_t* keys;
+  const int64_t* ids;
+  int64_t main_n, n, cap;
+  int out_cap, raw_cap;
+  int64_t* out_ids;
+  int* out_coll;
+  int* out_count;
+  int* out_count_clamped;
+  int64_t* out_offs;
+  unsigned long long* dbg;
+};
+
+__device__ __forceinline__ void hash_query_small(const float* X, const HashQueryArgs& a, uint64_t* sm) {
   __shared__ unsigned int sbits[32];
   __shared__ int last;
   unsigned long long t_in = 0;
-  if (dbg && threadIdx.x == 0) t_in = gtime();
-  hash_small_body(X, nq, dim, Rp, sig, sig_bytes, zero_flag, reinterpret_cast<float*>(sm), sbits);
+  if (a.dbg && threadIdx.x == 0) t_in = gtime();
+  hash_small_body(X, a.nq, a.dim, a.Rp, a.sig, a.sig_bytes, a.zero_flag, reinterpret_cast<float*>(sm), sbits);
   unsigned long long t_hashed = 0;
-  if (dbg && threadIdx.x == 0) t_hashed = gtime();
+  if (a.dbg && threadIdx.x == 0) t_hashed = gtime();
   __threadfence();                      // this CTA's signature bytes are visible before its ticket is
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(ticket, 1u);
+    const unsigned t = atomicAdd(a.ticket, 1u);
     last = (t == gridDim.x - 1) ? 1 : 0;
-    if (last) *ticket = 0u;             // ready for the next launch (launches on one stream do not overlap)
+    if (last) *a.ticket = 0u;           // ready for the next launch (launches on one stream do not overlap)
   }
   __syncthreads();
   if (!last) return;
   __threadfence();
-  if (dbg && threadIdx.x == 0) { dbg[0] = t_in; dbg[1] = t_hashed; dbg[2] = gtime(); }   // last CTA: in, hashed, ticket
-  for (int q = 0; q < nq; ++q) {
-    query_small_body(dbg, sm, q, sig, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap, out_ids, out_coll, out_count,
-                     out_count_clamped, out_offs);
+  if (a.dbg && threadIdx.x == 0) { a.dbg[0] = t_in; a.dbg[1] = t_hashed; a.dbg[2] = gtime(); }   // last CTA: in, hashed, ticket
+  for (int q = 0; q < a.nq; ++q) {
+    query_small_body(a.dbg, sm, q, a.sig, a.nb, a.bpb, a.keys, a.ids, a.main_n, a.n, a.cap, a.out_cap, a.raw_cap,
+                     a.out_ids, a.out_coll, a.out_count, a.out_count_clamped, a.out_offs);
     __syncthreads();
   }
+}
+
+__global__ void __launch_bounds__(JN_THREADS)
+index_hash_query_small_kernel(const float* __restrict__ X, const HashQueryArgs a) {
+  extern __shared__ __align__(16) uint64_t sm[];
+  hash_query_small(X, a, sm);
+}
+
+// ONE vector of up to 1024 floats travels in the kernel's PARAMETER block (sm_70+ launches take 32 KB of
+// parameters): it arrives with the launch itself instead of being fetched from pinned host memory by the CTAs.
+struct alignas(16) XRowParam { float v[1024]; };
+
+__global__ void __launch_bounds__(JN_THREADS)
+index_hash_query_one_kernel(const __grid_constant__ XRowParam x, const HashQueryArgs a) {
+  extern __shared__ __align__(16) uint64_t sm[];
+  hash_query_small(x.v, a, sm);
 }
 
 // dense [nq][k] prefix of the candidate lists (get_top_k mode, main.py:616-623)
@@ -762,8 +802,8 @@ int index_query_small(const uint8_t* d_sig, int nq, int nb, int bpb, const uint6
   return LSHX_OK;
 }
 
-int index_hash_query_small(const float* X, int nq, int dim, const float* d_Rp, uint8_t* d_sig, int sig_bytes,
-                           uint8_t* zero_flag, unsigned* d_ticket, int nb, int bpb, const uint64_t* keys,
+int index_hash_query_small(const float* X, const float* X_host, int nq, int dim, const float* d_Rp, uint8_t* d_sig,
+                           int sig_bytes, uint8_t* zero_flag, unsigned* d_ticket, int nb, int bpb, const uint64_t* keys,
                            const int64_t* ids, int64_t main_n, int64_t n, int64_t cap, int out_cap, int raw_cap,
                            int64_t* out_ids, int* out_coll, int* out_count, int* out_count_clamped, int64_t* out_offs,
                            unsigned long long* d_dbg, cudaStream_t st) {
@@ -771,10 +811,23 @@ int index_hash_query_small(const float* X, int nq, int dim, const float* d_Rp, u
   if (raw_cap <= 0 || raw_cap > (int)JN_SMEM_CAP) raw_cap = (int)JN_SMEM_CAP;
   const size_t smem = 2 * (size_t)JN_SMEM_CAP * sizeof(uint64_t);     // >= nq * dim floats (hash_small_max_rows)
   LSHX_REQUIRE((size_t)nq * dim * sizeof(float) <= smem, "too many rows for the fused latency kernel");
-  LSHX_CUDA(cudaFuncSetAttribute(index_hash_query_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  index_hash_query_small_kernel<<<(unsigned)sig_bytes, JN_THREADS, smem, st>>>(
-      X, nq, dim, d_Rp, d_sig, sig_bytes, zero_flag, d_ticket, nb, bpb, keys, ids, main_n, n, cap, out_cap, raw_cap,
-      out_ids, out_coll, out_count, out_count_clamped, out_offs, d_dbg);
+  static thread_local int attr_device = -1;   // once per host thread and device: the call is on the latency path
+  int dev_now = -1;
+  LSHX_CUDA(cudaGetDevice(&dev_now));
+  if (attr_device != dev_now) {
+    LSHX_CUDA(cudaFuncSetAttribute(index_hash_query_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LSHX_CUDA(cudaFuncSetAttribute(index_hash_query_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_device = dev_now;
+  }
+  const HashQueryArgs a{nq, dim, d_Rp, d_sig, sig_bytes, zero_flag, d_ticket, nb, bpb, keys, ids, main_n, n, cap, out_cap,
+                        raw_cap, out_ids, out_coll, out_count, out_count_clamped, out_offs, d_dbg};
+  if (nq == 1 && dim <= 1024 && X_host != nullptr) {
+    static thread_local XRowParam row;       // (the tail beyond dim is never read)
+    std::memcpy(row.v, X_host, (size_t)dim * sizeof(float));
+    index_hash_query_one_kernel<<<(unsigned)sig_bytes, JN_THREADS, smem, st>>>(row, a);
+  } else {
+    index_hash_query_small_kernel<<<(unsigned)sig_bytes, JN_THREADS, smem, st>>>(X, a);
+  }
   count_launch();
   LSHX_CUDA(cudaGetLastError());
   return LSHX_OK;

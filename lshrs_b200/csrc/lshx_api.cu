@@ -1441,7 +1441,7 @@ extern "C" int lshx_index_query_vectors(lshx_index* ix, lshx_hasher* h, const fl
   float* d_x_map = nullptr;                  // the kernel reads the vectors from the pinned block in place
   LSHX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_x_map), h->pin_x, 0));
   h->last_kernel = LSHX_KERNEL_SMALL;
-  rc = index_hash_query_small(d_x_map, nq, s.dim, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p), s.sig_bytes,
+  rc = index_hash_query_small(d_x_map, h->pin_x, nq, s.dim, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p), s.sig_bytes,
                               zero_flag ? d_res + off_flag : nullptr, ix->d_ticket, ix->nb, ix->bpb,
                               ix->keys[ix->cur], ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, capacity, 0,
                               reinterpret_cast<int64_t*>(d_res), reinterpret_cast<int*>(d_res + off_coll),
@@ -1527,7 +1527,7 @@ extern "C" int lshx_index_query_rerank_vectors(lshx_index* ix, lshx_hasher* h, l
   float* d_x_map = nullptr;
   LSHX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_x_map), h->pin_x, 0));
   h->last_kernel = LSHX_KERNEL_SMALL;
-  rc = index_hash_query_small(d_x_map, nq, s.dim, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p), s.sig_bytes,
+  rc = index_hash_query_small(d_x_map, h->pin_x, nq, s.dim, h->d_Rp, static_cast<uint8_t*>(ix->q_sig.p), s.sig_bytes,
                               zero_flag ? d_res + off_flag : nullptr, ix->d_ticket, ix->nb, ix->bpb,
                               ix->keys[ix->cur], ix->ids[ix->cur], ix->main_n, ix->n, ix->cap, RC, RC,
                               static_cast<int64_t*>(ix->out_ids.p), nullptr, reinterpret_cast<int*>(d_res + off_cand),

@@ -141,8 +141,10 @@ int index_join(int64_t nq, int nb, int nruns, const int64_t* ids, int64_t cap, c
                const int* d_raw_count, const int64_t* d_raw_off, const int64_t* d_ws_off, uint64_t* d_ws,
                int64_t ws_total, int64_t* d_out_ids, int* d_out_coll, int* d_uniq, cudaStream_t st);
 // hash (small-batch FP32 kernel body) + lookup / join / emit of nq <= hash_small_max_rows vectors in ONE launch
-int index_hash_query_small(const float* X, int nq, int dim, const float* d_Rp, uint8_t* d_sig, int sig_bytes,
-                           uint8_t* zero_flag, unsigned* d_ticket, int nb, int bpb, const uint64_t* keys,
+// (X: device-readable, e.g. mapped pinned memory; X_host: the same rows readable by the host, or null -- ONE row of
+// up to 1024 floats then travels in the kernel's parameter block)
+int index_hash_query_small(const float* X, const float* X_host, int nq, int dim, const float* d_Rp, uint8_t* d_sig,
+                           int sig_bytes, uint8_t* zero_flag, unsigned* d_ticket, int nb, int bpb, const uint64_t* keys,
                            const int64_t* ids, int64_t main_n, int64_t n, int64_t cap, int out_cap, int raw_cap,
                            int64_t* out_ids, int* out_coll, int* out_count, int* out_count_clamped, int64_t* out_offs,
                            unsigned long long* d_dbg, cudaStream_t st);
