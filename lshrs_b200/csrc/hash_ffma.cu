@@ -13,6 +13,8 @@
 // is measured against.  128x128 tile per CTA, 8x8 register tile per thread,
 // BK = 16, double-buffered shared memory with register prefetch.
 
+#include <cstring>
+
 #include "lshx_common.cuh"
 #include "hash_small.cuh"
 
@@ -213,6 +215,15 @@ hash_small_kernel(const float* __restrict__ X, int n, int dim, const float* __re
   hash_small_body(X, n, dim, Rp, out, sig_bytes, zero_flag, xs, sbits);
 }
 
+// the same for ONE row that travels in the parameter block
+__global__ void __launch_bounds__(SMALL_THREADS)
+hash_small_one_kernel(const __grid_constant__ XRowParam x, int dim, const float* __restrict__ Rp,
+                      uint8_t* __restrict__ out, int sig_bytes, uint8_t* __restrict__ zero_flag) {
+  extern __shared__ __align__(16) float xs[];
+  __shared__ unsigned int sbits[32];
+  hash_small_body(x.v, 1, dim, Rp, out, sig_bytes, zero_flag, xs, sbits);
+}
+
 }  // namespace
 
 int launch_hash_ffma(const HashShape& s, const float* d_X, int64_t n, const float* d_Rp,
@@ -264,6 +275,18 @@ namespace lshx {
 int hash_small_max_rows(const HashShape& s) {
   const int by_smem = (int)(65536 / ((size_t)s.dim * sizeof(float)));
   return by_smem < 32 ? by_smem : 32;
+}
+
+int launch_hash_small_one(const HashShape& s, const float* x_host, const float* d_Rp, uint8_t* out, uint8_t* zero_flag,
+                          cudaStream_t stream) {
+  LSHX_REQUIRE(s.dim <= SMALL_PARAM_FLOATS, "a row of %d floats does not fit the parameter block", s.dim);
+  static thread_local XRowParam row;
+  std::memcpy(row.v, x_host, (size_t)s.dim * sizeof(float));
+  hash_small_one_kernel<<<s.sig_bytes, SMALL_THREADS, (size_t)s.dim * sizeof(float), stream>>>(row, s.dim, d_Rp, out,
+                                                                                               s.sig_bytes, zero_flag);
+  count_launch();
+  LSHX_CUDA(cudaGetLastError());
+  return LSHX_OK;
 }
 
 int launch_hash_small(const HashShape& s, const float* d_X, int n, const float* d_Rp, uint8_t* out,

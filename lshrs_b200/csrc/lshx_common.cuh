@@ -69,6 +69,9 @@ int launch_hash_ffma_tiles(const HashShape& s, const float* d_X, int64_t n, cons
 int hash_small_max_rows(const HashShape& s);
 int launch_hash_small(const HashShape& s, const float* d_X, int n, const float* d_Rp, uint8_t* out,
                       uint8_t* zero_flag, cudaStream_t stream);
+// ONE host row (dim <= 1024) carried in the kernel's parameter block: no copy in front of the launch
+int launch_hash_small_one(const HashShape& s, const float* x_host, const float* d_Rp, uint8_t* out, uint8_t* zero_flag,
+                          cudaStream_t stream);
 
 struct TcPlan;  // opaque tcgen05 state (TMA descriptor of the split projections, ...)
 bool tc_shape_supported(const HashShape& s);
