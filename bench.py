@@ -60,9 +60,9 @@ FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustain
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel PER ROW from the committed ncu --set full
 # captures (file, bytes per launch, rows per launch); scaled to the rows of one launch of the run
 NCU_TRAFFIC = {
-    "hash768": ("profiles/r1_hash_tc_ncu.csv", 2.428e9, 781_250),
-    "hash128": ("profiles/r1_hash_tc_dim128_ncu.csv", 6.601e9, 12_500_000),
-    "rerank": ("profiles/r1_rerank_ncu.csv", 12.34e9, 2048),          # per 2048-query launch of 2000 x 768 candidates
+    "hash768": ("profiles/r2_hash_tc_ncu.csv", 2.429e9, 781_250),
+    "hash128": ("profiles/r2_hash_tc_dim128_ncu.csv", 6.600e9, 12_500_000),
+    "rerank": ("profiles/r2_rerank_ncu.csv", 12.345e9, 2048),          # per 2048-query launch of 2000 x 768 candidates
 }
 
 
