@@ -1,6 +1,9 @@
 // extern "C" entry points of liblshx.so (declared in include/lshx.h) and the host-side
 // staging pipelines around the kernels.
 
+#include <emmintrin.h>
+
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -243,6 +246,37 @@ extern "C" int lshx_hasher_set_kernel(lshx_hasher* h, int kernel) {
 extern "C" int lshx_hasher_last_kernel(const lshx_hasher* h) { return h ? h->last_kernel : 0; }
 extern "C" int lshx_hasher_signature_bytes(const lshx_hasher* h) { return h ? h->s.sig_bytes : 0; }
 
+// Copy into a pinned bounce buffer with NON-TEMPORAL stores.  A plain memcpy of a 1 MB piece leaves the lines
+// dirty in the copying core's cache; the DMA engine that reads the buffer next then has to snoop them out of a
+// dozen private caches, which runs at ~6.6 GB/s instead of PCIe's 55 (measured: a 12 MB H2D took 1.86 ms after the
+// pool's memcpy, 0.24 ms from an untouched buffer -- tools/h2d_probe.py, LSHX_TRACE_PAGEABLE).  Streaming stores
+// send the data to DRAM and keep the caches clean.
+static void stream_copy(void* dst, const void* src, size_t bytes) {
+  char* d = static_cast<char*>(dst);
+  const char* s = static_cast<const char*>(src);
+  if (bytes < 4096) {
+    std::memcpy(d, s, bytes);
+    return;
+  }
+  const size_t head = (64 - (reinterpret_cast<uintptr_t>(d) & 63)) & 63;
+  std::memcpy(d, s, head);
+  d += head; s += head; bytes -= head;
+  const size_t blocks = bytes / 64;
+  for (size_t i = 0; i < blocks; ++i) {
+    const __m128i a0 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s));
+    const __m128i a1 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 16));
+    const __m128i a2 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 32));
+    const __m128i a3 = _mm_loadu_si128(reinterpret_cast<const __m128i*>(s + 48));
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d), a0);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 16), a1);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 32), a2);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(d + 48), a3);
+    d += 64; s += 64;
+  }
+  std::memcpy(d, s, bytes - blocks * 64);
+  _mm_sfence();
+}
+
 // memcpy split over the host cores: one core copies ~5-10 GB/s, PCIe Gen5 takes 55.  A small process-wide
 // pool of sleeping workers (spawning threads per 64 MB chunk cost a third of the copy time).
 namespace {
@@ -276,7 +310,7 @@ class CopyPool {
       ++generation_;
     }
     cv_.notify_all();
-    std::memcpy(dst, src, piece < bytes ? piece : bytes);
+    stream_copy(dst, src, piece < bytes ? piece : bytes);
     std::unique_lock<std::mutex> lk(mu_);
     done_cv_.wait(lk, [this] { return pending_ == 0; });
   }
@@ -295,7 +329,7 @@ class CopyPool {
         char* d = dst_ + off;
         const char* s = src_ + off;
         lk.unlock();
-        std::memcpy(d, s, len);
+        stream_copy(d, s, len);
         lk.lock();
         if (--pending_ == 0) done_cv_.notify_all();
       }
@@ -330,8 +364,8 @@ static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     const int v = atoi(e);
     if (v >= 1 && v <= 64) nt = (unsigned)v;
   }
-  if (bytes < (8u << 20) || nt <= 1) {
-    std::memcpy(dst, src, bytes);
+  if (bytes < (2u << 20) || nt <= 1) {
+    stream_copy(dst, src, bytes);
     return;
   }
   static CopyPool* pool = new CopyPool(nt - 1);   // leaked on purpose: no join at process exit
@@ -440,7 +474,15 @@ static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, u
   }
   // rows per chunk: what fills a bounce buffer in the caller's element type (float32: bounce_rows;
   // float16: twice, 1-byte types: four times as many -- the per-chunk fixed costs are per byte moved)
-  const int64_t chunk = (int64_t)(h->bounce_rows * row_bytes / in_row) / 128 * 128;
+  int64_t chunk = (int64_t)(h->bounce_rows * row_bytes / in_row) / 128 * 128;
+  // a batch that does not fill four bounce buffers is cut in four anyway (pieces of at least 2 MB), so that the
+  // copy of one piece into its bounce buffer overlaps the DMA of the piece before it
+  {
+    int64_t quarter = ((n + 3) / 4 + 127) / 128 * 128;
+    const int64_t min_rows = ((int64_t)((2u << 20) / in_row) + 127) / 128 * 128;
+    if (quarter < min_rows) quarter = min_rows;
+    if (quarter < chunk) chunk = quarter;
+  }
   for (int i = 0; i < 2; ++i) {
     int rc;
     if ((rc = h->x_stage[i].reserve((size_t)chunk * row_bytes)) != LSHX_OK) return rc;
@@ -451,7 +493,7 @@ static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, u
   struct Pending { int64_t r0 = 0, rows = 0; } pending[2];
   auto drain = [&](int slot) -> int {  // copy a finished slot's results to the caller's memory
     if (pending[slot].rows == 0) return LSHX_OK;
-    LSHX_CUDA(cudaEventSynchronize(h->bounce_ev[slot]));
+    LSHX_CUDA(cudaStreamSynchronize(h->streams[slot]));   // (the slot's stream carries nothing but this chunk)
     const Pending pd = pending[slot];
     std::memcpy(out + pd.r0 * s.sig_bytes, h->bounce_out[slot], (size_t)pd.rows * s.sig_bytes);
     if (zero_flag) std::memcpy(zero_flag + pd.r0, h->bounce_out[slot] + (size_t)chunk * s.sig_bytes, (size_t)pd.rows);
@@ -459,11 +501,17 @@ static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, u
     return LSHX_OK;
   };
   int slot = 0;
+  static const bool trace = getenv("LSHX_TRACE_PAGEABLE") != nullptr;   // bring-up: phase times on stderr
+  auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = trace ? now_us() : 0.0;
+  double t_copy = 0.0;
   for (int64_t r0 = 0; r0 < n; r0 += chunk, slot ^= 1) {
     const int64_t rows = (n - r0 < chunk) ? (n - r0) : chunk;
     int rc = drain(slot);  // also guarantees the slot's H2D source is no longer being read
     if (rc != LSHX_OK) return rc;
+    const double tc0 = trace ? now_us() : 0.0;
     parallel_memcpy(h->bounce_x[slot], X + r0 * in_row, (size_t)rows * in_row);
+    if (trace) t_copy += now_us() - tc0;
     cudaStream_t st = h->streams[slot];
     if (dtype == LSHX_DTYPE_F32) {
       LSHX_CUDA(cudaMemcpyAsync(h->x_stage[slot].p, h->bounce_x[slot], (size_t)rows * row_bytes,
@@ -476,8 +524,15 @@ static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, u
     }
     uint8_t* d_o = static_cast<uint8_t*>(h->out_stage[slot].p);
     uint8_t* d_f = zero_flag ? static_cast<uint8_t*>(h->flag_stage[slot].p) : nullptr;
+    double t_a = 0, t_b = 0, t_c = 0;
+    if (trace) { t_a = now_us(); cudaStreamSynchronize(st); t_b = now_us(); }
     rc = launch_hash(h, static_cast<const float*>(h->x_stage[slot].p), rows, d_o, d_f, st);
     if (rc != LSHX_OK) return rc;
+    if (trace) {
+      cudaStreamSynchronize(st);
+      t_c = now_us();
+      fprintf(stderr, "[lshx pageable]   rows %lld: H2D %.0f us, kernel %.0f us\n", (long long)rows, t_b - t_a, t_c - t_b);
+    }
     LSHX_CUDA(cudaMemcpyAsync(h->bounce_out[slot], d_o, (size_t)rows * s.sig_bytes, cudaMemcpyDeviceToHost, st));
     if (zero_flag)
       LSHX_CUDA(cudaMemcpyAsync(h->bounce_out[slot] + (size_t)chunk * s.sig_bytes, d_f, (size_t)rows,
@@ -486,9 +541,14 @@ static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, u
     pending[slot].r0 = r0;
     pending[slot].rows = rows;
   }
+  const double t_issued = trace ? now_us() : 0.0;
   int rc = drain(slot);
   if (rc != LSHX_OK) return rc;
-  return drain(slot ^ 1);
+  rc = drain(slot ^ 1);
+  if (trace)
+    fprintf(stderr, "[lshx pageable] n=%lld chunk=%lld: total %.0f us, bounce memcpy %.0f us, issue %.0f us, drain %.0f us\n",
+            (long long)n, (long long)chunk, now_us() - t_begin, t_copy, t_issued - t_begin - t_copy, now_us() - t_issued);
+  return rc;
 }
 
 static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_out,
@@ -557,7 +617,7 @@ extern "C" int lshx_hash_batch(lshx_hasher* h, const float* X, int64_t n, int x_
   }
 
   // ---- a large pageable host batch: pinned bounce buffers filled by several CPU threads -----------
-  if (!x_is_device && !out_is_device && n >= 4096 && is_pageable_host(X)) {
+  if (!x_is_device && !out_is_device && (size_t)n * s.dim * sizeof(float) >= (1u << 20) && is_pageable_host(X)) {
     LSHX_CUDA(cudaStreamSynchronize(user));
     return hash_pageable(h, X, LSHX_DTYPE_F32, n, out, zero_flag);
   }
