@@ -475,10 +475,10 @@ static int hash_pageable(lshx_hasher* h, const void* Xv, int dtype, int64_t n, u
   // rows per chunk: what fills a bounce buffer in the caller's element type (float32: bounce_rows;
   // float16: twice, 1-byte types: four times as many -- the per-chunk fixed costs are per byte moved)
   int64_t chunk = (int64_t)(h->bounce_rows * row_bytes / in_row) / 128 * 128;
-  // a batch that does not fill four bounce buffers is cut in four anyway (pieces of at least 2 MB), so that the
+  // a batch that does not fill eight bounce buffers is cut in eight anyway (pieces of at least 2 MB), so that the
   // copy of one piece into its bounce buffer overlaps the DMA of the piece before it
   {
-    int64_t quarter = ((n + 3) / 4 + 127) / 128 * 128;
+    int64_t quarter = ((n + 7) / 8 + 127) / 128 * 128;
     const int64_t min_rows = ((int64_t)((2u << 20) / in_row) + 127) / 128 * 128;
     if (quarter < min_rows) quarter = min_rows;
     if (quarter < chunk) chunk = quarter;
