@@ -165,7 +165,8 @@ int lshx_hasher_destroy(lshx_hasher* h);
  * Bit mask of the tuning / bring-up environment overrides that are set in this
  * process: 1 LSHX_TC_FLAGS, 2 LSHX_TC_SPLIT (kernel variant / operand split of
  * the tcgen05 kernel), 4 LSHX_COPY_THREADS, 8 LSHX_BOUNCE_MB (pageable-input
- * staging).  No reference counterpart; bench.py records it so that a published
+ * staging), 16 LSHX_TRACE_PAGEABLE (phase times of that staging on stderr; adds
+ * synchronisations).  No reference counterpart; bench.py records it so that a published
  * number states that the product dispatch was not overridden.
  */
 int lshx_env_overrides(void);

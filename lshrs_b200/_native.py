@@ -277,7 +277,7 @@ def default_device() -> int:
 def env_overrides() -> list[str]:
     """Names of the LSHX_* tuning overrides set in this process (empty in a product run)."""
     mask = int(lib().lshx_env_overrides())
-    names = ("LSHX_TC_FLAGS", "LSHX_TC_SPLIT", "LSHX_COPY_THREADS", "LSHX_BOUNCE_MB")
+    names = ("LSHX_TC_FLAGS", "LSHX_TC_SPLIT", "LSHX_COPY_THREADS", "LSHX_BOUNCE_MB", "LSHX_TRACE_PAGEABLE")
     return [n for i, n in enumerate(names) if mask & (1 << i)]
 
 

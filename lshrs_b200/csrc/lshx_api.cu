@@ -689,9 +689,10 @@ extern "C" int lshx_hash_batch_typed(lshx_hasher* h, const void* X, int dtype, i
 }
 
 extern "C" int lshx_env_overrides(void) {
-  static const char* const names[] = {"LSHX_TC_FLAGS", "LSHX_TC_SPLIT", "LSHX_COPY_THREADS", "LSHX_BOUNCE_MB"};
+  static const char* const names[] = {"LSHX_TC_FLAGS", "LSHX_TC_SPLIT", "LSHX_COPY_THREADS", "LSHX_BOUNCE_MB",
+                                      "LSHX_TRACE_PAGEABLE"};
   int mask = 0;
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < 5; ++i) {
     const char* e = getenv(names[i]);
     if (e != nullptr && *e) mask |= 1 << i;
   }
