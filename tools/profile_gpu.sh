@@ -20,7 +20,7 @@ CMD2="python bench.py --steps 1 --warmup 3 --rows 781250 --no-cpu --no-configs -
 ncu --set full --clock-control none --import-source on -k regex:index_join_kernel -s 2 -c 1 \
     -f -o gpurun_out/${TAG}_index_join $CMD2 > gpurun_out/${TAG}_ncu_index.log 2>&1
 echo "index join capture exit $?"
-ncu --set full --clock-control none --import-source on -k regex:index_query_small_kernel -s 20 -c 2 \
+ncu --set full --clock-control none --import-source on -k regex:index_hash_query -s 20 -c 2 \
     -f -o gpurun_out/${TAG}_index_query_small $CMD2 > gpurun_out/${TAG}_ncu_index_small.log 2>&1
 echo "index latency-path capture exit $?"
 CMD3="python bench.py --workload hash128 --rows 25000000 --steps 1 --warmup 3 --no-cpu --no-e2e"
