@@ -382,6 +382,55 @@ static bool is_pageable_host(const void* p) {
   return attr.type == cudaMemoryTypeUnregistered;
 }
 
+// Host -> device upload of a buffer that may be ordinary pageable memory (numpy arrays: query vectors, candidate
+// ids, signatures).  cudaMemcpyAsync from pageable memory runs at ~10 GB/s through the driver's own staging; a
+// large pageable source instead goes through two pinned bounce buffers per device, filled with non-temporal
+// stores (stream_copy, see above) while the previous piece is on the wire: ~45 GB/s.  The source is consumed
+// when the call returns; the DMA is asynchronous on `st`.
+namespace {
+struct UploadRing {
+  void* buf[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  bool ok = false;
+};
+constexpr size_t UPLOAD_PIECE = 8u << 20;
+std::mutex g_upload_mu;
+UploadRing g_upload_rings[64];
+}  // namespace
+
+static int upload(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return LSHX_OK;
+  int dev = -1;
+  if (bytes < (1u << 20) || !is_pageable_host(h_src) || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    LSHX_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+    return LSHX_OK;
+  }
+  std::lock_guard<std::mutex> lk(g_upload_mu);
+  UploadRing& ring = g_upload_rings[dev];
+  if (!ring.ok) {
+    for (int i = 0; i < 2; ++i) {
+      if (cudaHostAlloc(&ring.buf[i], UPLOAD_PIECE, cudaHostAllocPortable) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ring.ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        (void)cudaGetLastError();   // no bounce buffers: the plain copy still works
+        LSHX_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        return LSHX_OK;
+      }
+    }
+    ring.ok = true;
+  }
+  const char* src = static_cast<const char*>(h_src);
+  char* dst = static_cast<char*>(d_dst);
+  int slot = 0;
+  for (size_t off = 0; off < bytes; off += UPLOAD_PIECE, slot ^= 1) {
+    const size_t len = bytes - off < UPLOAD_PIECE ? bytes - off : UPLOAD_PIECE;
+    LSHX_CUDA(cudaEventSynchronize(ring.ev[slot]));   // the DMA that last read this slot is done (a fresh event is)
+    parallel_memcpy(ring.buf[slot], src + off, len);
+    LSHX_CUDA(cudaMemcpyAsync(dst + off, ring.buf[slot], len, cudaMemcpyHostToDevice, st));
+    LSHX_CUDA(cudaEventRecord(ring.ev[slot], st));
+  }
+  return LSHX_OK;
+}
+
 static int launch_hash(lshx_hasher* h, const float* d_X, int64_t n, uint8_t* d_out,
                        uint8_t* d_flag, cudaStream_t st);
 
@@ -931,8 +980,7 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
   LSHX_CUDA(cudaMemcpyAsync(d_offs, cand_offsets, (size_t)(nq + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
                             streams[0]));
   if (host_vectors && cand_ids)
-    LSHX_CUDA(cudaMemcpyAsync(d_vecs, vectors, (size_t)vec_rows * dim * sizeof(float), cudaMemcpyHostToDevice,
-                              streams[0]));
+    if ((rc = upload(d_vecs, vectors, (size_t)vec_rows * dim * sizeof(float), streams[0])) != LSHX_OK) return rc;
   LSHX_CUDA(cudaEventRecord(r->ev, streams[0]));
   LSHX_CUDA(cudaStreamWaitEvent(streams[1], r->ev, 0));
 
@@ -944,14 +992,12 @@ static int rerank_common(lshx_reranker* r, const float* Q, int64_t nq, const flo
     const int64_t c1 = (c0 + qchunk < nq) ? c0 + qchunk : nq;
     const int64_t s0 = cand_offsets[c0], s1 = cand_offsets[c1];  // candidate slots of this chunk
     cudaStream_t st = streams[slot];
-    LSHX_CUDA(cudaMemcpyAsync(d_q + c0 * dim, Q + c0 * dim, (size_t)(c1 - c0) * dim * sizeof(float),
-                              cudaMemcpyHostToDevice, st));
+    if ((rc = upload(d_q + c0 * dim, Q + c0 * dim, (size_t)(c1 - c0) * dim * sizeof(float), st)) != LSHX_OK) return rc;
     if (a.ids && s1 > s0)
-      LSHX_CUDA(cudaMemcpyAsync(d_ids + s0, cand_ids + s0, (size_t)(s1 - s0) * sizeof(int64_t),
-                                cudaMemcpyHostToDevice, st));
+      if ((rc = upload(d_ids + s0, cand_ids + s0, (size_t)(s1 - s0) * sizeof(int64_t), st)) != LSHX_OK) return rc;
     if (host_vectors && !cand_ids && s1 > s0)  // packed candidates: the rows of this chunk's queries
-      LSHX_CUDA(cudaMemcpyAsync(d_vecs + s0 * dim, vectors + s0 * dim, (size_t)(s1 - s0) * dim * sizeof(float),
-                                cudaMemcpyHostToDevice, st));
+      if ((rc = upload(d_vecs + s0 * dim, vectors + s0 * dim, (size_t)(s1 - s0) * dim * sizeof(float), st)) != LSHX_OK)
+        return rc;
     RerankArgs c = a;
     c.nq = c1 - c0;
     c.Q = d_q + c0 * dim;
@@ -1178,8 +1224,8 @@ static int index_add_common(lshx_index* ix, const uint8_t* signatures, const int
   if (!on_device) {
     if ((rc = ix->stage_sig.reserve(sig_bytes)) != LSHX_OK) return rc;
     if ((rc = ix->stage_ids.reserve(id_bytes)) != LSHX_OK) return rc;
-    LSHX_CUDA(cudaMemcpyAsync(ix->stage_sig.p, signatures, sig_bytes, cudaMemcpyHostToDevice, ix->stream));
-    LSHX_CUDA(cudaMemcpyAsync(ix->stage_ids.p, ids, id_bytes, cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = upload(ix->stage_sig.p, signatures, sig_bytes, ix->stream)) != LSHX_OK) return rc;
+    if ((rc = upload(ix->stage_ids.p, ids, id_bytes, ix->stream)) != LSHX_OK) return rc;
     d_sig = static_cast<const uint8_t*>(ix->stage_sig.p);
     d_ids = static_cast<const int64_t*>(ix->stage_ids.p);
   } else {
@@ -1303,7 +1349,7 @@ extern "C" int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64
   const uint8_t* d_sig = signatures;
   if (!on_device) {
     if ((rc = ix->q_sig.reserve(sig_bytes)) != LSHX_OK) return rc;
-    LSHX_CUDA(cudaMemcpyAsync(ix->q_sig.p, signatures, sig_bytes, cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = upload(ix->q_sig.p, signatures, sig_bytes, ix->stream)) != LSHX_OK) return rc;
     d_sig = static_cast<const uint8_t*>(ix->q_sig.p);
   } else {
     LSHX_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
@@ -1718,7 +1764,7 @@ extern "C" int lshx_index_rerank(lshx_index* ix, lshx_reranker* r, const float* 
   const float* d_q = Q;
   if (!q_on_device) {
     if ((rc = ix->rr_q.reserve((size_t)nq * dim * sizeof(float))) != LSHX_OK) return rc;
-    LSHX_CUDA(cudaMemcpyAsync(ix->rr_q.p, Q, (size_t)nq * dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+    if ((rc = upload(ix->rr_q.p, Q, (size_t)nq * dim * sizeof(float), ix->stream)) != LSHX_OK) return rc;
     d_q = static_cast<const float*>(ix->rr_q.p);
   }
   if ((rc = ix->rr_pos.reserve((size_t)nq * out_stride * 4)) != LSHX_OK) return rc;
