@@ -380,6 +380,16 @@ int lshx_index_get_buckets(lshx_index* ix, const int32_t* band_ids, const uint8_
  */
 int lshx_index_export(lshx_index* ix, uint8_t* keys_out, int64_t* ids_out, int64_t capacity, int64_t* n_out);
 /*
+ * lshx_index_query for nq HOST vectors in one pass over PCIe (LSHRS.query_batch): the
+ * vectors are uploaded once, hashed on the device with `h` (same kernel choice as
+ * lshx_hash_batch makes for a device batch), joined -- the signatures never visit
+ * the host -- and stay in the handle, so that lshx_index_rerank can be called with
+ * Q = NULL for this result.  zero_flag (optional, nq bytes, host) as in
+ * lshx_hash_batch.
+ */
+int lshx_index_query_host_vectors(lshx_index* ix, lshx_hasher* h, const float* X, int64_t nq,
+                                  uint8_t* zero_flag, int64_t* total_candidates, int64_t* max_candidates);
+/*
  * Host copies of the last query's lists: query i owns ids[offsets[i] ..
  * offsets[i] + counts[i]) and, when collisions != NULL, the matching collision
  * counts.  offsets has nq + 1 entries, ids / collisions total_candidates.  Any
@@ -398,7 +408,8 @@ int lshx_index_topk(lshx_index* ix, int top_k, int64_t* out_ids, int32_t* out_co
  * kernel of `r`, keep min(k, max(1, ceil(n_i * p))) (k <= 0: no k; p <= 0: no p)
  * and return IDS (not positions): out_ids[nq][out_stride] (-1 padded), out_score,
  * out_count, out_zero (zero-norm vectors met, as lshx_rerank_topk).  Q: the nq
- * query vectors, host (q_on_device = 0) or device.  Outputs are host pointers.
+ * query vectors, host (q_on_device = 0) or device, or NULL after
+ * lshx_index_query_host_vectors (the handle still holds them).  Outputs are host pointers.
  */
 int lshx_index_rerank(lshx_index* ix, lshx_reranker* r, const float* Q, int q_on_device,
                       const float* corpus_device, int64_t n_vectors, int k, double p, int out_stride,

@@ -67,6 +67,7 @@ EXPORTED_SYMBOLS = (
     "lshx_index_add_entries",
     "lshx_index_remove",
     "lshx_index_get_buckets",
+    "lshx_index_query_host_vectors",
     "lshx_index_query_vectors",
     "lshx_index_query_rerank_vectors",
     "lshx_index_debug_timeline",
@@ -171,6 +172,8 @@ def _declare(cdll: ctypes.CDLL) -> None:
     cdll.lshx_index_add_entries.argtypes = [vp, vp, vp, c_int64]
     cdll.lshx_index_get_buckets.restype = c_int
     cdll.lshx_index_get_buckets.argtypes = [vp, vp, vp, c_int64, vp, vp, c_int64, POINTER(c_int64)]
+    cdll.lshx_index_query_host_vectors.restype = c_int
+    cdll.lshx_index_query_host_vectors.argtypes = [vp, vp, vp, c_int64, vp, POINTER(c_int64), POINTER(c_int64)]
     cdll.lshx_index_query_vectors.restype = c_int
     cdll.lshx_index_query_vectors.argtypes = [vp, vp, vp, c_int, c_int, vp, vp, vp, vp]
     cdll.lshx_index_query_rerank_vectors.restype = c_int

@@ -472,10 +472,16 @@ class LSHRS:
             raise ValueError("top_p must be within the range (0, 1]")
         if top_p is not None and top_k is not None and top_k <= 0:
             raise ValueError("top_k must be greater than zero when provided")
-        packed, zero_flag = self._hasher.hash_batch_packed(arr, return_zero_flag=True)
-        if zero_flag.any():
-            raise ValueError(_ZERO_VECTOR_MSG)
         nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
+        # one pass over PCIe (vectors up once, hashed and joined on the device) when the batch takes the batch
+        # kernel anyway; 32 rows and fewer keep the FP32 latency kernel every other path uses for them
+        one_pass = device_index and nq > 32 and self._hasher._kernel == 0
+        if one_pass:
+            packed = None
+        else:
+            packed, zero_flag = self._hasher.hash_batch_packed(arr, return_zero_flag=True)
+            if zero_flag.any():
+                raise ValueError(_ZERO_VECTOR_MSG)
         if device_index:
             with self._dindex.lock:     # the result of query() lives in the handle until it is consumed
                 done, ordered_all = self._query_batch_on_device(arr, packed, top_k, top_p, corpus, as_arrays)
@@ -527,7 +533,14 @@ class LSHRS:
     def _query_batch_on_device(self, arr, packed, top_k, top_p, corpus, as_arrays):
         """The device-index branch of :meth:`query_batch`; ``(True, result)`` or ``(False, candidate lists)``."""
         nq = arr.shape[0]
-        _, maxc = self._dindex.query(packed)
+        queries = arr
+        if packed is None:
+            _, maxc, zero_flag = self._dindex.query_host_vectors(self._hasher, arr)
+            if zero_flag.any():
+                raise ValueError(_ZERO_VECTOR_MSG)
+            queries = None              # the handle holds the uploaded vectors for the rerank
+        else:
+            _, maxc = self._dindex.query(packed)
         if top_p is None and top_k is not None:
             ids, counts = self._dindex.topk(top_k)
             if as_arrays:
@@ -539,7 +552,7 @@ class LSHRS:
             if top_k is not None:
                 stride = min(stride, int(top_k))
             rer = _get_reranker(self._dim, self._hasher.device)
-            ids, scores, counts, zero = self._dindex.rerank(rer, arr, corpus, k=int(top_k or 0), p=float(top_p),
+            ids, scores, counts, zero = self._dindex.rerank(rer, queries, corpus, k=int(top_k or 0), p=float(top_p),
                                                             stride=stride)
             if zero[counts > 0].any():
                 raise ValueError("Cannot normalize zero vector")

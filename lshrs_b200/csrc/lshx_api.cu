@@ -1101,8 +1101,10 @@ struct lshx_index {
   DevBuf hist, stage_sig, stage_ids, gone;
   // state of the last query (device buffers, valid until the next query on this handle)
   DevBuf q_sig, lo, cnt, raw_count, raw_off, ws_off, meta, ws, out_ids, out_coll, uniq, topk_ids, topk_cnt;
-  DevBuf rr_pos, rr_score, rr_count, rr_zero, rr_ids, rr_q;
+  DevBuf rr_pos, rr_score, rr_count, rr_zero, rr_ids, rr_q, q_flag;
   int64_t last_nq = -1, last_total = 0, last_max = 0;
+  int64_t last_q_rows = -1;   // >= 0: rr_q holds the query VECTORS of the last result (lshx_index_query_host_vectors)
+  int last_q_dim = 0;
   // latency path (lshx_index_query_vectors): pinned + mapped result block the kernel stores into, and the
   // ticket counter by which the fused hash + query kernel finds its last CTA
   uint8_t* pin_res = nullptr;
@@ -1196,7 +1198,7 @@ extern "C" int lshx_index_destroy(lshx_index* ix) {
     for (DevBuf* b : {&ix->hist, &ix->stage_sig, &ix->stage_ids, &ix->gone, &ix->q_sig, &ix->lo, &ix->cnt,
                       &ix->raw_count, &ix->raw_off, &ix->ws_off, &ix->meta, &ix->ws, &ix->out_ids, &ix->out_coll,
                       &ix->uniq, &ix->topk_ids, &ix->topk_cnt, &ix->rr_pos, &ix->rr_score, &ix->rr_count,
-                      &ix->rr_zero, &ix->rr_ids, &ix->rr_q})
+                      &ix->rr_zero, &ix->rr_ids, &ix->rr_q, &ix->q_flag})
       b->release();
     if (ix->stream) cudaStreamDestroy(ix->stream);
     (void)cudaGetLastError();
@@ -1328,32 +1330,10 @@ static int index_make_sorted(lshx_index* ix, bool force_full = false) {
   return LSHX_OK;
 }
 
-extern "C" int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64_t nq, int on_device, void* stream,
-                                int64_t* total_candidates, int64_t* max_candidates) {
-  LSHX_REQUIRE(ix != nullptr, "null handle");
-  LSHX_REQUIRE(nq >= 0, "nq must be >= 0");
-  std::lock_guard<std::mutex> lk(ix->mu);
-  DeviceGuard g(ix->device);
-  ix->last_nq = -1;
-  if (total_candidates) *total_candidates = 0;
-  if (max_candidates) *max_candidates = 0;
-  if (nq == 0) {
-    ix->last_nq = 0;
-    ix->last_total = ix->last_max = 0;
-    return LSHX_OK;
-  }
-  LSHX_REQUIRE(signatures != nullptr, "null buffer");
-  int rc = index_make_sorted(ix);
-  if (rc != LSHX_OK) return rc;
-  const size_t sig_bytes = (size_t)nq * ix->nb * ix->bpb;
-  const uint8_t* d_sig = signatures;
-  if (!on_device) {
-    if ((rc = ix->q_sig.reserve(sig_bytes)) != LSHX_OK) return rc;
-    if ((rc = upload(ix->q_sig.p, signatures, sig_bytes, ix->stream)) != LSHX_OK) return rc;
-    d_sig = static_cast<const uint8_t*>(ix->q_sig.p);
-  } else {
-    LSHX_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
-  }
+// lookup + scan + join of nq signatures that are in device memory and ordered on ix->stream (caller holds ix->mu)
+static int index_query_core(lshx_index* ix, const uint8_t* d_sig, int64_t nq, int64_t* total_candidates,
+                            int64_t* max_candidates) {
+  int rc;
   if ((rc = ix->lo.reserve((size_t)nq * ix->nb * 2 * 8)) != LSHX_OK) return rc;    // two runs per band
   if ((rc = ix->cnt.reserve((size_t)nq * ix->nb * 2 * 4)) != LSHX_OK) return rc;
   if ((rc = ix->raw_count.reserve((size_t)nq * 4)) != LSHX_OK) return rc;
@@ -1390,6 +1370,77 @@ extern "C" int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64
   ix->last_max = maxc;
   if (total_candidates) *total_candidates = total;
   if (max_candidates) *max_candidates = maxc;
+  return LSHX_OK;
+}
+
+extern "C" int lshx_index_query(lshx_index* ix, const uint8_t* signatures, int64_t nq, int on_device, void* stream,
+                                int64_t* total_candidates, int64_t* max_candidates) {
+  LSHX_REQUIRE(ix != nullptr, "null handle");
+  LSHX_REQUIRE(nq >= 0, "nq must be >= 0");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  DeviceGuard g(ix->device);
+  ix->last_nq = -1;
+  ix->last_q_rows = -1;
+  if (total_candidates) *total_candidates = 0;
+  if (max_candidates) *max_candidates = 0;
+  if (nq == 0) {
+    ix->last_nq = 0;
+    ix->last_total = ix->last_max = 0;
+    return LSHX_OK;
+  }
+  LSHX_REQUIRE(signatures != nullptr, "null buffer");
+  int rc = index_make_sorted(ix);
+  if (rc != LSHX_OK) return rc;
+  const size_t sig_bytes = (size_t)nq * ix->nb * ix->bpb;
+  const uint8_t* d_sig = signatures;
+  if (!on_device) {
+    if ((rc = ix->q_sig.reserve(sig_bytes)) != LSHX_OK) return rc;
+    if ((rc = upload(ix->q_sig.p, signatures, sig_bytes, ix->stream)) != LSHX_OK) return rc;
+    d_sig = static_cast<const uint8_t*>(ix->q_sig.p);
+  } else {
+    LSHX_CUDA(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+  }
+  return index_query_core(ix, d_sig, nq, total_candidates, max_candidates);
+}
+
+// query_batch on HOST vectors in one pass over PCIe: upload the nq vectors once, hash them on the device, join --
+// the signatures never visit the host, and the vectors stay in the handle for lshx_index_rerank (Q = NULL).
+extern "C" int lshx_index_query_host_vectors(lshx_index* ix, lshx_hasher* h, const float* X, int64_t nq,
+                                             uint8_t* zero_flag, int64_t* total_candidates,
+                                             int64_t* max_candidates) {
+  LSHX_REQUIRE(ix != nullptr && h != nullptr, "null handle");
+  LSHX_REQUIRE(ix->device == h->device, "index and hasher live on different devices");
+  LSHX_REQUIRE(nq >= 0, "nq must be >= 0");
+  std::lock_guard<std::mutex> lk(ix->mu);
+  std::lock_guard<std::mutex> lk2(h->mu);
+  DeviceGuard g(ix->device);
+  const HashShape& s = h->s;
+  LSHX_REQUIRE(s.num_bands == ix->nb && s.sig_bytes == ix->nb * ix->bpb, "hasher and index shapes differ");
+  ix->last_nq = -1;
+  ix->last_q_rows = -1;
+  if (total_candidates) *total_candidates = 0;
+  if (max_candidates) *max_candidates = 0;
+  if (nq == 0) {
+    ix->last_nq = 0;
+    ix->last_total = ix->last_max = 0;
+    return LSHX_OK;
+  }
+  LSHX_REQUIRE(X != nullptr, "null buffer");
+  int rc = index_make_sorted(ix);
+  if (rc != LSHX_OK) return rc;
+  if ((rc = ix->rr_q.reserve((size_t)nq * s.dim * sizeof(float))) != LSHX_OK) return rc;
+  if ((rc = ix->q_sig.reserve((size_t)nq * s.sig_bytes)) != LSHX_OK) return rc;
+  if ((rc = ix->q_flag.reserve((size_t)nq)) != LSHX_OK) return rc;
+  if ((rc = upload(ix->rr_q.p, X, (size_t)nq * s.dim * sizeof(float), ix->stream)) != LSHX_OK) return rc;
+  rc = launch_hash(h, static_cast<const float*>(ix->rr_q.p), nq, static_cast<uint8_t*>(ix->q_sig.p),
+                   zero_flag ? static_cast<uint8_t*>(ix->q_flag.p) : nullptr, ix->stream);
+  if (rc != LSHX_OK) return rc;
+  if (zero_flag)
+    LSHX_CUDA(cudaMemcpyAsync(zero_flag, ix->q_flag.p, (size_t)nq, cudaMemcpyDeviceToHost, ix->stream));
+  rc = index_query_core(ix, static_cast<const uint8_t*>(ix->q_sig.p), nq, total_candidates, max_candidates);
+  if (rc != LSHX_OK) return rc;
+  ix->last_q_rows = nq;       // rr_q holds the queries of this result
+  ix->last_q_dim = s.dim;
   return LSHX_OK;
 }
 
@@ -1758,11 +1809,16 @@ extern "C" int lshx_index_rerank(lshx_index* ix, lshx_reranker* r, const float* 
   LSHX_REQUIRE(ix->last_nq >= 0, "no query result on this handle (lshx_index_query first)");
   const int64_t nq = ix->last_nq;
   if (nq == 0) return LSHX_OK;
-  LSHX_REQUIRE(Q != nullptr && corpus_device != nullptr && n_vectors > 0, "null buffer");
+  LSHX_REQUIRE(corpus_device != nullptr && n_vectors > 0, "null buffer");
   const int dim = r->dim;
   int rc;
   const float* d_q = Q;
-  if (!q_on_device) {
+  if (Q == nullptr) {   // the vectors lshx_index_query_host_vectors uploaded for this very result
+    LSHX_REQUIRE(ix->last_q_rows == nq && ix->last_q_dim == dim,
+                 "Q is NULL but the handle holds no query vectors for this result (lshx_index_query_host_vectors)");
+    d_q = static_cast<const float*>(ix->rr_q.p);
+  } else if (!q_on_device) {
+    ix->last_q_rows = -1;     // rr_q is about to hold these vectors instead
     if ((rc = ix->rr_q.reserve((size_t)nq * dim * sizeof(float))) != LSHX_OK) return rc;
     if ((rc = upload(ix->rr_q.p, Q, (size_t)nq * dim * sizeof(float), ix->stream)) != LSHX_OK) return rc;
     d_q = static_cast<const float*>(ix->rr_q.p);

@@ -184,6 +184,21 @@ class DeviceIndex:
         c = int(counts[0])
         return ids[:c], coll[:c]
 
+    def query_host_vectors(self, hasher, vectors: np.ndarray):
+        """:meth:`query` for host VECTORS in one pass over PCIe (``lshx_index_query_host_vectors``): uploaded once,
+        hashed on the device, joined; the vectors stay in the handle for :meth:`rerank` with ``queries=None``.
+        Returns ``(candidate slots, largest list bound, zero_flag uint8[nq])``."""
+        x = np.ascontiguousarray(vectors, dtype=np.float32).reshape(-1, hasher.dim)
+        nq = x.shape[0]
+        flag = np.zeros(nq, dtype=np.uint8)
+        total, maxc = ctypes.c_int64(0), ctypes.c_int64(0)
+        with self.lock:
+            _native.check(_native.lib().lshx_index_query_host_vectors(
+                self._handle, hasher._ensure_handle(), x.ctypes.data, nq, flag.ctypes.data, ctypes.byref(total),
+                ctypes.byref(maxc)))
+            self._nq, self._total = nq, int(total.value)
+        return self._total, int(maxc.value), flag
+
     def fetch(self, *, collisions: bool = False):
         """``(offsets int64[nq+1], counts int32[nq], ids int64[slots] [, collisions int32[slots]])`` of the last
         query: list i is ``ids[offsets[i] : offsets[i] + counts[i]]``, ordered by (-collisions, id)."""
@@ -208,7 +223,7 @@ class DeviceIndex:
         """Cosine rerank of the last query's lists against a CUDA corpus tensor (candidate id = row).
 
         Returns ``(ids int64[nq, stride] (-1 padded), scores float32[nq, stride], counts int32[nq], zero int32[nq])``."""
-        q = np.ascontiguousarray(queries, dtype=np.float32)
+        q = None if queries is None else np.ascontiguousarray(queries, dtype=np.float32)   # None: the handle has them
         nq = self._nq
         ids = np.empty((nq, stride), dtype=np.int64)
         scores = np.empty((nq, stride), dtype=np.float32)
@@ -218,7 +233,8 @@ class DeviceIndex:
             if corpus.dim() != 2 or corpus.shape[1] != reranker.dim or not corpus.is_contiguous():
                 raise ValueError(f"corpus must be a contiguous (n, {reranker.dim}) float32 CUDA tensor")
             _native.check(_native.lib().lshx_index_rerank(
-                self._handle, reranker._handle, q.ctypes.data, 0, int(corpus.data_ptr()), int(corpus.shape[0]),
+                self._handle, reranker._handle, None if q is None else q.ctypes.data, 0, int(corpus.data_ptr()),
+                int(corpus.shape[0]),
                 int(k), float(p), int(stride), ids.ctypes.data, scores.ctypes.data, counts.ctypes.data,
                 zero.ctypes.data))
         return ids, scores, counts, zero

@@ -439,6 +439,18 @@ def _index_methods():
         self.launches += 3
         return 0
 
+    def lshx_index_query_host_vectors(self, h, hh, X_ptr, nq, flag_ptr, total_ref, max_ref):
+        ix, hs = self._get(h), self._get(hh)
+        X = _arr(X_ptr, (nq, hs.dim), np.float32).copy()
+        sig = np.ascontiguousarray(
+            (oracle.hash_batch_packed(hs.projs, X) if nq <= 64 else oracle.hash_batch_vectorized(hs.projs, X))
+            .reshape(nq, ix.nb, ix.bpb))
+        if not _null(flag_ptr):
+            _arr(flag_ptr, (nq,), np.uint8)[...] = [1 if oracle.is_zero_vector(x) else 0 for x in X]
+        rc = self.lshx_index_query(h, sig.ctypes.data, nq, 0, None, total_ref, max_ref)
+        ix.queries = X
+        return rc
+
     def lshx_index_fetch(self, h, offs_ptr, counts_ptr, ids_ptr, coll_ptr):
         ix = self._get(h)
         lists, raw = ix.result
@@ -475,7 +487,7 @@ def _index_methods():
         dim = self._get(rh)["dim"]
         lists, _ = ix.result
         nq = len(lists)
-        Q = _arr(Q_ptr, (nq, dim), np.float32)
+        Q = ix.queries if _null(Q_ptr) else _arr(Q_ptr, (nq, dim), np.float32)
         V = _arr(V_ptr, (nvec, dim), np.float32)
         offs = np.concatenate([[0], np.cumsum([len(x) for x in lists])]).astype(np.int64)
         flat = np.array([i for order in lists for i, _ in order], dtype=np.int64)
