@@ -293,3 +293,63 @@ def test_single_queries_rerank_against_a_resident_corpus():
     res.set_corpus(None)
     with pytest.raises(RuntimeError, match="vector_fetch_fn"):
         res.get_above_p(X[1], p=0.5)
+
+
+def test_packed_index_matches_the_per_row_loop_for_random_schedules():
+    """Property test (CPU double): for random buffer sizes, pre-buffered ingests, batch lengths and an optional
+    invalid row, index() on the packed path leaves the same buffer, the same store and raises the same error as
+    the tuple path that walks the rows like the reference's loop (main.py:504-518)."""
+    import fake_lshx
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+
+    from lshrs_b200 import _native
+    from lshrs_b200.utils import similarity
+
+    X = _clustered(64, 16, seed=8)
+    probe_rows = None
+
+    @settings(max_examples=60, deadline=None)
+    @given(buffer_size=st.integers(1, 150), pre=st.integers(0, 12), n=st.integers(1, 40),
+           bad=st.one_of(st.none(), st.tuples(st.integers(0, 39), st.sampled_from(["zero", "negative"]))))
+    def run(buffer_size, pre, n, bad):
+        made: list = []
+        a, b = _pair(made, X, buffer_size=buffer_size)
+        ids = list(range(100, 100 + n))
+        batch = X[:n].copy()
+        expect = None
+        if bad is not None and bad[0] < n:
+            if bad[1] == "zero":
+                batch[bad[0]] = 0
+                expect = "zero vector"
+            else:
+                ids[bad[0]] = -1
+                expect = "non-negative"
+        for lsh in (a, b):
+            for i in range(pre):
+                lsh.ingest(500 + i, X[40 + i])
+            if expect:
+                with pytest.raises(ValueError, match=expect):
+                    lsh.index(ids, batch)
+            else:
+                lsh.index(ids, batch)
+        assert a._buffer == b._buffer
+        probe = [(band, bytes(sig)) for row in a._hasher.hash_batch_packed(X) for band, sig in enumerate(row)]
+        assert a._storage.get_buckets(probe) == b._storage.get_buckets(probe)
+        for lsh in (a, b):
+            lsh.flush()
+        assert a._storage.get_buckets(probe) == b._storage.get_buckets(probe)
+        for lsh in made:
+            lsh._hasher.close()
+            if lsh._dindex is not None:
+                lsh._dindex.close()
+
+    saved = _native._lib
+    fake_lshx.install()
+    try:
+        run()
+    finally:
+        for r in list(similarity._rerankers.values()):
+            r.close()
+        similarity._rerankers.clear()
+        _native._lib = saved
