@@ -266,21 +266,80 @@ class LSHRS:
         nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
         if self._store_on_device:
             return self._index_packed(indices, packed, zero_flag)
+        ids = self._ids_array(indices)
+        if ids is None:
+            return self._index_rows(indices, packed, zero_flag)      # odd index types: row by row, like the reference
+        # The reference's loop (main.py:504-518) flushes after the row at which the buffer reaches buffer_size and
+        # once at the end.  Same operations, same batches -- but built one flush segment at a time (one list
+        # comprehension, one lock round trip per segment instead of per row: the Python loop was 3x the store's time).
+        n = len(indices)
+        negative = ids < 0
+        invalid = negative | (zero_flag != 0)
+        stop = int(np.argmax(invalid)) if invalid.any() else n
         # every band key as an exact-length bytes object, created in C (void-dtype tolist)
+        keys = np.ascontiguousarray(packed[:stop]).reshape(stop, nb * bpb).view(f"V{bpb}").tolist()
+        id_list = ids[:stop].tolist()
+        buffer, lock, limit = self._buffer, self._buffer_lock, self._buffer_size
+        with lock:
+            pre = len(buffer)
+        per_flush = max(1, -(-limit // nb))              # rows between two flushes of the loop
+        first = max(1, -(-(limit - pre) // nb))          # rows until its first flush
+        mirrored = 0                                     # rows [0, mirrored) are already queued for the device mirror
+
+        def queue_mirror(upto: int) -> None:
+            nonlocal mirrored
+            if self._dindex is not None and upto > mirrored:
+                with lock:
+                    self._mirror_pending.append((packed[mirrored:upto], ids[mirrored:upto].copy()))
+                mirrored = upto
+
+        row, seg_end = 0, min(stop, first)
+        while row < stop:
+            ops = [(b, key, idx) for krow, idx in zip(keys[row:seg_end], id_list[row:seg_end])
+                   for b, key in enumerate(krow)]
+            with lock:
+                buffer.extend(ops)
+                due = len(buffer) >= limit
+            if due:
+                queue_mirror(seg_end)
+                self.flush()
+            row, seg_end = seg_end, min(stop, seg_end + per_flush)
+        queue_mirror(stop)
+        if stop < n:        # the rows before the invalid one stay buffered, as in the reference's loop
+            raise ValueError("index must be non-negative" if negative[stop] else _ZERO_VECTOR_MSG)
+        self.flush()
+
+    @staticmethod
+    def _ids_array(indices) -> Optional[np.ndarray]:
+        """``indices`` as an int64 array, or None when they are not plain integers (the caller then walks them)."""
+        try:
+            ids = np.asarray(indices)
+            if ids.dtype.kind not in "iu" or ids.ndim != 1:
+                return None
+            return ids.astype(np.int64, copy=False)
+        except (TypeError, ValueError, OverflowError):
+            return None
+
+    def _index_rows(self, indices: Sequence[int], packed: np.ndarray, zero_flag: np.ndarray) -> None:
+        """``index()`` row by row (index sequences that are not plain integers: ``int()`` is applied to each in
+        turn, so a bad one is met exactly where the reference's loop meets it)."""
+        nb, bpb = self._hasher.num_bands, self._hasher.bytes_per_band
         keys = np.ascontiguousarray(packed).reshape(len(indices), nb * bpb).view(f"V{bpb}").tolist()
         flags = zero_flag.tolist()
         band_ids = range(nb)
         buffer, lock, limit = self._buffer, self._buffer_lock, self._buffer_size
         mirrored = 0                # rows [0, mirrored) are already queued for the device mirror
+        store_packed = self._store_on_device
 
         def queue_mirror(upto: int) -> None:
             nonlocal mirrored
-            if self._dindex is not None and upto > mirrored:
+            if self._dindex is not None and not store_packed and upto > mirrored:
                 ids_arr = np.fromiter((int(i) for i in indices[mirrored:upto]), dtype=np.int64, count=upto - mirrored)
                 with lock:
                     self._mirror_pending.append((packed[mirrored:upto], ids_arr))
                 mirrored = upto
 
+        row = 0
         try:
             for row, idx in enumerate(indices):
                 idx = int(idx)
@@ -335,13 +394,9 @@ class LSHRS:
         flushes after the row at which the buffer reaches ``buffer_size`` and once at the end, so on an invalid
         row ``stop`` the rows since the last such flush point stay in the buffer (as tuples, the rare path)."""
         n, nb, bpb = len(indices), self._hasher.num_bands, self._hasher.bytes_per_band
-        try:
-            ids = np.asarray(indices)
-            if ids.dtype.kind not in "iu" or ids.shape != (n,):
-                raise TypeError
-            ids = ids.astype(np.int64, copy=False)
-        except (TypeError, ValueError, OverflowError):
-            ids = np.fromiter((int(i) for i in indices), dtype=np.int64, count=n)
+        ids = self._ids_array(indices)
+        if ids is None:
+            return self._index_rows(indices, packed, zero_flag)      # through batch_add, row by row
         negative = ids < 0
         invalid = negative | (zero_flag != 0)
         stop = int(np.argmax(invalid)) if invalid.any() else n

@@ -41,26 +41,32 @@ class BucketStorage(Protocol):
 
 
 class InMemoryStorage:
-    """Thread-safe dict of sets, one per ``(band_id, band bytes)`` -- the buckets a Redis key of
-    :func:`bucket_key` names (the string itself is only formatted on request: at hundreds of thousands of
-    operations per second the f-string per operation was most of this double's time)."""
+    """Thread-safe dict of sets per band, one set per band key -- the buckets a Redis key of :func:`bucket_key`
+    names (the string itself is only formatted on request: at hundreds of thousands of operations per second the
+    f-string per operation was most of this double's time, and so was a ``(band, key)`` tuple per lookup -- hence
+    one dict per band, keyed by the band bytes alone)."""
 
     def __init__(self, prefix: str = "lsh") -> None:
         self.prefix = prefix
-        self._buckets: dict[tuple[int, bytes], set[int]] = {}
+        self._bands: dict[int, dict[bytes, set[int]]] = {}
         self._lock = threading.Lock()
 
     def bucket_key(self, band_id: int, hash_val: bytes) -> str:
         return bucket_key(self.prefix, band_id, hash_val)
 
     def batch_add(self, operations: Iterable[BucketOperation]) -> None:
-        buckets = self._buckets
+        bands = self._bands
         with self._lock:
+            last_band, table = None, None
             for band_id, hash_val, index in operations:
-                key = (band_id, hash_val)
-                members = buckets.get(key)
+                if band_id != last_band:
+                    table = bands.get(band_id)
+                    if table is None:
+                        table = bands[band_id] = {}
+                    last_band = band_id
+                members = table.get(hash_val)
                 if members is None:
-                    buckets[key] = {index}
+                    table[hash_val] = {index}
                 else:
                     members.add(index)
 
@@ -69,23 +75,24 @@ class InMemoryStorage:
 
     def get_bucket(self, band_id: int, hash_val: bytes) -> set[int]:
         with self._lock:
-            return set(self._buckets.get((band_id, bytes(hash_val)), ()))
+            return set(self._bands.get(band_id, {}).get(bytes(hash_val), ()))
 
     def get_buckets(self, keys: Iterable[tuple[int, bytes]]) -> list[set[int]]:
         """Many buckets in one call (the batched query path asks for nq * num_bands at once)."""
-        buckets = self._buckets
+        bands, empty = self._bands, {}
         with self._lock:
-            return [set(buckets.get((b, h), ())) for b, h in keys]
+            return [set(bands.get(b, empty).get(h, ())) for b, h in keys]
 
     def remove_indices(self, indices: Iterable[int]) -> None:
         drop = {int(i) for i in indices}
         with self._lock:
-            for members in self._buckets.values():
-                members -= drop
+            for table in self._bands.values():
+                for members in table.values():
+                    members -= drop
 
     def clear(self) -> None:
         with self._lock:
-            self._buckets.clear()
+            self._bands.clear()
 
     def close(self) -> None:
         pass
@@ -93,17 +100,20 @@ class InMemoryStorage:
     def keys(self) -> list[str]:
         """The Redis-style key strings of the non-empty buckets."""
         with self._lock:
-            return [bucket_key(self.prefix, b, h) for (b, h), m in self._buckets.items() if m]
+            return [bucket_key(self.prefix, b, h) for b, table in self._bands.items() for h, m in table.items() if m]
 
     def __len__(self) -> int:
         with self._lock:
-            return sum(1 for m in self._buckets.values() if m)
+            return sum(1 for table in self._bands.values() for m in table.values() if m)
 
     def __getstate__(self) -> dict:
         with self._lock:
-            return {"prefix": self.prefix, "buckets": {k: set(v) for k, v in self._buckets.items()}}
+            return {"prefix": self.prefix,
+                    "buckets": {(b, h): set(m) for b, table in self._bands.items() for h, m in table.items()}}
 
     def __setstate__(self, state: dict) -> None:
         self.prefix = state["prefix"]
-        self._buckets = state["buckets"]
+        self._bands = {}
+        for (b, h), members in state["buckets"].items():
+            self._bands.setdefault(b, {})[h] = set(members)
         self._lock = threading.Lock()

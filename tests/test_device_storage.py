@@ -313,8 +313,21 @@ def test_packed_index_matches_the_per_row_loop_for_random_schedules():
     @given(buffer_size=st.integers(1, 150), pre=st.integers(0, 12), n=st.integers(1, 40),
            bad=st.one_of(st.none(), st.tuples(st.integers(0, 39), st.sampled_from(["zero", "negative"]))))
     def run(buffer_size, pre, n, bad):
+        class Recording(InMemoryStorage):
+            def __init__(self):
+                super().__init__()
+                self.batches = []
+
+            def batch_add(self, operations):
+                self.batches.append(list(operations))
+                super().batch_add(operations)
+
         made: list = []
         a, b = _pair(made, X, buffer_size=buffer_size)
+        a._storage = Recording()
+        # c: the literal row-by-row loop (LSHRS._index_rows), the yardstick for both batched paths
+        c = LSHRS(storage=Recording(), dim=16, num_perm=16, num_bands=8, rows_per_band=2, buffer_size=buffer_size)
+        made.append(c)
         ids = list(range(100, 100 + n))
         batch = X[:n].copy()
         expect = None
@@ -333,12 +346,21 @@ def test_packed_index_matches_the_per_row_loop_for_random_schedules():
                     lsh.index(ids, batch)
             else:
                 lsh.index(ids, batch)
-        assert a._buffer == b._buffer
+        for i in range(pre):
+            c.ingest(500 + i, X[40 + i])
+        packed, flag = c._hasher.hash_batch_packed(batch, return_zero_flag=True)
+        if expect:
+            with pytest.raises(ValueError, match=expect):
+                c._index_rows(ids, packed, flag)
+        else:
+            c._index_rows(ids, packed, flag)
+        assert a._buffer == b._buffer == c._buffer
+        assert a._storage.batches == c._storage.batches          # the same batch_add calls, batch for batch
         probe = [(band, bytes(sig)) for row in a._hasher.hash_batch_packed(X) for band, sig in enumerate(row)]
-        assert a._storage.get_buckets(probe) == b._storage.get_buckets(probe)
-        for lsh in (a, b):
+        assert a._storage.get_buckets(probe) == b._storage.get_buckets(probe) == c._storage.get_buckets(probe)
+        for lsh in (a, b, c):
             lsh.flush()
-        assert a._storage.get_buckets(probe) == b._storage.get_buckets(probe)
+        assert a._storage.get_buckets(probe) == b._storage.get_buckets(probe) == c._storage.get_buckets(probe)
         for lsh in made:
             lsh._hasher.close()
             if lsh._dindex is not None:

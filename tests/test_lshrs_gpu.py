@@ -225,7 +225,7 @@ def test_full_size_config_autoconfig_and_bucket_keys():
     from pathlib import Path
 
     manifest = json.loads((Path(__file__).parent / "golden" / "manifest.json").read_text())
-    by_key = {st.bucket_key(b, h): members for (b, h), members in st._buckets.items()}
+    by_key = {st.bucket_key(b, h): members for b, table in st._bands.items() for h, members in table.items()}
     assert sorted(by_key) == sorted(st.keys())
     for row, keys in zip((10, 11), manifest["bucket_keys_768"]):
         for key in keys:                      # the reference's own Redis key strings for these two vectors

@@ -265,7 +265,7 @@ def test_create_signatures_takes_the_postgres_feed():
             _chunks(pgcopy_stream(ids, X), 3000)), fetch_query="SELECT id, embedding FROM t", batch_size=128)
         b = LSHRS(dim=32, num_perm=16, num_bands=4, rows_per_band=4, storage=InMemoryStorage())
         b.index(ids, X)
-        assert a._storage._buckets == b._storage._buckets and len(a._storage) > 0
+        assert a._storage._bands == b._storage._bands and len(a._storage) > 0
         a._hasher.close()      # handles of the double must not reach the real library's destroy
         b._hasher.close()
     finally:
