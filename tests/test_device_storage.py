@@ -375,3 +375,22 @@ def test_packed_index_matches_the_per_row_loop_for_random_schedules():
             r.close()
         similarity._rerankers.clear()
         _native._lib = saved
+
+
+def test_single_queries_beyond_the_latency_path_fall_back_to_the_batched_join(lib):
+    """A query that matches more bucket entries than the one-launch path sorts in shared memory (4096) is reported
+    as -1 by lshx_index_query_vectors and answered by the batched join instead -- same results as the dict store."""
+    rng = np.random.default_rng(21)
+    base = rng.standard_normal((1, 16)).astype(np.float32)
+    X = np.concatenate([np.repeat(base, 700, axis=0) + 1e-4 * rng.standard_normal((700, 16)).astype(np.float32),
+                        _clustered(100, 16, seed=22)])
+    a, b = _pair(lib, X)
+    for lsh in (a, b):
+        lsh.index(list(range(800)), X)
+    ids, coll, counts, _ = b._dindex.query_vectors(b._hasher, X[:1], 16)
+    assert counts[0] == -1                                   # 700 near-duplicates x 8 bands = 5600 bucket entries
+    assert a.get_top_k(X[0], topk=20) == b.get_top_k(X[0], topk=20)
+    assert a.query(X[0], top_k=None) == b.query(X[0], top_k=None) and len(b.query(X[0], top_k=None)) >= 700
+    ra, rb = a.get_above_p(X[0], p=0.01), b.get_above_p(X[0], p=0.01)
+    assert [i for i, _ in ra] == [i for i, _ in rb]
+    assert a.get_top_k(X[750], topk=5) == b.get_top_k(X[750], topk=5)      # an ordinary query next to it
